@@ -1,0 +1,587 @@
+#!/usr/bin/env python
+"""Generate golden input/output vectors from the *reference itself*.
+
+Run in the build container, where the reference checkout is mounted read-only:
+
+    PYTHONPATH=/root/reference PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+It imports dmosopt's own modules (dda, indicators, MOEA, NSGA2, AGEMOEA, SMPSO,
+CMAES, hv, hv_box_decomposition, model + scikit-learn) and records seeded
+inputs together with the outputs the reference produces, as small ``.npz``
+files next to this script.  The reference cannot travel to the GPU box, the
+fixtures do; ``tests/test_oracle_golden.py`` pins the oracle to them and the
+``-m gpu`` tests pin the CUDA path to the same files.
+
+Nothing outside ``tests/golden/`` is written.
+"""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+from dmosopt import dda, indicators, MOEA, NSGA2, AGEMOEA, SMPSO, CMAES  # noqa: E402
+from dmosopt import hv as hv_mod  # noqa: E402
+from dmosopt import hv_box_decomposition as hvbd  # noqa: E402
+from dmosopt import model as model_mod  # noqa: E402
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {name}.npz  ({os.path.getsize(path)} bytes)")
+
+
+class ReplayRng:
+    """Generator stand-in whose .random(n) replays pre-drawn uniforms (for operator goldens)."""
+
+    def __init__(self, u):
+        self.u = np.asarray(u, dtype=np.float64)
+        self.k = 0
+
+    def random(self, n=None):
+        if n is None:
+            v = self.u.ravel()[self.k]
+            self.k += 1
+            return v
+        v = self.u.ravel()[self.k : self.k + n]
+        self.k += n
+        return v.copy()
+
+
+def zdt1(x):
+    f1 = x[:, 0]
+    g = 1.0 + 9.0 / (x.shape[1] - 1) * x[:, 1:].sum(axis=1)
+    return np.column_stack((f1, g * (1.0 - np.sqrt(f1 / g))))
+
+
+def dtlz2(x, M):
+    g = ((x[:, M - 1 :] - 0.5) ** 2).sum(axis=1)
+    f = np.ones((x.shape[0], M)) * (1.0 + g)[:, None]
+    for i in range(M):
+        for j in range(M - 1 - i):
+            f[:, i] *= np.cos(0.5 * np.pi * x[:, j])
+        if i > 0:
+            f[:, i] *= np.sin(0.5 * np.pi * x[:, M - 1 - i])
+    return f
+
+
+# ---------------------------------------------------------------------------
+def gen_dda(rng):
+    out = {}
+    # the reference's own known-answer example (tests/test_dda.py:162-171): expected [0 2 1 1 0 0]
+    Y1 = np.asarray(
+        [
+            [0.2031, 0.7894, 0.5678, 0.4940, 0.1343, 0.2031],
+            [0.4031, 0.8041, 0.4940, 0.4954, 0.4131, 0.4031],
+            [0.3946, 0.9640, 0.4947, 0.5494, 0.4113, 0.3946],
+        ]
+    ).T
+    out["ex_Y"] = Y1
+    out["ex_rank_ens"] = dda.dda_ens(Y1)
+    out["ex_rank_ns"] = dda.dda_non_dominated_sort(Y1)
+    out["ex_D"] = dda.dominance_degree_matrix(Y1)
+    k = 0
+    for n, M in [(1, 2), (2, 2), (7, 3), (50, 2), (200, 2), (200, 3), (333, 5), (600, 3), (400, 4)]:
+        Y = rng.random((n, M))
+        out[f"c{k}_Y"] = Y
+        out[f"c{k}_rank"] = dda.dda_ens(Y)
+        out[f"c{k}_rank_ns"] = dda.dda_non_dominated_sort(Y)
+        k += 1
+    # near-single-front (DTLZ2 sphere) and ZDT1-like data
+    x = rng.random((300, 12))
+    Y = dtlz2(x, 3) * (1 + 0.01 * rng.random((300, 1)))
+    out[f"c{k}_Y"] = Y
+    out[f"c{k}_rank"] = dda.dda_ens(Y)
+    out[f"c{k}_rank_ns"] = dda.dda_non_dominated_sort(Y)
+    k += 1
+    Y = zdt1(rng.random((250, 30)))
+    out[f"c{k}_Y"] = Y
+    out[f"c{k}_rank"] = dda.dda_ens(Y)
+    out[f"c{k}_rank_ns"] = dda.dda_non_dominated_sort(Y)
+    k += 1
+    # duplicates (identical vectors are mutually non-dominating) with objective 0 tie-free otherwise
+    Y = rng.random((60, 3))
+    Y[10] = Y[3]
+    Y[44] = Y[3]
+    out[f"c{k}_Y"] = Y
+    out[f"c{k}_rank"] = dda.dda_ens(Y)
+    out[f"c{k}_rank_ns"] = dda.dda_non_dominated_sort(Y)
+    k += 1
+    # integer grid: many ties in every objective -> canonical (dda_non_dominated_sort) is the contract
+    Y = rng.integers(0, 6, size=(150, 3)).astype(float)
+    out[f"c{k}_Y"] = Y
+    out[f"c{k}_rank"] = dda.dda_ens(Y)
+    out[f"c{k}_rank_ns"] = dda.dda_non_dominated_sort(Y)
+    k += 1
+    out["ncases"] = np.array(k)
+    # the objective-0 tie quirk
+    Yq = np.array([[0.5, 0.9], [0.5, 0.1]])
+    out["quirk_Y"] = Yq
+    out["quirk_rank_ens"] = dda.dda_ens(Yq)
+    out["quirk_rank_ns"] = dda.dda_non_dominated_sort(Yq)
+    save("dda", **out)
+
+
+def gen_distance(rng):
+    out = {}
+    k = 0
+    for n, M in [(1, 3), (2, 2), (3, 3), (17, 2), (100, 3), (257, 5), (500, 2), (64, 4)]:
+        Y = rng.random((n, M)) * rng.uniform(0.1, 10.0, size=(1, M))
+        out[f"c{k}_Y"] = Y
+        out[f"c{k}_crowd"] = indicators.crowding_distance_metric(Y)
+        out[f"c{k}_eucl"] = indicators.euclidean_distance_metric(Y)
+        k += 1
+    # a constant column (zero range -> 1.0)
+    Y = rng.random((40, 3))
+    Y[:, 1] = 0.25
+    out[f"c{k}_Y"] = Y
+    out[f"c{k}_crowd"] = indicators.crowding_distance_metric(Y)
+    out[f"c{k}_eucl"] = indicators.euclidean_distance_metric(Y)
+    k += 1
+    out["ncases"] = np.array(k)
+    save("distance", **out)
+
+
+def gen_sortmo(rng):
+    out = {}
+    k = 0
+    for n, d, M, pop, metric in [
+        (40, 5, 2, 20, None),
+        (40, 5, 2, 20, "crowding"),
+        (300, 8, 3, 150, "crowding"),
+        (300, 8, 3, 150, "euclidean"),
+        (300, 8, 3, 100, None),
+        (128, 4, 5, 64, "crowding"),
+    ]:
+        x = rng.random((n, d))
+        y = rng.random((n, M))
+        ym = None if metric is None else [metric]
+        xs, ys, rank, perm = MOEA.remove_worst(x, y, pop, y_distance_metrics=ym, return_perm=True)
+        perm_full, rank_full, _ = MOEA.orderMO(x, y, y_distance_metrics=ym)
+        out[f"c{k}_x"] = x
+        out[f"c{k}_y"] = y
+        out[f"c{k}_pop"] = np.array(pop)
+        out[f"c{k}_metric"] = np.array(metric if metric else "none")
+        out[f"c{k}_xs"] = xs
+        out[f"c{k}_ys"] = ys
+        out[f"c{k}_rank"] = rank
+        out[f"c{k}_perm"] = perm
+        out[f"c{k}_perm_full"] = perm_full
+        out[f"c{k}_rank_full"] = rank_full
+        k += 1
+    out["ncases"] = np.array(k)
+    save("sortmo", **out)
+
+
+def gen_variation(rng):
+    out = {}
+    k = 0
+    for d, rate, dim, dic in [(30, 1.0 / 30, 20.0, 1.0), (12, 1.0 / 12, 20.0, 1.0), (5, 0.5, 7.0, 3.0), (8, 0.25, 30.0, 15.0)]:
+        npar = 64
+        xlb = -rng.random(d) * 2.0
+        xub = 1.0 + rng.random(d) * 3.0
+        parents = xlb + rng.random((npar, d)) * (xub - xlb)
+        parents2 = xlb + rng.random((npar, d)) * (xub - xlb)
+        u_m = rng.random((npar, d))
+        u_c = rng.random((npar, d))
+        # a few exact edge draws
+        u_m[0, 0] = 0.0
+        u_c[0, 0] = 0.5
+        u_c[0, 1] = 0.0
+        di_m = np.asarray([dim] * d)
+        di_c = np.asarray([dic] * d)
+        if k == 3:  # per-dimension distribution indices (sa.py consumers)
+            di_m = rng.uniform(5.0, 40.0, size=d)
+            di_c = rng.uniform(0.5, 20.0, size=d)
+        mut = np.vstack([MOEA.mutation(ReplayRng(u_m[i]), parents[i], di_m, xlb, xub, mutation_rate=rate)[0] for i in range(npar)])
+        c1 = []
+        c2 = []
+        for i in range(npar):
+            a, b = MOEA.crossover_sbx(ReplayRng(u_c[i]), parents[i], parents2[i], di_c, xlb, xub)
+            c1.append(a[0])
+            c2.append(b[0])
+        out[f"c{k}_xlb"] = xlb
+        out[f"c{k}_xub"] = xub
+        out[f"c{k}_p1"] = parents
+        out[f"c{k}_p2"] = parents2
+        out[f"c{k}_um"] = u_m
+        out[f"c{k}_uc"] = u_c
+        out[f"c{k}_dim"] = di_m
+        out[f"c{k}_dic"] = di_c
+        out[f"c{k}_rate"] = np.array(rate)
+        out[f"c{k}_mut"] = mut
+        out[f"c{k}_c1"] = np.vstack(c1)
+        out[f"c{k}_c2"] = np.vstack(c2)
+        k += 1
+    out["ncases"] = np.array(k)
+    save("variation", **out)
+
+
+def gen_tournament(rng):
+    """Inclusion frequencies of the reference's tournament_selection (distributional golden)."""
+    out = {}
+    k = 0
+    for pop, pool, trials in [(12, 6, 40000), (30, 15, 20000), (9, 4, 40000)]:
+        rank = rng.integers(0, 4, size=pop)
+        crowd = rng.random(pop)
+        counts1 = np.zeros(pop)
+        counts2 = np.zeros(pop)
+        first1 = np.zeros(pop)
+        r = np.random.default_rng(1234 + k)
+        for _ in range(trials):
+            idx = MOEA.tournament_selection(r, pop, pool, rank)
+            counts1[idx] += 1
+            first1[idx[0]] += 1
+            idx = MOEA.tournament_selection(r, pop, pool, -crowd, rank)
+            counts2[idx] += 1
+        out[f"c{k}_rank"] = rank
+        out[f"c{k}_crowd"] = crowd
+        out[f"c{k}_pool"] = np.array(pool)
+        out[f"c{k}_trials"] = np.array(trials)
+        out[f"c{k}_freq_rank"] = counts1 / trials
+        out[f"c{k}_first_rank"] = first1 / trials
+        out[f"c{k}_freq_rank_crowd"] = counts2 / trials
+        out[f"c{k}_order_rank"] = np.lexsort((rank,))
+        out[f"c{k}_order_rank_crowd"] = np.lexsort((-crowd, rank))
+        k += 1
+    out["ncases"] = np.array(k)
+    save("tournament", **out)
+
+
+def gen_duplicates(rng):
+    out = {}
+    X = rng.random((80, 6))
+    X[7] = X[2]
+    X[50] = X[2]
+    X[51] = X[30]
+    out["X"] = X
+    out["dup"] = MOEA.get_duplicates(X)
+    save("duplicates", **out)
+
+
+def gen_gp(rng):
+    """GPR_Matern / GPR_RBF posterior: fitted state (from sklearn) + predictions."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, RBF, WhiteKernel
+
+    out = {}
+    k = 0
+    cases = [
+        # (N, d, M, P, kind, length_scale (None = fixed initial theta), anisotropic)
+        (64, 5, 2, 40, "matern", None, False),
+        (200, 12, 3, 96, "matern", None, False),
+        (150, 30, 2, 64, "matern", None, False),
+        (120, 6, 2, 50, "matern", "fit", False),
+        (100, 4, 2, 50, "matern", "fit", True),
+        (90, 5, 2, 40, "rbf", None, False),
+    ]
+    for N, d, M, P, kind, mode, aniso in cases:
+        xlb = -rng.random(d)
+        xub = 1.0 + rng.random(d)
+        xin = xlb + rng.random((N, d)) * (xub - xlb)
+        xn = (xin - xlb) / (xub - xlb)
+        yin = dtlz2(xn, M) if M > 2 else zdt1(xn)
+        xtest = xlb + rng.random((P, d)) * (xub - xlb)
+        # a few test points very close to training points (small posterior variance)
+        xtest[:4] = xin[:4] + 1e-4 * (xub - xlb) * rng.standard_normal((4, d))
+        xtest = np.clip(xtest, xlb, xub)
+        if mode == "fit":
+            # the reference's own class: SCE-UA optimised hyper-parameters (model.py:1182-1252)
+            mdl = model_mod.GPR_Matern(xin, yin, d, M, xlb, xub, optimizer="sceua", seed=7, anisotropic=aniso)
+            mean, var = mdl.predict(xtest)
+            smlist = mdl.smlist
+        else:
+            # fixed initial theta, sklearn optimizer=None, then the
+            # reference's own predict() body run on these regressors
+            if kind == "matern":
+                kern = ConstantKernel(1, (1e-4, 1e3)) * Matern(length_scale=0.5, length_scale_bounds=(1e-3, 100.0), nu=2.5) + WhiteKernel(
+                    noise_level=1e-6, noise_level_bounds=(1e-9, 1e-2)
+                )
+                cls = model_mod.GPR_Matern
+            else:
+                kern = ConstantKernel(1, (1e-4, 1e3)) * RBF(length_scale=0.5, length_scale_bounds=(1e-3, 100.0)) + WhiteKernel(
+                    noise_level=1e-5, noise_level_bounds=(1e-9, 1e-2)
+                )
+                cls = model_mod.GPR_RBF
+            smlist = []
+            for m in range(M):
+                g = GaussianProcessRegressor(kernel=kern, optimizer=None, normalize_y=True)
+                g.fit(xn, yin[:, m])
+                smlist.append(g)
+            mdl = cls.__new__(cls)
+            mdl.nInput, mdl.nOutput, mdl.xlb, mdl.xub, mdl.xrg = d, M, xlb, xub, xub - xlb
+            mdl.smlist = smlist
+            mdl.return_mean_variance = False
+            mean, var = mdl.predict(xtest)
+        out[f"c{k}_kind"] = np.array(kind)
+        out[f"c{k}_xlb"] = xlb
+        out[f"c{k}_xub"] = xub
+        out[f"c{k}_xin"] = xin
+        out[f"c{k}_yin"] = yin
+        out[f"c{k}_xtest"] = xtest
+        out[f"c{k}_mean"] = mean
+        out[f"c{k}_var"] = var
+        out[f"c{k}_Xtrain"] = np.asarray(smlist[0].X_train_)
+        out[f"c{k}_alpha"] = np.stack([np.ravel(g.alpha_) for g in smlist])
+        out[f"c{k}_L"] = np.stack([g.L_ for g in smlist])
+        out[f"c{k}_const"] = np.array([g.kernel_.k1.k1.constant_value for g in smlist])
+        out[f"c{k}_ls"] = np.stack([np.broadcast_to(np.asarray(g.kernel_.k1.k2.length_scale, float), (d,)) for g in smlist])
+        out[f"c{k}_noise"] = np.array([g.kernel_.k2.noise_level for g in smlist])
+        out[f"c{k}_ymean"] = np.array([np.ravel(g._y_train_mean)[0] for g in smlist])
+        out[f"c{k}_ystd"] = np.array([np.ravel(g._y_train_std)[0] for g in smlist])
+        k += 1
+    out["ncases"] = np.array(k)
+    save("gp", **out)
+
+
+def gen_hv(rng):
+    out = {}
+    # analytic known answers from the reference's tests (tests/test_hv_box_decomposition.py:29-67,100-108)
+    ka = [
+        (np.array([[1.0, 1.0]]), np.array([3.0, 3.0]), 4.0),
+        (np.array([[1.0, 3.0], [2.0, 2.0], [3.0, 1.0]]), np.array([4.0, 4.0]), 6.0),
+        (np.array([[1.0, 2.0], [2.0, 1.0]]), np.array([3.0, 3.0]), 3.0),
+        (np.array([[1.0, 1.0, 1.0]]), np.array([2.0, 2.0, 2.0]), 1.0),
+        (np.array([[2.0]]), np.array([5.0]), 3.0),
+    ]
+    for i, (P, r, v) in enumerate(ka):
+        out[f"ka{i}_P"] = P
+        out[f"ka{i}_ref"] = r
+        out[f"ka{i}_expected"] = np.array(v)
+        out[f"ka{i}_refimpl"] = np.array(hvbd.HyperVolumeBoxDecomposition(r).compute_hypervolume(P))
+    out["nka"] = np.array(len(ka))
+    k = 0
+    for n, d in [(1, 2), (5, 2), (60, 2), (300, 2), (30, 3), (120, 3), (40, 4), (60, 4), (25, 5), (12, 6)]:
+        P = 0.05 + rng.random((n, d))
+        ref = np.full(d, 1.0 + 0.1 * rng.random())
+        if k % 3 == 2:  # a non-dominated-ish cloud
+            P = dtlz2(rng.random((n, d + 4)), d) + 0.05
+            ref = np.full(d, 1.3)
+        out[f"c{k}_P"] = P
+        out[f"c{k}_ref"] = ref
+        out[f"c{k}_hv_box"] = np.array(hvbd.HyperVolumeBoxDecomposition(ref).compute_hypervolume(P))
+        out[f"c{k}_hv_adaptive"] = np.array(hv_mod.AdaptiveHyperVolume(ref).compute_hypervolume(P, algorithm="box"))
+        k += 1
+    # reference point cutting through the cloud (hv.py:159 mask)
+    P = rng.random((80, 3)) + 0.05
+    ref = np.array([0.8, 0.9, 0.7])
+    out[f"c{k}_P"] = P
+    out[f"c{k}_ref"] = ref
+    out[f"c{k}_hv_box"] = np.array(np.nan)  # box algorithm alone is not defined for points outside ref
+    out[f"c{k}_hv_adaptive"] = np.array(hv_mod.AdaptiveHyperVolume(ref).compute_hypervolume(P, algorithm="box"))
+    k += 1
+    out["ncases"] = np.array(k)
+    # the documented <=0 coordinate divergence
+    out["quirk_P"] = np.array([[-1.0, -1.0]])
+    out["quirk_ref"] = np.array([1.0, 1.0])
+    out["quirk_refimpl"] = np.array(hvbd.HyperVolumeBoxDecomposition(np.array([1.0, 1.0])).compute_hypervolume(np.array([[-1.0, -1.0]])))
+    save("hv", **out)
+
+
+def gen_ehvi(rng):
+    out = {}
+    k = 0
+    for nf, nc, d, kk in [(30, 50, 2, 10), (100, 200, 3, 40), (60, 120, 5, 25), (8, 20, 4, 5)]:
+        chosen = dtlz2(rng.random((nf, d + 5)), d) * (1.0 + 0.3 * rng.random((nf, 1)))
+        cand = dtlz2(rng.random((nc, d + 5)), d) * (1.0 + 0.3 * rng.random((nc, 1)))
+        ref = np.max(np.vstack((chosen, cand)), axis=0) + 1
+        variances = np.ones_like(cand) if k % 2 == 0 else 0.05 + rng.random(cand.shape)
+        ind = indicators.HypervolumeImprovement(ref_point=ref, nds=True)
+        sel = ind.do(chosen, cand, variances, kk)
+        # intermediate values straight from the reference's box code
+        rank = dda.dda_ens(chosen)
+        front = chosen[rank == 0]
+        hvo = hvbd.HyperVolumeBoxDecomposition(ref)
+        boxes = hvo._decompose_dominated_space(front)
+        ehvi = hvo._compute_batch_ehvi(boxes, cand, variances)
+        out[f"c{k}_chosen"] = chosen
+        out[f"c{k}_cand"] = cand
+        out[f"c{k}_var"] = variances
+        out[f"c{k}_ref"] = ref
+        out[f"c{k}_k"] = np.array(kk)
+        out[f"c{k}_sel"] = np.asarray(sel)
+        out[f"c{k}_ehvi"] = ehvi
+        out[f"c{k}_lower"] = np.array([b.lower for b in boxes])
+        out[f"c{k}_upper"] = np.array([b.upper for b in boxes])
+        k += 1
+    out["ncases"] = np.array(k)
+    save("ehvi", **out)
+
+
+def gen_nsga2(rng):
+    """Reference NSGA2 plugin: initialize_state + update_strategy on recorded offspring."""
+    out = {}
+    k = 0
+    # ZDT1's f1 = x0 ties exactly at clipped genes, which makes the reference's own result depend on
+    # numpy's unstable sorts (crowding argsort, dda_ens order); those cases are flagged ``ties`` and only
+    # pin the oracle on this machine.  The other cases add a small random linear term to DTLZ2 so that
+    # every objective is tie-free even at clipped genes.
+    for pop, d, M, metric, fname in [(40, 6, 2, "crowding", "dtlz2"), (100, 12, 3, None, "dtlz2"), (64, 30, 2, None, "zdt1"),
+                                     (64, 30, 2, "crowding", "dtlz2"), (50, 10, 3, "euclidean", "dtlz2")]:
+        bounds = np.column_stack((np.zeros(d), np.ones(d)))
+        W = rng.random((d, M))
+        f = (lambda x: zdt1(x)) if fname == "zdt1" else (lambda x, M=M, W=W: dtlz2(x, M) + 0.01 * (x @ W))
+        out[f"c{k}_ties"] = np.array(fname == "zdt1")
+        x0 = rng.random((pop + 17, d))
+        y0 = f(x0).astype(np.float32)  # MOASMO.optimize casts the initial objectives (MOASMO.py:64)
+        opt = NSGA2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=model_mod.Model(), distance_metric=metric)
+        r = np.random.default_rng(99 + k)
+        opt.initialize_strategy(x0, y0, bounds, r)
+        out[f"c{k}_x0"] = x0
+        out[f"c{k}_y0"] = y0
+        out[f"c{k}_metric"] = np.array(metric if metric else "none")
+        out[f"c{k}_init_px"] = opt.state.population_parm.copy()
+        out[f"c{k}_init_py"] = opt.state.population_obj.copy()
+        out[f"c{k}_init_rank"] = opt.state.rank.copy()
+        for g in range(3):
+            x_gen, st = opt.generate()
+            y_gen = f(x_gen)
+            opt.update(x_gen, y_gen, st)
+            out[f"c{k}_g{g}_xgen"] = x_gen
+            out[f"c{k}_g{g}_ygen"] = y_gen
+            out[f"c{k}_g{g}_cidx"] = st["crossover_indices"]
+            out[f"c{k}_g{g}_midx"] = st["mutation_indices"]
+            out[f"c{k}_g{g}_px"] = opt.state.population_parm.copy()
+            out[f"c{k}_g{g}_py"] = opt.state.population_obj.copy()
+            out[f"c{k}_g{g}_rank"] = opt.state.rank.copy()
+        # offspring-count distribution of the serial variation loop (NSGA2.py:142-178)
+        counts = []
+        ncross = []
+        for _ in range(300):
+            xg, st = opt.generate()
+            counts.append(xg.shape[0])
+            ncross.append(len(st["crossover_indices"]) // 2)
+        out[f"c{k}_count_hist"] = np.bincount(np.asarray(counts), minlength=pop + 2)
+        out[f"c{k}_ncross_mean"] = np.array(np.mean(ncross))
+        k += 1
+    out["ncases"] = np.array(k)
+    save("nsga2", **out)
+
+
+def gen_agemoea(rng):
+    out = {}
+    k = 0
+    for n, d, M, pop in [(60, 5, 2, 30), (200, 8, 3, 100), (150, 6, 3, 120), (120, 5, 4, 40)]:
+        x = rng.random((n, d))
+        y = dtlz2(x, M) * (1.0 + (0.0 if k == 2 else 0.4) * rng.random((n, 1)))
+        xs, ys, rank, cd = AGEMOEA.environmental_selection(np.random.default_rng(5), x, y, pop, d, M)
+        out[f"c{k}_x"] = x
+        out[f"c{k}_y"] = y
+        out[f"c{k}_pop"] = np.array(pop)
+        out[f"c{k}_xs"] = xs
+        out[f"c{k}_ys"] = ys
+        out[f"c{k}_rank"] = rank
+        out[f"c{k}_cd"] = cd
+        # survival score of the first front on its own
+        r = dda.dda_ens(y)
+        idxr = r.argsort()
+        ys_sorted = y[idxr]
+        front = np.argwhere(r[idxr] == 0).ravel()
+        ideal = np.min(ys_sorted[front], axis=0)
+        norm_, p_, cd_ = AGEMOEA.survival_score(ys_sorted, front, ideal)
+        out[f"c{k}_front_y"] = ys_sorted[front]
+        out[f"c{k}_ss_norm"] = np.asarray(norm_, dtype=float)
+        out[f"c{k}_ss_p"] = np.array(p_, dtype=float)
+        out[f"c{k}_ss_cd"] = cd_
+        k += 1
+    out["ncases"] = np.array(k)
+    save("agemoea", **out)
+
+
+def gen_smpso(rng):
+    out = {}
+
+    class FixedRng:
+        """Replays the scalar draws of velocity_vector (SMPSO.py:316-321, 332)."""
+
+        def __init__(self, vals, ints):
+            self.vals = list(vals)
+            self.ints = ints
+
+        def uniform(self, low=0.0, high=1.0, size=1):
+            v = self.vals.pop(0)
+            return np.array([low + (high - low) * v])
+
+        def integers(self, low=0, high=None, size=None):
+            return np.asarray(self.ints)
+
+    k = 0
+    for n, d, M in [(40, 6, 2), (100, 10, 3)]:
+        xlb = -rng.random(d)
+        xub = 1 + rng.random(d)
+        pos = (xlb + rng.random((n, d)) * (xub - xlb)).astype(np.float32)
+        vel = xlb + rng.random((n, d)) * (xub - xlb)
+        arch = (xlb + rng.random((n, d)) * (xub - xlb)).astype(np.float32)
+        y = rng.random((n, M))
+        crowd = indicators.crowding_distance_metric(y)
+        u5 = rng.random(5)
+        if k == 1:
+            u5[3] = 0.9
+            u5[4] = 0.95  # c1 + c2 > 4 -> constriction active
+        ints = rng.integers(0, n, size=2)
+        v = SMPSO.velocity_vector(FixedRng(u5, ints), pos, vel, arch, crowd, xlb, xub)
+        out[f"c{k}_xlb"] = xlb
+        out[f"c{k}_xub"] = xub
+        out[f"c{k}_pos"] = pos
+        out[f"c{k}_vel"] = vel
+        out[f"c{k}_arch"] = arch
+        out[f"c{k}_crowd"] = crowd
+        out[f"c{k}_u5"] = u5
+        out[f"c{k}_ints"] = ints
+        out[f"c{k}_vout"] = v
+        out[f"c{k}_newpos"] = SMPSO.update_position(pos, v, xlb, xub)
+        k += 1
+    out["ncases"] = np.array(k)
+    save("smpso", **out)
+
+
+def gen_cmaes(rng):
+    """CMAES._select masks (fronts + HV-improvement split) on recorded candidates."""
+    out = {}
+    k = 0
+    for pop, d, M in [(40, 6, 2), (60, 8, 3)]:
+        opt = CMAES.CMAES(popsize=pop, nInput=d, nOutput=M, model=model_mod.Model(), distance_metric=None)
+        n = pop + pop // 2
+        cx = rng.random((n, d))
+        cy = dtlz2(cx, M) * (1.0 + 0.5 * rng.random((n, 1)))
+        inds = np.arange(n)
+        chosen, not_chosen, rank = opt._select(cx, cy, None, inds)
+        out[f"c{k}_pop"] = np.array(pop)
+        out[f"c{k}_cx"] = cx
+        out[f"c{k}_cy"] = cy
+        out[f"c{k}_chosen"] = chosen
+        out[f"c{k}_not_chosen"] = not_chosen
+        out[f"c{k}_rank"] = rank
+        k += 1
+    out["ncases"] = np.array(k)
+    save("cmaes", **out)
+
+
+def main():
+    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes"]
+    gens = {
+        "dda": gen_dda,
+        "distance": gen_distance,
+        "sortmo": gen_sortmo,
+        "variation": gen_variation,
+        "tournament": gen_tournament,
+        "duplicates": gen_duplicates,
+        "gp": gen_gp,
+        "hv": gen_hv,
+        "ehvi": gen_ehvi,
+        "nsga2": gen_nsga2,
+        "agemoea": gen_agemoea,
+        "smpso": gen_smpso,
+        "cmaes": gen_cmaes,
+    }
+    for i, name in enumerate(which):
+        gens[name](np.random.default_rng(20260921 + i * 0 + sum(map(ord, name))))
+
+
+if __name__ == "__main__":
+    main()
