@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Headline benchmark: candidate-evaluations / second of one surrogate generation step.
+
+Workload (BASELINE.json metric): NSGA-II generation at pop = 65 536, dim = 30, 3 objectives, exact-GP surrogate with
+N_train = 4096 (fixed initial theta: ConstantKernel(1) * Matern(l=0.5, nu=2.5) + WhiteKernel(1e-6), BASELINE.md
+section 3), synthetic DTLZ2-shaped training targets.  One *step* = one generation of MOASMO.optimize's loop
+(dmosopt/MOASMO.py:92-122) including the per-generation termination hypervolume (hv_termination.py:1093-1106):
+
+    tournament -> SBX / polynomial mutation (P ~ pop offspring) -> GP posterior mean + variance of the offspring
+    -> non-dominated rank of the merged 2*pop set + stable truncation to pop -> exact hypervolume of the population
+
+  value : the step with the population resident in HBM (C-ABI calls on device buffers)
+  e2e   : the same step through the reference-facing plugin API (NSGA2.generate / GPR_Matern.evaluate /
+          NSGA2.update / Hypervolume.do) with HOST buffers, host<->device copies inside the timed region
+
+  python bench.py --gpus N --steps K --warmup W            # this build (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                     # CPU arm: the oracle port of the reference on host cores
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "candidate-evals/sec (GP+sort+HV) pop=65536 dim=30 obj=3"
+UNIT = "candidates/s"
+
+
+def workload(pop, d, M, N, seed=20260921 + 2):
+    rng = np.random.default_rng(seed)
+    xlb, xub = np.zeros(d), np.ones(d)
+    Xtr = rng.random((N, d))
+    g = ((Xtr[:, M - 1 :] - 0.5) ** 2).sum(axis=1)
+    Ytr = np.ones((N, M)) * (1.0 + g)[:, None]
+    for i in range(M):  # DTLZ2 (dmosopt/benchmarks/moo_benchmarks.py:59-94), vectorised
+        for j in range(M - 1 - i):
+            Ytr[:, i] *= np.cos(0.5 * np.pi * Xtr[:, j])
+        if i > 0:
+            Ytr[:, i] *= np.sin(0.5 * np.pi * Xtr[:, M - 1 - i])
+    X0 = rng.random((pop, d))
+    return dict(rng=rng, xlb=xlb, xub=xub, Xtr=Xtr, Ytr=Ytr, X0=X0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = os.path.join(ROOT, "gpurun_out", f"clocks_bench_{os.getpid()}.csv")
+
+    def start(self):
+        try:
+            os.makedirs(os.path.dirname(self.path), exist_ok=True)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_generation_sample(w, pop_s, N, M, d, threads=None):
+    """The reference path restated on the CPU (oracle/, kind = "port"), one generation at a bounded population.
+
+    Returns seconds for: GP predict (mean+var) of pop_s offspring against the FULL N_train model, rank of the merged
+    2*pop_s set + truncation, exact hypervolume of the survivors.  Variation is excluded (negligible, and its serial
+    reference loop cannot run beyond pop ~ 2150).
+    """
+    from oracle import dda, gp, hv, moea
+
+    st = w["gp_state"]
+    rng = np.random.default_rng(1)
+    x_par = rng.random((pop_s, d))
+    y_par = gp.predict(st, x_par)[0]
+    x_gen = np.clip(x_par + 0.05 * rng.standard_normal((pop_s, d)), 0, 1)
+    t0 = time.perf_counter()
+    y_gen, _ = gp.predict(st, x_gen)
+    t1 = time.perf_counter()
+    X = np.vstack((x_gen, x_par))
+    Y = np.vstack((y_gen, y_par))
+    xs, ys, rank, perm = moea.remove_worst(X, Y, pop_s, None, rank_fn=dda.rank_canonical)
+    t2 = time.perf_counter()
+    ref = Y.max(axis=0) + 0.1
+    hv.hypervolume(ys, ref)
+    t3 = time.perf_counter()
+    return {"gp": t1 - t0, "sort": t2 - t1, "hv": t3 - t2, "total": t3 - t0}
+
+
+def run_reference(args):
+    """--impl reference: the CPU arm.  The reference is pure Python and cannot travel to the GPU box, so this is the
+    oracle port (bit-pinned to the reference by tests/test_oracle_golden.py) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gp
+
+    pop, d, M, N = args.pop, args.dim, args.obj, args.ntrain
+    w = workload(pop, d, M, N)
+    w["gp_state"] = gp.fit_fixed(w["Xtr"], w["Ytr"], w["xlb"], w["xub"], 1.0, 0.5, 1e-6)
+    pop_s = args.cpu_sample
+    cores = os.cpu_count()
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_generation_sample(w, pop_s, N, M, d)
+    ts = [cpu_generation_sample(w, pop_s, N, M, d) for _ in range(max(1, min(args.steps, 5)))]
+    tot = float(np.mean([t["total"] for t in ts]))
+    val = pop_s / tot
+    sample = f"one generation at pop={pop_s} (of {pop}) against the full N_train={N} model: GP mean+var, rank of 2*{pop_s} + truncate, exact HV"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": 1,
+        "ms_per_step": tot * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"NSGA2 surrogate generation pop={pop} dim={d} obj={M} N_train={N} (bounded sample pop={pop_s})"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "breakdown_s": {k: float(np.mean([t[k] for t in ts])) for k in ("gp", "sort", "hv")}},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ResidentStep:
+    """One NSGA-II surrogate generation with the population resident in HBM (C-ABI on device buffers)."""
+
+    def __init__(self, L, gp_handle, pop, d, M, xlb, xub, x0, y0, rank0, ref, seed, world=1, rank=0, dist=None, torch=None):
+        self.L, self.gp, self.pop, self.d, self.M = L, gp_handle, pop, d, M
+        self.world, self.rank_id, self.dist, self.torch = world, rank, dist, torch
+        self.cap = pop + 1
+        DA = L.DeviceArray
+        self.pop_x = DA((pop, d)).upload(x0)
+        self.pop_y = DA((pop, M)).upload(y0)
+        self.rank = DA((pop,), np.int32).upload(rank0.astype(np.int32))
+        self.pool = DA((pop // 2,), np.int64)
+        self.Xs = DA((self.cap + pop, d))
+        self.Ys = DA((self.cap + pop, M))
+        self.kind = DA((self.cap,), np.int32)
+        self.perm = DA((pop,), np.int64)
+        self.var = DA((self.cap, M))
+        self.xlb, self.xub = DA((d,)).upload(xlb), DA((d,)).upload(xub)
+        self.dic, self.dim = DA((d,)).upload(np.full(d, 1.0)), DA((d,)).upload(np.full(d, 20.0))
+        self.ref = np.asarray(ref, dtype=np.float64)
+        self.seed, self.stream = seed, 0
+        self.nch = np.zeros(1, dtype=np.int64)
+        self.hv = 0.0
+        if world > 1:
+            per = -(-self.cap // world)
+            self.per = per
+            self.t_local = torch.empty((per, 2 * M), dtype=torch.float64, device="cuda")
+            self.t_all = torch.empty((world * per, 2 * M), dtype=torch.float64, device="cuda")
+            self.t_mean = torch.empty((per, M), dtype=torch.float64, device="cuda")
+            self.t_var = torch.empty((per, M), dtype=torch.float64, device="cuda")
+
+    def step(self):
+        L, lib, ctx = self.L, self.L.load_library(), self.L.context()
+        pop, d, M = self.pop, self.d, self.M
+        chk = L._check
+        self.stream += 1
+        chk(lib.dmo_tournament(ctx, self.rank.ptr, None, pop, pop // 2, self.seed, self.stream, self.pool.ptr, None), "tournament")
+        self.stream += 1
+        chk(lib.dmo_nsga2_generate(ctx, self.pop_x.ptr, pop, d, self.pool.ptr, pop // 2, pop, 0.9, 0.1, 1.0 / d, self.dic.ptr, self.dim.ptr,
+                                   self.xlb.ptr, self.xub.ptr, self.seed, self.stream, self.Xs.ptr, self.kind.ptr, self.nch.ctypes.data, None), "generate")
+        P = int(self.nch[0])
+        if self.world == 1:
+            chk(lib.dmo_gp_predict(ctx, self.gp._h, self.Xs.ptr, P, self.Ys.ptr, self.var.ptr, self.precision), "gp_predict")
+        else:
+            torch = self.torch
+            per = self.per
+            lo = min(self.rank_id * per, P)
+            hi = min(lo + per, P)
+            if hi > lo:
+                chk(lib.dmo_gp_predict(ctx, self.gp._h, self.Xs.offset(lo * d), hi - lo, self.t_mean.data_ptr(), self.t_var.data_ptr(), self.precision), "gp_predict")
+            self.t_local[:, :M] = self.t_mean
+            self.t_local[:, M:] = self.t_var
+            self.dist.all_gather_into_tensor(self.t_all, self.t_local)  # the one exchange step (NCCL over NVLink)
+            torch.cuda.synchronize()
+            mean_all = self.t_all[:P, :M].contiguous()
+            L.memcpy(self.Ys.ptr, mean_all.data_ptr(), P * M * 8)
+        # stack parents under the children (NSGA2.py:205-206), rank + stable truncation, float32 state rounding
+        L.memcpy(self.Xs.offset(P * d), self.pop_x.ptr, pop * d * 8)
+        L.memcpy(self.Ys.offset(P * M), self.pop_y.ptr, pop * M * 8)
+        chk(lib.dmo_remove_worst(ctx, self.Xs.ptr, self.Ys.ptr, P + pop, d, M, L.METRIC_NONE, None, 0, pop, self.pop_x.ptr, self.pop_y.ptr,
+                                 self.rank.ptr, self.perm.ptr), "remove_worst")
+        L.round_f32(self.pop_y.ptr, pop * M)
+        import ctypes
+
+        out = ctypes.c_double(0.0)
+        chk(lib.dmo_hypervolume(ctx, self.pop_y.ptr, pop, M, self.ref.ctypes.data, ctypes.byref(out)), "hypervolume")
+        self.hv = out.value
+        return P
+
+
+def run_ours(args):
+    import dmosopt_b200 as b2
+    from dmosopt_b200 import _lib as L
+    from dmosopt_b200.indicators import Hypervolume
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L.context(local_rank)
+    pop, d, M, N = args.pop, args.dim, args.obj, args.ntrain
+    prec = L.GP_TENSOR if args.precision == "tensor" else L.GP_FP64
+    w = workload(pop, d, M, N)
+    t0 = time.time()
+    sm = b2.GPR_Matern(w["Xtr"], w["Ytr"], d, M, w["xlb"], w["xub"], optimizer=None, precision=args.precision)
+    t_fit = time.time() - t0
+    mdl = b2.Model(objective=sm)
+    y0 = sm.evaluate(w["X0"]).astype(np.float32)
+    ref = y0.max(axis=0).astype(np.float64) + 0.1 * (y0.max(axis=0) - y0.min(axis=0))
+    peaks, peak_kind = load_peaks()
+
+    def barrier():
+        L.synchronize()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ e2e: plugin API, host buffers
+    from dmosopt_b200.parallel import ShardedSurrogate
+
+    sm_e2e = ShardedSurrogate(sm, device=torch.device("cuda", local_rank)) if world > 1 else sm
+    opt = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=mdl, distance_metric=None)
+    opt.initialize_strategy(w["X0"], y0, np.column_stack((w["xlb"], w["xub"])), np.random.default_rng(args.seed))
+    hv_ind = Hypervolume(ref_point=ref)
+
+    def plugin_step():
+        x_gen, st = opt.generate()  # MOASMO.py:105
+        y_gen = sm_e2e.evaluate(x_gen)  # MOASMO.py:114
+        opt.update(x_gen, y_gen, st)  # MOASMO.py:116
+        _, py = opt.population_objectives  # termination criterion reads the population ... (MOASMO.py:93-97)
+        return hv_ind.do(py.astype(np.float64)), x_gen.shape[0]  # ... and computes its hypervolume
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(args.warmup, 3) if args.e2e_warmup is None else args.e2e_warmup):
+        plugin_step()
+    barrier()
+    h0, d0 = L.transfer_bytes()
+    n_e2e = 0
+    t0 = time.perf_counter()
+    L.timer_begin()
+    for _ in range(e2e_steps):
+        _, P = plugin_step()
+        n_e2e += P
+    ms_e2e_dev = L.timer_end()
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    h1, d1 = L.transfer_bytes()
+    e2e_val = n_e2e / t_e2e
+
+    # ------------------------------------------------------------------ value: resident step
+    rank0 = opt.state.rank.copy()
+    rs = ResidentStep(L, sm._gp, pop, d, M, w["xlb"], w["xub"], opt.state.population_parm, opt.state.population_obj.astype(np.float64), rank0, ref,
+                      args.seed, world, rank, dist, torch)
+    rs.precision = prec
+    for _ in range(args.warmup):
+        rs.step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    L.profile_enable(True)
+    launches0 = L.launch_count()
+    n_val = 0
+    t0 = time.perf_counter()
+    L.timer_begin()
+    for _ in range(args.steps):
+        n_val += rs.step()
+    ms_dev = L.timer_end()
+    barrier()
+    t_val = max_over_ranks(max(time.perf_counter() - t0, ms_dev * 1e-3))
+    launches = L.launch_count() - launches0
+    prof = L.profile_report()
+    L.profile_enable(False)
+    clk = clocks.stop() if rank == 0 else {}
+    value = n_val / t_val
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel (GP variance)
+    var_ms, var_cnt = prof.get("gp_var", (0.0, 0))
+    P_local = (n_val / args.steps) / world
+    flops_per_launch = 2.0 * N * N * M * P_local  # GEMM form 2 N^2 M per candidate
+    roof = None
+    if var_cnt:
+        avg_s = var_ms * 1e-3 / var_cnt
+        ach = flops_per_launch / avg_s / 1e12
+        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        roof = {"bound": "tensor", "kernel": "gp_var (V = L^-1 K_*^T, column sums of V^2)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "peak_kind": f"bf16 dense, sustained, {peak_kind}", "avg_launch_ms": avg_s * 1e3,
+                "flops_per_launch": flops_per_launch, "arithmetic": "float64 CUDA cores" if prec == L.GP_FP64 else "tcgen05 split-fp16"}
+    shares = {k: v[0] / (ms_dev if ms_dev > 0 else 1.0) for k, v in prof.items()}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ CPU baseline beside it (rank 0, bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import gp as ogp
+
+        w["gp_state"] = ogp.fit_fixed(w["Xtr"], w["Ytr"], w["xlb"], w["xub"], 1.0, 0.5, 1e-6)
+        cs = cpu_generation_sample(w, args.cpu_sample, N, M, d)
+        cpu = {"value": args.cpu_sample / cs["total"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"one generation at pop={args.cpu_sample} (of {pop}) against the full N_train={N} model; oracle/ NumPy+BLAS port of the reference path",
+               "breakdown_s": {k: cs[k] for k in ("gp", "sort", "hv")}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_val * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"NSGA2 surrogate generation pop={pop} dim={d} obj={M} N_train={N} GPR_Matern fixed theta (DTLZ2-shaped targets)",
+                   "parallelism": f"candidates sharded over {world} GPU(s), one all-gather of predicted objectives" if world > 1 else "single GPU",
+                   "gp_precision": args.precision, "l2": "inputs larger than L2 (L^-1: %.0f MB float64, streamed every step)" % (M * N * N * 8 / 1e6),
+                   "surrogate_fit_s": t_fit},
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": (h1 - h0) / e2e_steps, "d2h_bytes_per_step": (d1 - d0) / e2e_steps,
+                "steps": e2e_steps, "ms_per_step": t_e2e * 1e3 / e2e_steps, "device_ms_per_step": ms_e2e_dev / e2e_steps},
+        "gpu_launches": int(launches), "clocks": clk, "kernel_share_of_step": shares, "hypervolume": rs.hv,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pop", type=int, default=65536)
+    ap.add_argument("--dim", type=int, default=30)
+    ap.add_argument("--obj", type=int, default=3)
+    ap.add_argument("--ntrain", type=int, default=4096)
+    ap.add_argument("--precision", default=os.environ.get("DMOSOPT_B200_GP", "fp64"), choices=["fp64", "tensor"])
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--cpu-sample", type=int, default=768)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-warmup", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

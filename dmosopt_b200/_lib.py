@@ -1,0 +1,492 @@
+"""ctypes binding of libdmosopt_b200.so (include/dmosopt_b200.h).
+
+Thin layer: argument marshalling and error translation only.  Every function
+takes/returns NumPy arrays (host) -- or, for inputs, anything exposing a CUDA
+device pointer through ``data_ptr()`` (torch tensors) when the caller keeps
+data resident.  There is deliberately NO CPU fallback: if the CUDA library is
+missing or no GPU is present the import of the library / creation of the
+context raises.
+"""
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdmosopt_b200.so")
+
+METRIC_NONE, METRIC_CROWDING, METRIC_EUCLIDEAN = 0, 1, 2
+KERNEL_MATERN52, KERNEL_RBF = 0, 1
+GP_FP64, GP_TENSOR = 0, 1
+
+_c_i64 = ctypes.c_int64
+_c_u64 = ctypes.c_uint64
+_c_int = ctypes.c_int
+_c_dbl = ctypes.c_double
+_vp = ctypes.c_void_p
+
+# exported symbols -> (restype, argtypes); checked against the header by tests/test_abi.py
+_SIGNATURES = {
+    "dmo_version": (_c_int, []),
+    "dmo_create": (_c_int, [_c_int, ctypes.POINTER(_vp)]),
+    "dmo_destroy": (_c_int, [_vp]),
+    "dmo_last_error": (ctypes.c_char_p, [_vp]),
+    "dmo_synchronize": (_c_int, [_vp]),
+    "dmo_stream": (_vp, [_vp]),
+    "dmo_launch_count": (_c_i64, [_vp]),
+    "dmo_sm_count": (_c_int, [_vp]),
+    "dmo_timer_begin": (_c_int, [_vp]),
+    "dmo_timer_end": (_c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "dmo_host_alloc": (_c_int, [ctypes.POINTER(_vp), _c_u64]),
+    "dmo_host_free": (_c_int, [_vp]),
+    "dmo_device_alloc": (_c_int, [_vp, ctypes.POINTER(_vp), _c_u64]),
+    "dmo_device_free": (_c_int, [_vp, _vp]),
+    "dmo_memcpy": (_c_int, [_vp, _vp, _vp, _c_u64]),
+    "dmo_flush_l2": (_c_int, [_vp]),
+    "dmo_transfer_bytes": (_c_int, [_vp, ctypes.POINTER(_c_u64), ctypes.POINTER(_c_u64)]),
+    "dmo_profile_enable": (_c_int, [_vp, _c_int]),
+    "dmo_profile_report": (_c_int, [_vp, ctypes.c_char_p, _c_u64]),
+    "dmo_round_f32": (_c_int, [_vp, _vp, _c_i64]),
+    "dmo_rank_nd": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp]),
+    "dmo_crowding_distance": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp]),
+    "dmo_euclidean_distance": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp]),
+    "dmo_order_mo": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp]),
+    "dmo_remove_worst": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp, _c_int, _c_i64, _vp, _vp, _vp, _vp]),
+    "dmo_tournament": (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_u64, _c_u64, _vp, _vp]),
+    "dmo_mutation_u": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _vp]),
+    "dmo_sbx_u": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _vp, _vp]),
+    "dmo_nsga2_generate": (
+        _c_int,
+        [_vp, _vp, _c_i64, _c_int, _vp, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _vp, _vp, _c_u64, _c_u64, _vp, _vp, _vp, _vp],
+    ),
+    "dmo_gp_create": (_c_int, [_vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "dmo_gp_destroy": (_c_int, [_vp, _vp]),
+    "dmo_gp_predict": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _c_int]),
+    "dmo_hypervolume": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp, ctypes.POINTER(_c_dbl)]),
+    "dmo_ehvi_select": (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp, _c_int, _c_i64, _vp, _vp]),
+    "dmo_get_duplicates": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_dbl, _vp]),
+}
+
+_lib = None
+_ctx = None
+_ctx_device = None
+_lock = threading.Lock()
+
+
+class DmoError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """Load the shared library and declare every prototype.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise DmoError(
+            f"dmosopt_b200: CUDA library {path} not found. Build it with `python -m dmosopt_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def default_device():
+    for k in ("DMOSOPT_B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(k)
+        if v is not None and v.strip() != "":
+            return int(v)
+    return 0
+
+
+def context(device=None):
+    """The process-wide context (one per process == one per GPU)."""
+    global _ctx, _ctx_device
+    with _lock:
+        if _ctx is not None and (device is None or device == _ctx_device):
+            return _ctx
+        lib = load_library()
+        dev = default_device() if device is None else int(device)
+        h = _vp()
+        st = lib.dmo_create(dev, ctypes.byref(h))
+        if st != 0 or not h.value:
+            raise DmoError(f"dmosopt_b200: dmo_create(device={dev}) failed with status {st}: no usable CUDA device (B200 required)")
+        if _ctx is not None:
+            lib.dmo_destroy(_ctx)
+        _ctx, _ctx_device = h, dev
+        return _ctx
+
+
+def _check(st, what):
+    if st != 0:
+        msg = _lib.dmo_last_error(_ctx)
+        raise DmoError(f"{what} failed (status {st}): {msg.decode() if msg else ''}")
+
+
+def _ptr(a):
+    """Raw pointer of a NumPy array, a torch CUDA tensor (data_ptr) or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    if isinstance(a, int):
+        return a
+    raise TypeError(f"cannot pass {type(a)} to the CUDA library")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------- context utilities
+def synchronize():
+    _check(load_library().dmo_synchronize(context()), "dmo_synchronize")
+
+
+def launch_count():
+    return int(load_library().dmo_launch_count(context()))
+
+
+def sm_count():
+    return int(load_library().dmo_sm_count(context()))
+
+
+def timer_begin():
+    _check(load_library().dmo_timer_begin(context()), "dmo_timer_begin")
+
+
+def timer_end():
+    ms = ctypes.c_float()
+    _check(load_library().dmo_timer_end(context(), ctypes.byref(ms)), "dmo_timer_end")
+    return float(ms.value)
+
+
+def flush_l2():
+    _check(load_library().dmo_flush_l2(context()), "dmo_flush_l2")
+
+
+def transfer_bytes():
+    a, b = _c_u64(0), _c_u64(0)
+    _check(load_library().dmo_transfer_bytes(context(), ctypes.byref(a), ctypes.byref(b)), "dmo_transfer_bytes")
+    return int(a.value), int(b.value)
+
+
+def profile_enable(on=True):
+    _check(load_library().dmo_profile_enable(context(), 1 if on else 0), "dmo_profile_enable")
+
+
+def profile_report():
+    """{kernel name: (total ms, launches)} recorded since profile_enable(True)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    _check(load_library().dmo_profile_report(context(), buf, len(buf)), "dmo_profile_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, cnt = line.rsplit(" ", 2)
+        out[name] = (float(ms), int(cnt))
+    return out
+
+
+def round_f32(dev_ptr, n):
+    _check(load_library().dmo_round_f32(context(), _ptr(dev_ptr), int(n)), "dmo_round_f32")
+
+
+class DeviceArray:
+    """A typed device buffer owned by the library context (for callers that keep populations resident)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(np.atleast_1d(shape).tolist()) if not isinstance(shape, tuple) else shape
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = _vp()
+        _check(load_library().dmo_device_alloc(context(), ctypes.byref(p), max(self.nbytes, 1)), "dmo_device_alloc")
+        self.ptr = p.value
+
+    def data_ptr(self):
+        return self.ptr
+
+    def offset(self, nelem):
+        """Raw pointer ``nelem`` elements into the buffer."""
+        return self.ptr + int(nelem) * self.dtype.itemsize
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.nbytes <= self.nbytes
+        _check(load_library().dmo_memcpy(context(), self.ptr, a.ctypes.data, a.nbytes), "dmo_memcpy")
+        return self
+
+    def download(self, count=None):
+        n = int(np.prod(self.shape)) if count is None else int(count)
+        out = np.empty(n, dtype=self.dtype)
+        _check(load_library().dmo_memcpy(context(), out.ctypes.data, self.ptr, out.nbytes), "dmo_memcpy")
+        return out.reshape(self.shape) if count is None else out
+
+    def free(self):
+        if self.ptr:
+            load_library().dmo_device_free(context(), self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def memcpy(dst, src, nbytes):
+    _check(load_library().dmo_memcpy(context(), _ptr(dst), _ptr(src), int(nbytes)), "dmo_memcpy")
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """NumPy array backed by page-locked host memory (released when the last view is collected)."""
+    import weakref
+
+    lib = load_library()
+    context()
+    dt = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = max(count * dt.itemsize, 1)
+    p = _vp()
+    if lib.dmo_host_alloc(ctypes.byref(p), nbytes) != 0:
+        raise DmoError("dmo_host_alloc failed")
+    buf = (ctypes.c_char * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib.dmo_host_free, p.value)
+    return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+
+
+# --------------------------------------------------------------------------- A1/A2
+def rank_nd(Y):
+    """dda.dda_ens (dmosopt/dda.py:97-152) -> int64 rank array (canonical non-dominated rank)."""
+    Y = _f64(Y)
+    n, M = Y.shape
+    rank = np.empty(n, dtype=np.int32)
+    _check(load_library().dmo_rank_nd(context(), _ptr(Y), n, M, _ptr(rank)), "dmo_rank_nd")
+    return rank.astype(np.intp)
+
+
+# --------------------------------------------------------------------------- A3/A4
+def crowding_distance(Y):
+    Y = _f64(Y)
+    n, M = Y.shape
+    D = np.empty(n, dtype=np.float64)
+    _check(load_library().dmo_crowding_distance(context(), _ptr(Y), n, M, _ptr(D)), "dmo_crowding_distance")
+    return D
+
+
+def euclidean_distance(Y):
+    Y = _f64(Y)
+    n, M = Y.shape
+    D = np.empty(n, dtype=np.float64)
+    _check(load_library().dmo_euclidean_distance(context(), _ptr(Y), n, M, _ptr(D)), "dmo_euclidean_distance")
+    return D
+
+
+# --------------------------------------------------------------------------- A5
+def _extra_keys(extra):
+    if not extra:
+        return None, 0, []
+    arrs = [_f64(e) for e in extra]
+    tab = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    return ctypes.cast(tab, ctypes.c_void_p), len(arrs), arrs
+
+
+def order_mo(Y, metric=METRIC_NONE, extra_desc_keys=None):
+    """(perm, rank[perm], dist[perm] or None): the ordering of MOEA.orderMO (dmosopt/MOEA.py:300-347)."""
+    Y = _f64(Y)
+    n, M = Y.shape
+    perm = np.empty(n, dtype=np.int64)
+    rank = np.empty(n, dtype=np.int32)
+    dist = np.empty(n, dtype=np.float64) if metric != METRIC_NONE else None
+    tab, nex, keep = _extra_keys(extra_desc_keys)
+    _check(load_library().dmo_order_mo(context(), _ptr(Y), n, M, metric, tab, nex, _ptr(perm), _ptr(rank), _ptr(dist)), "dmo_order_mo")
+    return perm, rank.astype(np.intp), dist
+
+
+def remove_worst(X, Y, keep, metric=METRIC_NONE, extra_desc_keys=None):
+    """First ``keep`` rows of the sortMO order (dmosopt/MOEA.py:398-423): (X, Y, rank, perm)."""
+    X = _f64(X)
+    Y = _f64(Y)
+    n, d = X.shape
+    M = Y.shape[1]
+    keep = int(min(keep, n))
+    Xo = np.empty((keep, d), dtype=np.float64)
+    Yo = np.empty((keep, M), dtype=np.float64)
+    rank = np.empty(keep, dtype=np.int32)
+    perm = np.empty(keep, dtype=np.int64)
+    tab, nex, hold = _extra_keys(extra_desc_keys)
+    _check(
+        load_library().dmo_remove_worst(context(), _ptr(X), _ptr(Y), n, d, M, metric, tab, nex, keep, _ptr(Xo), _ptr(Yo), _ptr(rank), _ptr(perm)),
+        "dmo_remove_worst",
+    )
+    return Xo, Yo, rank.astype(np.intp), perm
+
+
+# --------------------------------------------------------------------------- A6
+def tournament(rank, poolsize, seed, stream_id, crowd=None, return_uniforms=False):
+    rank = np.ascontiguousarray(rank, dtype=np.int32)
+    pop = rank.shape[0]
+    cr = None if crowd is None else _f64(crowd)
+    pool = np.empty(int(poolsize), dtype=np.int64)
+    u = np.empty(pop, dtype=np.float64) if return_uniforms else None
+    _check(
+        load_library().dmo_tournament(context(), _ptr(rank), _ptr(cr), pop, int(poolsize), int(seed) & (2**64 - 1), int(stream_id), _ptr(pool), _ptr(u)),
+        "dmo_tournament",
+    )
+    return (pool, u) if return_uniforms else pool
+
+
+# --------------------------------------------------------------------------- A7/A8
+def mutation_u(parents, u, di_mutation, xlb, xub, mutation_rate):
+    parents = np.atleast_2d(_f64(parents))
+    u = np.atleast_2d(_f64(u))
+    n, d = parents.shape
+    di = _f64(np.broadcast_to(np.asarray(di_mutation, dtype=np.float64), (d,)))
+    out = np.empty((n, d), dtype=np.float64)
+    _check(load_library().dmo_mutation_u(context(), _ptr(parents), _ptr(u), n, d, _ptr(di), _ptr(_f64(xlb)), _ptr(_f64(xub)), float(mutation_rate), _ptr(out)), "dmo_mutation_u")
+    return out
+
+
+def sbx_u(parent1, parent2, u, di_crossover, xlb, xub):
+    p1 = np.atleast_2d(_f64(parent1))
+    p2 = np.atleast_2d(_f64(parent2))
+    u = np.atleast_2d(_f64(u))
+    n, d = p1.shape
+    di = _f64(np.broadcast_to(np.asarray(di_crossover, dtype=np.float64), (d,)))
+    c1 = np.empty((n, d), dtype=np.float64)
+    c2 = np.empty((n, d), dtype=np.float64)
+    _check(load_library().dmo_sbx_u(context(), _ptr(p1), _ptr(p2), _ptr(u), n, d, _ptr(di), _ptr(_f64(xlb)), _ptr(_f64(xub)), _ptr(c1), _ptr(c2)), "dmo_sbx_u")
+    return c1, c2
+
+
+# --------------------------------------------------------------------------- A9
+def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, mutation_rate, di_crossover, di_mutation, xlb, xub, seed, stream_id, return_draws=False):
+    """Offspring of the NSGA-II / AGE-MOEA variation loop (dmosopt/NSGA2.py:142-178).
+
+    Returns (x_gen (P, d), child_kind (P,) int32 [0/1 = SBX child 1/2, 2 = mutant][, draws]).
+    ``draws`` (if requested) is a dict with the random draws the kernel used, for replay on the
+    CPU oracle: u_cross (T,), u_mut (T,), pair (T, 2), single (T,), u_genes (T, 2, d), T = 2*popsize+64.
+    """
+    pop_x = _f64(pop_x)
+    npop, d = pop_x.shape
+    pool_idx = np.ascontiguousarray(pool_idx, dtype=np.int64)
+    popsize = int(popsize)
+    T = 2 * popsize + 64
+    x_gen = np.empty((popsize + 1, d), dtype=np.float64)
+    kind = np.empty(popsize + 1, dtype=np.int32)
+    nch = np.zeros(1, dtype=np.int64)
+    draws = np.empty(T * (5 + 2 * d), dtype=np.float64) if return_draws else None
+    dic = _f64(np.broadcast_to(np.asarray(di_crossover, dtype=np.float64), (d,)))
+    dim = _f64(np.broadcast_to(np.asarray(di_mutation, dtype=np.float64), (d,)))
+    _check(
+        load_library().dmo_nsga2_generate(
+            context(), _ptr(pop_x), npop, d, _ptr(pool_idx), pool_idx.shape[0], popsize, float(crossover_prob), float(mutation_prob),
+            float(mutation_rate), _ptr(dic), _ptr(dim), _ptr(_f64(xlb)), _ptr(_f64(xub)), int(seed) & (2**64 - 1), int(stream_id),
+            _ptr(x_gen), _ptr(kind), _ptr(nch), _ptr(draws),
+        ),
+        "dmo_nsga2_generate",
+    )
+    P = int(nch[0])
+    if not return_draws:
+        return x_gen[:P], kind[:P]
+    dd = {
+        "u_cross": draws[0:T],
+        "u_mut": draws[T : 2 * T],
+        "pair": draws[2 * T : 4 * T].reshape(T, 2).astype(np.int64),
+        "single": draws[4 * T : 5 * T].astype(np.int64),
+        "u_genes": draws[5 * T :].reshape(T, 2, d),
+    }
+    return x_gen[:P], kind[:P], dd
+
+
+# --------------------------------------------------------------------------- A18
+class GPHandle:
+    """Owns a dmo_gp object (posterior state resident in HBM)."""
+
+    def __init__(self, X_train, alpha, factor, constant, length_scale, noise, y_mean, y_std, xlb, xub, kernel=KERNEL_MATERN52, factor_is_inverse=False):
+        lib = load_library()
+        X_train = _f64(X_train)
+        N, d = X_train.shape
+        alpha = _f64(alpha)
+        M = alpha.shape[0]
+        factor = _f64(factor)
+        assert factor.shape == (M, N, N), factor.shape
+        ls = np.empty((M, d), dtype=np.float64)
+        for m in range(M):
+            ls[m, :] = np.asarray(length_scale[m], dtype=np.float64)
+        self.N, self.d, self.M = N, d, M
+        h = _vp()
+        _check(
+            lib.dmo_gp_create(
+                context(), N, d, M, int(kernel), _ptr(X_train), _ptr(alpha), _ptr(factor), 1 if factor_is_inverse else 0, _ptr(_f64(constant)),
+                _ptr(ls), _ptr(_f64(noise)), _ptr(_f64(y_mean)), _ptr(_f64(y_std)), _ptr(_f64(xlb)), _ptr(_f64(xub)), ctypes.byref(h),
+            ),
+            "dmo_gp_create",
+        )
+        self._h = h
+
+    def predict(self, X, return_var=True, precision=GP_FP64):
+        X = _f64(X)
+        if X.ndim == 1:
+            X = X.reshape(1, -1)
+        P = X.shape[0]
+        mean = np.empty((P, self.M), dtype=np.float64)
+        var = np.empty((P, self.M), dtype=np.float64) if return_var else None
+        _check(load_library().dmo_gp_predict(context(), self._h, _ptr(X), P, _ptr(mean), _ptr(var), int(precision)), "dmo_gp_predict")
+        return mean, var
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and _lib is not None and _ctx is not None:
+            _lib.dmo_gp_destroy(_ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------- A16/A17
+def hypervolume(F, ref):
+    F = _f64(F)
+    if F.ndim == 1:
+        F = F.reshape(1, -1)
+    n, M = F.shape
+    ref = _f64(ref)
+    out = _c_dbl(0.0)
+    _check(load_library().dmo_hypervolume(context(), _ptr(F), n, M, _ptr(ref), ctypes.byref(out)), "dmo_hypervolume")
+    return float(out.value)
+
+
+def ehvi_select(F, means, variances, ref, k, nds=True, return_scores=False):
+    F = _f64(F)
+    means = _f64(means)
+    variances = _f64(variances)
+    nf, M = F.shape
+    nc = means.shape[0]
+    k = int(min(k, nc))
+    sel = np.empty(k, dtype=np.int64)
+    score = np.empty(nc, dtype=np.float64) if return_scores else None
+    _check(
+        load_library().dmo_ehvi_select(context(), _ptr(F), nf, _ptr(means), _ptr(variances), nc, M, _ptr(_f64(ref)), 1 if nds else 0, k, _ptr(sel), _ptr(score)),
+        "dmo_ehvi_select",
+    )
+    return (sel, score) if return_scores else sel
+
+
+# --------------------------------------------------------------------------- A21
+def get_duplicates(X, eps=1e-16):
+    X = _f64(X)
+    n, d = X.shape
+    out = np.empty(n, dtype=np.uint8)
+    _check(load_library().dmo_get_duplicates(context(), _ptr(X), n, d, float(eps), _ptr(out)), "dmo_get_duplicates")
+    return out.astype(bool)

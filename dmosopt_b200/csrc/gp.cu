@@ -1,0 +1,442 @@
+// Exact-GP posterior mean / variance.
+// Replaces GPR_Matern.predict / GPR_RBF.predict (dmosopt/model.py:1254-1275, 1343-1364), i.e. per objective
+// sklearn GaussianProcessRegressor.predict(return_std=True) with ConstantKernel * Matern(2.5) [RBF] + WhiteKernel:
+//     mean = y_std * (K_* alpha) + y_mean
+//     var  = y_std^2 * max(0, (c + noise) - || L^-1 K_*^T ||^2_col)
+// The variance contraction is evaluated in its triangular "GEMM form": V = L^-1 K_*^T with L^-1 formed once per
+// epoch (dmo_gp_create), then a sum of squares per candidate -- all positive terms, so the only cancellation is the
+// final subtraction from the prior variance.
+//
+// This file holds the float64 CUDA-core path (DMO_GP_FP64, the parity anchor, ~1e-10 of sklearn) and the object
+// management; the tcgen05 split-precision path lives in gp_tensor.cu.
+#include "gp.cuh"
+
+namespace {
+
+// ---- L^-1 by column-parallel forward substitution (once per epoch, not on the per-generation path)
+__global__ void trinv_kernel(const double* __restrict__ L, int64_t N, int64_t ldo, double* __restrict__ X) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c0 = c - (threadIdx.x & 31);  // first column of this warp
+  const bool live = c < N;
+  for (int64_t i = c0; i < N; ++i) {
+    double s = (i == c) ? 1.0 : 0.0;
+    const double* Li = L + i * N;
+    for (int64_t k = c0; k < i; ++k) {
+      double l = Li[k];                                  // broadcast
+      double x = (live && k >= c) ? X[k * ldo + c] : 0.0;  // coalesced
+      s -= l * x;
+    }
+    if (live && i >= c) X[i * ldo + c] = s / Li[i];
+    __syncwarp();
+  }
+}
+
+__global__ void copy_pad_kernel(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t ldo,
+                                double* __restrict__ dst) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * cols) return;
+  int64_t r = t / cols, c = t - r * cols;
+  dst[r * ldo + c] = src[t];
+}
+
+__global__ void normalise_x_kernel(const double* __restrict__ X, int64_t P, int d, const double* __restrict__ xlb,
+                                   const double* __restrict__ xrg, double* __restrict__ Xn) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P * d) return;
+  int j = (int)(t % d);
+  Xn[t] = (X[t] - xlb[j]) / xrg[j];  // model.py:1262-1263
+}
+
+// ---- K_* tiles: Ks[m][p][n] = c_m * k(||x_p - x_n|| / l_m), float64 ---------------------------------------
+constexpr int KS_TN = 128;  // train points per block (one per thread)
+constexpr int KS_TP = 32;   // candidates per block
+constexpr int KS_DMAX = 64; // input dimensions held in registers
+
+__device__ __forceinline__ double stationary(double s2, int kind) {
+  // s2 = squared scaled distance r^2
+  if (kind == DMO_KERNEL_MATERN52) {
+    double K = sqrt(s2) * 2.23606797749978969641;  // sqrt(5) r
+    return (1.0 + K + K * K / 3.0) * exp(-K);
+  }
+  return exp(-0.5 * s2);
+}
+
+template <bool ISO>
+__global__ void __launch_bounds__(KS_TN) kstar_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base,
+                                                      int64_t Pc, const double* __restrict__ Xt, int64_t N, int d,
+                                                      int M, int kind, const double* __restrict__ inv_ls,
+                                                      const double* __restrict__ constant, int64_t ldk,
+                                                      int64_t plane, double* __restrict__ Ks) {
+  extern __shared__ double sx[];  // [KS_TP][d] candidate tile
+  const int64_t n = (int64_t)blockIdx.x * KS_TN + threadIdx.x;
+  const int64_t pt0 = (int64_t)blockIdx.y * KS_TP;  // within the chunk
+  for (int t = threadIdx.x; t < KS_TP * d; t += KS_TN) {
+    int64_t p = p_base + pt0 + t / d;
+    sx[t] = (p < P) ? Xn[p * d + (t % d)] : 0.0;
+  }
+  double xt[KS_DMAX];
+#pragma unroll
+  for (int j = 0; j < KS_DMAX; ++j) xt[j] = (j < d && n < N) ? Xt[n * d + j] : 0.0;
+  __syncthreads();
+  if (n >= ldk) return;
+  for (int q = 0; q < KS_TP; ++q) {
+    const int64_t pl = pt0 + q;
+    if (pl >= Pc) break;
+    const double* xc = sx + q * d;
+    if (ISO) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < KS_DMAX; ++j)
+        if (j < d) {
+          double df = xc[j] - xt[j];
+          s += df * df;
+        }
+      for (int m = 0; m < M; ++m) {
+        double il = inv_ls[m * d];
+        double v = (n < N) ? constant[m] * stationary(s * il * il, kind) : 0.0;
+        Ks[m * plane + pl * ldk + n] = v;
+      }
+    } else {
+      for (int m = 0; m < M; ++m) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < KS_DMAX; ++j)
+          if (j < d) {
+            double df = (xc[j] - xt[j]) * inv_ls[m * d + j];
+            s += df * df;
+          }
+        double v = (n < N) ? constant[m] * stationary(s, kind) : 0.0;
+        Ks[m * plane + pl * ldk + n] = v;
+      }
+    }
+  }
+}
+
+// ---- mean[p][m] = y_std * (Ks[m][p][:] . alpha[m]) + y_mean: one warp per row ---------------------------------
+__global__ void mean_kernel(const double* __restrict__ Ks, int64_t Pc, int64_t N, int64_t ldk, int64_t plane, int M,
+                            const double* __restrict__ alpha, const double* __restrict__ ymean,
+                            const double* __restrict__ ystd, int64_t p_base, double* __restrict__ mean) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= Pc * M) return;
+  const int m = (int)(w / Pc);
+  const int64_t pl = w - (int64_t)m * Pc;
+  const double* row = Ks + m * plane + pl * ldk;
+  const double* a = alpha + (int64_t)m * N;
+  double s = 0.0;
+  for (int64_t n = lane; n < N; n += 32) s += row[n] * a[n];
+  s = warp_sum(s);
+  if (lane == 0) mean[(p_base + pl) * M + m] = ystd[m] * s + ymean[m];
+}
+
+// ---- variance: V = Linv . Ks^T tile by tile, column sums of V^2 -------------------------------------------------
+// C[i][p] = sum_k Linv[i][k] Ks[p][k]  (both operands k-contiguous).  128 x 128 tile, 256 threads, 8 x 8 per thread.
+// A thread's 8 rows / 8 columns are the interleaved sets {q*32 + t*2 + e : q<4, e<2} so that its double2 shared-memory
+// reads are bank-conflict free (consecutive threads read consecutive 16-byte words).
+constexpr int VB = 128;           // tile edge (rows of Linv and candidates)
+constexpr int VK = 16;            // k step
+constexpr int VLD = VB + 2;       // padded shared-memory row (doubles), even => 16-byte aligned rows
+constexpr size_t VAR_SMEM = (size_t)2 * 2 * VK * VLD * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+    var_kernel(const double* __restrict__ Linv, int64_t ldl, int64_t lplane, const double* __restrict__ Ks, int64_t ldk,
+               int64_t kplane, int64_t Npad, double* __restrict__ vnorm, int64_t Pcpad) {
+  extern __shared__ __align__(16) double vsm[];
+  double* As = vsm;                      // [2][VK][VLD]
+  double* Bs = vsm + 2 * VK * VLD;       // [2][VK][VLD]
+  const int m = blockIdx.y;
+  const int64_t p0 = (int64_t)blockIdx.x * VB;
+  const double* A = Linv + (int64_t)m * lplane;
+  const double* B = Ks + (int64_t)m * kplane + p0 * ldk;
+  const int tid = threadIdx.x;
+  const int ti = tid >> 4, tj = tid & 15;  // 16 x 16 thread grid, 8 x 8 elements each
+  const int lrow = tid >> 1;               // global->shared: each thread moves 8 doubles of A and of B per k step
+  const int lk = (tid & 1) * 8;
+  double vsum[8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) vsum[x] = 0.0;
+
+  const int64_t ntile = Npad / VB;
+  for (int64_t it = 0; it < ntile; ++it) {
+    const int64_t i0 = it * VB;
+    const int64_t nk = (i0 + VB) / VK;  // L^-1 is lower triangular: row block `it` only touches k < i0 + VB
+    double acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+    double ra[8], rb[8];
+    {
+      const double* ap = A + (i0 + lrow) * ldl + lk;
+      const double* bp = B + (int64_t)lrow * ldk + lk;
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        ra[x] = ap[x];
+        rb[x] = bp[x];
+      }
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        As[(lk + x) * VLD + lrow] = ra[x];
+        Bs[(lk + x) * VLD + lrow] = rb[x];
+      }
+    }
+    __syncthreads();
+    for (int64_t kt = 0; kt < nk; ++kt) {
+      const int cur = (int)(kt & 1);
+      const double* Ac = As + cur * VK * VLD;
+      const double* Bc = Bs + cur * VK * VLD;
+      if (kt + 1 < nk) {
+        const double* ap = A + (i0 + lrow) * ldl + (kt + 1) * VK + lk;
+        const double* bp = B + (int64_t)lrow * ldk + (kt + 1) * VK + lk;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          ra[x] = ap[x];
+          rb[x] = bp[x];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < VK; ++k) {
+        double a[8], b[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          double2 av = *reinterpret_cast<const double2*>(Ac + k * VLD + q * 32 + ti * 2);
+          double2 bv = *reinterpret_cast<const double2*>(Bc + k * VLD + q * 32 + tj * 2);
+          a[2 * q] = av.x;
+          a[2 * q + 1] = av.y;
+          b[2 * q] = bv.x;
+          b[2 * q + 1] = bv.y;
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+          for (int y = 0; y < 8; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+      }
+      if (kt + 1 < nk) {
+        double* An = As + (cur ^ 1) * VK * VLD;
+        double* Bn = Bs + (cur ^ 1) * VK * VLD;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          An[(lk + x) * VLD + lrow] = ra[x];
+          Bn[(lk + x) * VLD + lrow] = rb[x];
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int y = 0; y < 8; ++y)
+#pragma unroll
+      for (int x = 0; x < 8; ++x) vsum[y] = fma(acc[x][y], acc[x][y], vsum[y]);
+  }
+  // reduce the 16 row-groups (ti) that share candidate columns; column of vsum[2q+e] is q*32 + tj*2 + e
+  __syncthreads();
+  double* red = vsm;  // 16 x 128 doubles
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    red[ti * VB + q * 32 + tj * 2 + 0] = vsum[2 * q];
+    red[ti * VB + q * 32 + tj * 2 + 1] = vsum[2 * q + 1];
+  }
+  __syncthreads();
+  if (tid < VB) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s += red[r * VB + tid];
+    vnorm[(int64_t)m * Pcpad + p0 + tid] = s;
+  }
+}
+
+__global__ void var_finish_kernel(const double* __restrict__ vnorm, int64_t Pc, int64_t Pcpad, int M,
+                                  const double* __restrict__ constant, const double* __restrict__ noise,
+                                  const double* __restrict__ ystd, int64_t p_base, double* __restrict__ var) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Pc * M) return;
+  int64_t pl = t / M;
+  int m = (int)(t - pl * M);
+  double v = (constant[m] + noise[m]) - vnorm[(int64_t)m * Pcpad + pl];  // kernel_.diag(X) - einsum(V^2)
+  if (v < 0.0) v = 0.0;                                                  // sklearn clamps negative variances
+  double sd = sqrt(v * (ystd[m] * ystd[m]));                             // sklearn returns the std ...
+  var[(p_base + pl) * M + m] = sd * sd;                                  // ... dmosopt squares it (model.py:1267)
+}
+
+}  // namespace
+
+int gp_predict_fp64(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var) {
+  const int64_t N = gp->N, Npad = gp->Npad;
+  const int M = gp->M, d = gp->d;
+  // candidate chunk so that Ks (M x Pc x Npad float64) stays within ~8 GiB
+  int64_t budget = (int64_t)8 << 30;
+  int64_t Pc_max = budget / ((int64_t)M * Npad * 8);
+  Pc_max = (Pc_max / VB) * VB;
+  if (Pc_max < VB) Pc_max = VB;
+  const int64_t Pc_alloc = P < Pc_max ? ceil_div(P, VB) * VB : Pc_max;
+  DevBuf<double> Ks, vnorm;
+  DMO_TRY(Ks.alloc(ctx, (size_t)M * Pc_alloc * Npad));
+  DMO_TRY(vnorm.alloc(ctx, (size_t)M * Pc_alloc));
+  const int64_t kplane = Pc_alloc * Npad;
+  for (int64_t p_base = 0; p_base < P; p_base += Pc_alloc) {
+    const int64_t Pc = (P - p_base) < Pc_alloc ? (P - p_base) : Pc_alloc;
+    const int64_t Pcpad = ceil_div(Pc, VB) * VB;
+    dim3 gk((unsigned)ceil_div(Npad, KS_TN), (unsigned)ceil_div(Pcpad, KS_TP));
+    size_t smem = (size_t)KS_TP * d * sizeof(double);
+    {
+      ProfileScope ps(ctx, "gp_kstar");
+      if (gp->isotropic)
+      DMO_LAUNCH(kstar_kernel<true>, gk, KS_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel,
+                 gp->inv_ls.p, gp->constant.p, Npad, kplane, Ks.p);
+    else
+      DMO_LAUNCH(kstar_kernel<false>, gk, KS_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel,
+                 gp->inv_ls.p, gp->constant.p, Npad, kplane, Ks.p);
+    }
+    {
+      ProfileScope ps(ctx, "gp_mean");
+    DMO_LAUNCH(mean_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Ks.p, Pc, N, Npad, kplane, M, gp->alpha.p,
+               gp->ymean.p, gp->ystd.p, p_base, d_mean);
+    }
+    if (d_var) {
+      ProfileScope ps(ctx, "gp_var");
+      dim3 gv((unsigned)(Pcpad / VB), (unsigned)M);
+      DMO_CUDA(cudaFuncSetAttribute(var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VAR_SMEM));
+      DMO_LAUNCH(var_kernel, gv, 256, VAR_SMEM, gp->Linv.p, Npad, Npad * Npad, Ks.p, Npad, kplane, Npad, vnorm.p, Pc_alloc);
+      DMO_LAUNCH(var_finish_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, Pc, Pc_alloc, M, gp->constant.p,
+                 gp->noise.p, gp->ystd.p, p_base, d_var);
+    }
+  }
+  DMO_CHECK_LAUNCH();
+  return DMO_OK;
+}
+
+extern "C" {
+
+int dmo_gp_create(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const double* X_train, const double* alpha,
+                  const double* factor, int factor_is_inverse, const double* constant, const double* length_scale,
+                  const double* noise, const double* y_mean, const double* y_std, const double* xlb, const double* xub,
+                  dmo_gp** out) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(out, "gp_create: null output");
+  *out = nullptr;
+  DMO_REQUIRE(N >= 1 && d >= 1 && d <= KS_DMAX && M >= 1 && M <= 16, "gp_create: unsupported shape N=%lld d=%d M=%d",
+              (long long)N, d, M);
+  DMO_REQUIRE(kernel == DMO_KERNEL_MATERN52 || kernel == DMO_KERNEL_RBF, "gp_create: unknown kernel %d", kernel);
+  DMO_REQUIRE(X_train && alpha && factor && constant && length_scale && noise && y_mean && y_std && xlb && xub,
+              "gp_create: null pointer");
+  // host copies of the small parameter vectors (needed to derive 1/l, ranges, isotropy)
+  std::vector<double> h_ls((size_t)M * d), h_lb(d), h_ub(d);
+  DMO_CUDA(cudaMemcpy(h_ls.data(), length_scale, h_ls.size() * sizeof(double), cudaMemcpyDefault));
+  DMO_CUDA(cudaMemcpy(h_lb.data(), xlb, d * sizeof(double), cudaMemcpyDefault));
+  DMO_CUDA(cudaMemcpy(h_ub.data(), xub, d * sizeof(double), cudaMemcpyDefault));
+  dmo_gp* gp = new dmo_gp();
+  gp->N = N;
+  gp->d = d;
+  gp->M = M;
+  gp->kernel = kernel;
+  gp->Npad = ceil_div(N, VB) * VB;
+  gp->isotropic = true;
+  std::vector<double> h_inv((size_t)M * d), h_rg(d);
+  for (int m = 0; m < M; ++m)
+    for (int j = 0; j < d; ++j) {
+      h_inv[(size_t)m * d + j] = 1.0 / h_ls[(size_t)m * d + j];
+      if (h_ls[(size_t)m * d + j] != h_ls[(size_t)m * d]) gp->isotropic = false;
+    }
+  for (int j = 0; j < d; ++j) h_rg[j] = h_ub[j] - h_lb[j];
+  int st = DMO_OK;
+  auto fail = [&](int s) {
+    delete gp;
+    return s;
+  };
+#define GP_TRY(e)                    \
+  do {                               \
+    st = (e);                        \
+    if (st != DMO_OK) return fail(st); \
+  } while (0)
+#define GP_CUDA(call)                                                                                 \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return fail(dmo_fail(ctx, DMO_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)));      \
+  } while (0)
+  const int64_t Npad = gp->Npad;
+  GP_TRY(gp->Xt.alloc(ctx, (size_t)N * d));
+  GP_TRY(gp->alpha.alloc(ctx, (size_t)M * N));
+  GP_TRY(gp->Linv.alloc(ctx, (size_t)M * Npad * Npad));
+  GP_TRY(gp->inv_ls.alloc(ctx, (size_t)M * d));
+  GP_TRY(gp->constant.alloc(ctx, M));
+  GP_TRY(gp->noise.alloc(ctx, M));
+  GP_TRY(gp->ymean.alloc(ctx, M));
+  GP_TRY(gp->ystd.alloc(ctx, M));
+  GP_TRY(gp->xlb.alloc(ctx, d));
+  GP_TRY(gp->xrg.alloc(ctx, d));
+  GP_CUDA(cudaMemcpyAsync(gp->Xt.p, X_train, (size_t)N * d * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemcpyAsync(gp->alpha.p, alpha, (size_t)M * N * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemcpyAsync(gp->inv_ls.p, h_inv.data(), h_inv.size() * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemcpyAsync(gp->constant.p, constant, M * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemcpyAsync(gp->noise.p, noise, M * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemcpyAsync(gp->ymean.p, y_mean, M * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemcpyAsync(gp->ystd.p, y_std, M * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemcpyAsync(gp->xlb.p, h_lb.data(), d * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemcpyAsync(gp->xrg.p, h_rg.data(), d * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GP_CUDA(cudaMemsetAsync(gp->Linv.p, 0, (size_t)M * Npad * Npad * sizeof(double), ctx->stream));
+  {
+    In<double> f;
+    GP_TRY(f.init(ctx, factor, (size_t)M * N * N));
+    for (int m = 0; m < M; ++m) {
+      const double* src = f.d + (size_t)m * N * N;
+      double* dst = gp->Linv.p + (size_t)m * Npad * Npad;
+      if (factor_is_inverse) {
+        DMO_LAUNCH(copy_pad_kernel, (unsigned)ceil_div(N * N, 256), 256, 0, src, N, N, Npad, dst);
+      } else {
+        DMO_LAUNCH(trinv_kernel, (unsigned)ceil_div(N, 128), 128, 0, src, N, Npad, dst);
+      }
+    }
+    GP_CUDA(cudaGetLastError());
+    GP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  // host copies used by the tensor path's scaling
+  gp->h_constant.resize(M);
+  gp->h_noise.resize(M);
+  gp->h_ystd.resize(M);
+  GP_CUDA(cudaMemcpy(gp->h_constant.data(), constant, M * sizeof(double), cudaMemcpyDefault));
+  GP_CUDA(cudaMemcpy(gp->h_noise.data(), noise, M * sizeof(double), cudaMemcpyDefault));
+  GP_CUDA(cudaMemcpy(gp->h_ystd.data(), y_std, M * sizeof(double), cudaMemcpyDefault));
+#undef GP_TRY
+#undef GP_CUDA
+  *out = gp;
+  return DMO_OK;
+}
+
+int dmo_gp_destroy(dmo_ctx* ctx, dmo_gp* gp) {
+  if (!ctx) return DMO_ERR_ARG;
+  if (!gp) return DMO_OK;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  delete gp;
+  return DMO_OK;
+}
+
+int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double* mean, double* var, int precision) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(gp, "gp_predict: null model");
+  if (P == 0) return DMO_OK;
+  DMO_REQUIRE(P > 0 && X && mean, "gp_predict: bad arguments");
+  In<double> x;
+  Out<double> om, ov;
+  DMO_TRY(x.init(ctx, X, (size_t)P * gp->d));
+  DMO_TRY(om.init(ctx, mean, (size_t)P * gp->M));
+  DMO_TRY(ov.init(ctx, var, (size_t)P * gp->M));
+  DevBuf<double> xn;
+  DMO_TRY(xn.alloc(ctx, (size_t)P * gp->d));
+  DMO_LAUNCH(normalise_x_kernel, (unsigned)ceil_div(P * gp->d, 256), 256, 0, x.d, P, gp->d, gp->xlb.p, gp->xrg.p, xn.p);
+  if (precision == DMO_GP_FP64) {
+    DMO_TRY(gp_predict_fp64(ctx, gp, xn.p, P, om.d, ov.d));
+  } else if (precision == DMO_GP_TENSOR) {
+    DMO_TRY(gp_predict_tensor(ctx, gp, xn.p, P, om.d, ov.d));
+  } else {
+    return dmo_fail(ctx, DMO_ERR_ARG, "gp_predict: unknown precision %d", precision);
+  }
+  DMO_TRY(om.finish(ctx));
+  DMO_TRY(ov.finish(ctx));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+// GP posterior state shared by gp.cu (float64 path) and gp_tensor.cu (tcgen05 path).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct dmo_gp {
+  int64_t N = 0, Npad = 0;  // training points; padded to the variance tile edge
+  int d = 0, M = 0, kernel = 0;
+  bool isotropic = true;
+  DevBuf<double> Xt;        // (N, d) normalised training inputs
+  DevBuf<double> alpha;     // (M, N)
+  DevBuf<double> Linv;      // (M, Npad, Npad) lower-triangular inverse Cholesky factors, zero padded
+  DevBuf<double> inv_ls;    // (M, d) 1 / length_scale
+  DevBuf<double> constant, noise, ymean, ystd;  // (M,)
+  DevBuf<double> xlb, xrg;  // (d,)
+  std::vector<double> h_constant, h_noise, h_ystd;
+  // tensor path (built lazily on first DMO_GP_TENSOR predict)
+  bool tensor_ready = false;
+  DevBuf<uint16_t> Lhi, Llo;  // (M, Npad, Npad) fp16 split of the row-scaled L^-1
+  DevBuf<float> Lscale;       // (M, Npad) power-of-two row scales
+};
+
+int gp_predict_fp64(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var);
+int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var);

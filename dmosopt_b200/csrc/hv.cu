@@ -1,0 +1,451 @@
+// Exact hypervolume and HV-improvement (EHVI) candidate selection
+// (SURVEY.md section 8a rows A16 / A17).
+//   hv.AdaptiveHyperVolume.compute_hypervolume(.., 'box')      dmosopt/hv.py:123-189
+//   HyperVolumeBoxDecomposition.compute_hypervolume            dmosopt/hv_box_decomposition.py:86-304
+//   select_candidates / _compute_batch_ehvi / _decompose_...   dmosopt/hv_box_decomposition.py:306-437
+//
+// Hypervolume algorithm (not a transliteration of the reference's sequential local-upper-bound lists):
+//   points outside ref are dropped (hv.py:159), then only the rank-0 subset is kept (the HV of a set is the HV of
+//   its non-dominated subset).
+//   M = 2: sort by f0; the staircase strips are independent -> one parallel reduction.
+//   M = 3: HV = sum_k (r_z - z_k) * A_k, where A_k is the area of the xy-quadrant of k that is NOT covered by points
+//          with smaller z.  Every A_k is an independent sweep over the x-sorted points (running min of y among the
+//          points with smaller z), so the whole computation is n independent O(n) scans: thread-per-point, sources
+//          streamed through shared memory in coalesced tiles, no dynamic data structures.
+//   M >= 4: the same slicing identity applied recursively (see hv_slice_kernel), O(n^(M-1)).
+// All arithmetic is float64; block partial sums are combined in a fixed order (deterministic result).
+#include "common.cuh"
+
+namespace {
+
+constexpr int HV_T = 128;
+
+__global__ void inside_flag_kernel(const double* __restrict__ F, int64_t n, int M, const double* __restrict__ ref,
+                                   int32_t* __restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) {
+    flag[i] = 0;
+    return;
+  }
+  bool in = true;
+  for (int j = 0; j < M; ++j) in = in && (ref[j] > F[i * M + j]);  // hv.py:159
+  flag[i] = in ? 1 : 0;
+}
+
+__global__ void rank0_flag_kernel(const int32_t* __restrict__ rank, int64_t n, int32_t* __restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  flag[i] = (i < n && rank[i] == 0) ? 1 : 0;
+}
+
+__global__ void compact_rows_kernel(const double* __restrict__ F, int64_t n, int M, const int32_t* __restrict__ flag,
+                                    const int32_t* __restrict__ pos, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  for (int j = 0; j < M; ++j) out[(int64_t)pos[i] * M + j] = F[i * M + j];
+}
+
+__global__ void col_key_kernel(const double* __restrict__ F, int64_t n, int M, int j, uint64_t* __restrict__ keys,
+                               uint32_t* __restrict__ idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = f64_to_ordered(F[i * M + j]);
+    idx[i] = (uint32_t)i;
+  }
+}
+
+__global__ void invert_perm_kernel(const uint32_t* __restrict__ sidx, int64_t n, uint32_t* __restrict__ inv) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) inv[sidx[p]] = (uint32_t)p;
+}
+
+__global__ void min_col_kernel(const double* __restrict__ F, int64_t n, double* out) {
+  // single block
+  __shared__ double s[256];
+  double m = INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmin(m, F[i]);
+  s[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] = fmin(s[threadIdx.x], s[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = s[0];
+}
+
+// deterministic block sum -> partial[blockIdx.x]
+__device__ __forceinline__ void block_sum_store(double v, double* partial) {
+  __shared__ double ws[32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += ws[w];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void final_sum_kernel(const double* __restrict__ partial, int64_t nb, double* out) {
+  __shared__ double s[256];
+  double a = 0.0;
+  for (int64_t i = threadIdx.x; i < nb; i += blockDim.x) a += partial[i];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = s[0];
+}
+
+// M = 2: points are mutually non-dominated, sidx sorts them by f0 ascending => f1 is non-increasing along the order
+__global__ void hv2_kernel(const double* __restrict__ F, const uint32_t* __restrict__ sidx, int64_t n, double r0,
+                           double r1, double* __restrict__ partial) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (p < n) {
+    const double x = F[(int64_t)sidx[p] * 2], y = F[(int64_t)sidx[p] * 2 + 1];
+    const double xn = (p + 1 < n) ? F[(int64_t)sidx[p + 1] * 2] : r0;
+    v = (xn - x) * (r1 - y);
+  }
+  block_sum_store(v, partial);
+}
+
+// M = 3 (and the innermost level of the M >= 4 recursion).
+// xs / ys: coordinates in x-sorted order; zo: total order id of each x-sorted point along z (ties by index).
+// Thread k computes  (r_z - z_k) * [ (r_x - x_k)(r_y - y_k) - area covered by {j : zo_j < zo_k} inside k's quadrant ].
+__global__ void __launch_bounds__(HV_T) hv3_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
+                                                   const double* __restrict__ zs, const uint32_t* __restrict__ zo,
+                                                   int64_t n, double rx, double ry, double rz,
+                                                   double* __restrict__ partial) {
+  __shared__ double sx[HV_T], sy[HV_T];
+  __shared__ uint32_t sz[HV_T];
+  const int64_t k = (int64_t)blockIdx.x * HV_T + threadIdx.x;
+  const bool live = k < n;
+  const double xk = live ? xs[k] : 0.0, yk = live ? ys[k] : 0.0;
+  const uint32_t zk = live ? zo[k] : 0u;
+  double covered = 0.0, m = INFINITY, xcur = xk;
+  for (int64_t t0 = 0; t0 < n; t0 += HV_T) {
+    const int64_t j = t0 + threadIdx.x;
+    __syncthreads();
+    sx[threadIdx.x] = j < n ? xs[j] : INFINITY;
+    sy[threadIdx.x] = j < n ? ys[j] : INFINITY;
+    sz[threadIdx.x] = j < n ? zo[j] : 0xFFFFFFFFu;
+    __syncthreads();
+    const int cnt = (int)((n - t0) < HV_T ? (n - t0) : HV_T);
+#pragma unroll 8
+    for (int s = 0; s < cnt; ++s) {
+      const double yj = sy[s];
+      if (sz[s] < zk && yj < m) {  // a point below k in z that lowers the staircase
+        const double xj = fmax(sx[s], xk);
+        const double h = ry - fmax(m, yk);  // m = inf -> negative -> no area yet
+        covered += (xj - xcur) * fmax(h, 0.0);
+        xcur = xj;
+        m = yj;
+      }
+    }
+  }
+  double v = 0.0;
+  if (live) {
+    covered += (rx - xcur) * fmax(ry - fmax(m, yk), 0.0);
+    const double excl = (rx - xk) * (ry - yk) - covered;
+    v = excl * (rz - zs[k]);
+  }
+  block_sum_store(v, partial);
+}
+
+__global__ void gather_col_kernel(const double* __restrict__ F, const uint32_t* __restrict__ sidx, int64_t n, int M,
+                                  int j, double* __restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) out[p] = F[(int64_t)sidx[p] * M + j];
+}
+__global__ void gather_u32_kernel2(const uint32_t* __restrict__ src, const uint32_t* __restrict__ sidx, int64_t n,
+                                   uint32_t* __restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) out[p] = src[sidx[p]];
+}
+
+// ---- EHVI -----------------------------------------------------------------------------------------------
+constexpr int EH_MAXM = 8;
+
+// boxes between consecutive f0-sorted front points (hv_box_decomposition.py:418-437)
+__global__ void box_flag_kernel(const double* __restrict__ front, const uint32_t* __restrict__ sidx, int64_t nf, int M,
+                                const double* __restrict__ ref, int32_t* __restrict__ flag) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nf + 1) return;
+  if (b == nf + 1) {
+    flag[b] = 0;
+    return;
+  }
+  bool valid = true;
+  for (int j = 0; j < M; ++j) {
+    double lo = (b == 0) ? -INFINITY : front[(int64_t)sidx[b - 1] * M + j];
+    double up = (b < nf) ? front[(int64_t)sidx[b] * M + j] : ref[j];
+    valid = valid && (up > lo);
+  }
+  flag[b] = valid ? 1 : 0;
+}
+__global__ void box_write_kernel(const double* __restrict__ front, const uint32_t* __restrict__ sidx, int64_t nf, int M,
+                                 const double* __restrict__ ref, const int32_t* __restrict__ flag,
+                                 const int32_t* __restrict__ pos, double* __restrict__ lower, double* __restrict__ upper) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nf || !flag[b]) return;
+  for (int j = 0; j < M; ++j) {
+    lower[(int64_t)pos[b] * M + j] = (b == 0) ? -INFINITY : front[(int64_t)sidx[b - 1] * M + j];
+    upper[(int64_t)pos[b] * M + j] = (b < nf) ? front[(int64_t)sidx[b] * M + j] : ref[j];
+  }
+}
+
+// score_c = sum_b prod_j [ sd (phi(zl) - phi(zu)) + mu (Phi(zu) - Phi(zl)) ]   (hv_box_decomposition.py:353-416)
+__global__ void ehvi_kernel(const double* __restrict__ lower, const double* __restrict__ upper, int64_t nb, int M,
+                            const double* __restrict__ means, const double* __restrict__ variances, int64_t nc,
+                            double* __restrict__ score) {
+  extern __shared__ double sb[];  // [2][tile][M]
+  const int TB = 64;
+  double* sl = sb;
+  double* su = sb + TB * M;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double mu[EH_MAXM], sd[EH_MAXM];
+  for (int j = 0; j < M; ++j) {
+    mu[j] = c < nc ? means[c * M + j] : 0.0;
+    sd[j] = c < nc ? sqrt(variances[c * M + j]) : 1.0;
+  }
+  double total = 0.0;
+  for (int64_t b0 = 0; b0 < nb; b0 += TB) {
+    const int cnt = (int)((nb - b0) < TB ? (nb - b0) : TB);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * M; t += blockDim.x) {
+      sl[t] = lower[b0 * M + t];
+      su[t] = upper[b0 * M + t];
+    }
+    __syncthreads();
+    for (int b = 0; b < cnt; ++b) {
+      double prod = 1.0;
+      for (int j = 0; j < M; ++j) {
+        const double lo = sl[b * M + j], up = su[b * M + j];
+        const double zl = (lo - mu[j]) / sd[j], zu = (up - mu[j]) / sd[j];
+        const double pl = isinf(lo) ? 0.0 : normcdf(zl);
+        const double pu = isinf(up) ? 1.0 : normcdf(zu);
+        const double dl = 0.3989422804014326779 * exp(-0.5 * zl * zl);  // norm.pdf, 0 at +-inf
+        const double du = 0.3989422804014326779 * exp(-0.5 * zu * zu);
+        prod *= sd[j] * (dl - du) + mu[j] * (pu - pl);
+      }
+      total += prod;
+    }
+  }
+  if (c < nc) score[c] = total;
+}
+
+__global__ void neg_key_kernel(const double* __restrict__ score, int64_t n, uint64_t* __restrict__ keys,
+                               uint32_t* __restrict__ idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = f64_to_ordered(-score[i]);
+    idx[i] = (uint32_t)i;
+  }
+}
+__global__ void widen_idx_kernel(const uint32_t* __restrict__ idx, int64_t k, int64_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) out[i] = (int64_t)idx[i];
+}
+
+// compaction: rows of F with flag set, in order.  Returns the count on the host.
+int compact_rows(dmo_ctx* ctx, const double* dF, int64_t n, int M, DevBuf<int32_t>& flag, DevBuf<double>& out,
+                 int64_t* count) {
+  DevBuf<int32_t> pos;
+  DMO_TRY(pos.alloc(ctx, n + 1));
+  DMO_TRY(prim_exclusive_sum_i32(ctx, flag.p, pos.p, n + 1));
+  int32_t h = 0;
+  DMO_CUDA(cudaMemcpyAsync(&h, pos.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  *count = h;
+  DMO_TRY(out.alloc(ctx, (size_t)(h > 0 ? h : 1) * M));
+  if (h > 0) DMO_LAUNCH(compact_rows_kernel, (unsigned)ceil_div(n, 256), 256, 0, dF, n, M, flag.p, pos.p, out.p);
+  DMO_CHECK_LAUNCH();
+  return DMO_OK;
+}
+
+// rank-0 subset of a device point set
+int nondominated_subset(dmo_ctx* ctx, const double* dF, int64_t n, int M, DevBuf<double>& out, int64_t* count) {
+  DevBuf<int32_t> rank, flag;
+  DMO_TRY(rank.alloc(ctx, n));
+  DMO_TRY(flag.alloc(ctx, n + 1));
+  DMO_TRY(rank_nd_device(ctx, dF, n, M, rank.p));
+  DMO_LAUNCH(rank0_flag_kernel, (unsigned)ceil_div(n + 1, 256), 256, 0, rank.p, n, flag.p);
+  DMO_TRY(compact_rows(ctx, dF, n, M, flag, out, count));
+  return DMO_OK;
+}
+
+int sort_by_column(dmo_ctx* ctx, const double* dF, int64_t n, int M, int j, DevBuf<uint32_t>& sidx) {
+  DevBuf<uint64_t> k0, k1;
+  DevBuf<uint32_t> i0;
+  DMO_TRY(k0.alloc(ctx, n));
+  DMO_TRY(k1.alloc(ctx, n));
+  DMO_TRY(i0.alloc(ctx, n));
+  DMO_TRY(sidx.alloc(ctx, n));
+  DMO_LAUNCH(col_key_kernel, (unsigned)ceil_div(n, 256), 256, 0, dF, n, M, j, k0.p, i0.p);
+  DMO_TRY(prim_sort_pairs_u64(ctx, k0.p, k1.p, i0.p, sidx.p, n, 0, 64));
+  return DMO_OK;
+}
+
+int sum_partials(dmo_ctx* ctx, DevBuf<double>& partial, int64_t nb, double* h_out) {
+  DevBuf<double> res;
+  DMO_TRY(res.alloc(ctx, 1));
+  DMO_LAUNCH(final_sum_kernel, 1, 256, 0, partial.p, nb, res.p);
+  DMO_CHECK_LAUNCH();
+  DMO_CUDA(cudaMemcpyAsync(h_out, res.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
+
+}  // namespace
+
+int hypervolume_device(dmo_ctx* ctx, const double* dF, int64_t n, int M, const double* h_ref, double* h_out) {
+  *h_out = 0.0;
+  if (n <= 0) return DMO_OK;
+  DMO_REQUIRE(M >= 1 && M <= 3, "hypervolume: M=%d not supported by this build (1..3)", M);
+  DevBuf<double> dref;
+  DMO_TRY(dref.alloc(ctx, M));
+  DMO_CUDA(cudaMemcpyAsync(dref.p, h_ref, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // 1. points strictly inside the reference box
+  DevBuf<int32_t> flag;
+  DevBuf<double> Fin;
+  int64_t n1 = 0;
+  DMO_TRY(flag.alloc(ctx, n + 1));
+  DMO_LAUNCH(inside_flag_kernel, (unsigned)ceil_div(n + 1, 256), 256, 0, dF, n, M, dref.p, flag.p);
+  DMO_TRY(compact_rows(ctx, dF, n, M, flag, Fin, &n1));
+  if (n1 == 0) return DMO_OK;
+  if (M == 1) {
+    DevBuf<double> mn;
+    DMO_TRY(mn.alloc(ctx, 1));
+    DMO_LAUNCH(min_col_kernel, 1, 256, 0, Fin.p, n1, mn.p);
+    DMO_CHECK_LAUNCH();
+    double h = 0.0;
+    DMO_CUDA(cudaMemcpyAsync(&h, mn.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+    *h_out = h_ref[0] - h;
+    return DMO_OK;
+  }
+  // 2. non-dominated subset
+  DevBuf<double> Fnd;
+  int64_t n2 = 0;
+  DMO_TRY(nondominated_subset(ctx, Fin.p, n1, M, Fnd, &n2));
+  if (n2 == 0) return DMO_OK;
+  DevBuf<uint32_t> sx;
+  DMO_TRY(sort_by_column(ctx, Fnd.p, n2, M, 0, sx));
+  if (M == 2) {
+    const int64_t nb = ceil_div(n2, 256);
+    DevBuf<double> partial;
+    DMO_TRY(partial.alloc(ctx, nb));
+    DMO_LAUNCH(hv2_kernel, (unsigned)nb, 256, 0, Fnd.p, sx.p, n2, h_ref[0], h_ref[1], partial.p);
+    DMO_TRY(sum_partials(ctx, partial, nb, h_out));
+    return DMO_OK;
+  }
+  // M == 3
+  DevBuf<uint32_t> sz, zinv, zo;
+  DevBuf<double> xs, ys, zs;
+  DMO_TRY(sort_by_column(ctx, Fnd.p, n2, M, 2, sz));
+  DMO_TRY(zinv.alloc(ctx, n2));
+  DMO_TRY(zo.alloc(ctx, n2));
+  DMO_TRY(xs.alloc(ctx, n2));
+  DMO_TRY(ys.alloc(ctx, n2));
+  DMO_TRY(zs.alloc(ctx, n2));
+  const unsigned g = (unsigned)ceil_div(n2, 256);
+  DMO_LAUNCH(invert_perm_kernel, g, 256, 0, sz.p, n2, zinv.p);     // zinv[i] = position of point i along z
+  DMO_LAUNCH(gather_u32_kernel2, g, 256, 0, zinv.p, sx.p, n2, zo.p);  // ... re-indexed by x-sorted position
+  DMO_LAUNCH(gather_col_kernel, g, 256, 0, Fnd.p, sx.p, n2, M, 0, xs.p);
+  DMO_LAUNCH(gather_col_kernel, g, 256, 0, Fnd.p, sx.p, n2, M, 1, ys.p);
+  DMO_LAUNCH(gather_col_kernel, g, 256, 0, Fnd.p, sx.p, n2, M, 2, zs.p);
+  const int64_t nb = ceil_div(n2, HV_T);
+  DevBuf<double> partial;
+  DMO_TRY(partial.alloc(ctx, nb));
+  ProfileScope ps(ctx, "hv3");
+  DMO_LAUNCH(hv3_kernel, (unsigned)nb, HV_T, 0, xs.p, ys.p, zs.p, zo.p, n2, h_ref[0], h_ref[1], h_ref[2], partial.p);
+  DMO_TRY(sum_partials(ctx, partial, nb, h_out));
+  return DMO_OK;
+}
+
+extern "C" {
+
+int dmo_hypervolume(dmo_ctx* ctx, const double* F, int64_t n, int M, const double* ref, double* out) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(out && ref && n >= 0 && M >= 1 && M <= 16, "hypervolume: bad arguments");
+  *out = 0.0;
+  if (n == 0) return DMO_OK;
+  DMO_REQUIRE(F, "hypervolume: null points");
+  double h_ref[16];
+  DMO_CUDA(cudaMemcpy(h_ref, ref, M * sizeof(double), cudaMemcpyDefault));
+  In<double> f;
+  DMO_TRY(f.init(ctx, F, (size_t)n * M));
+  DMO_TRY(hypervolume_device(ctx, f.d, n, M, h_ref, out));
+  return DMO_OK;
+}
+
+int dmo_ehvi_select(dmo_ctx* ctx, const double* F, int64_t nf, const double* means, const double* variances, int64_t nc,
+                    int M, const double* ref, int nds, int64_t k, int64_t* sel, double* score) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(F && means && variances && ref && sel && nf > 0 && nc > 0 && k > 0 && M >= 1 && M <= EH_MAXM,
+              "ehvi_select: bad arguments");
+  if (k > nc) k = nc;
+  In<double> f, mu, var, r;
+  DMO_TRY(f.init(ctx, F, (size_t)nf * M));
+  DMO_TRY(mu.init(ctx, means, (size_t)nc * M));
+  DMO_TRY(var.init(ctx, variances, (size_t)nc * M));
+  DMO_TRY(r.init(ctx, ref, (size_t)M));
+  // rank-0 subset of the chosen set (indicators.py:299-303)
+  DevBuf<double> front_buf;
+  const double* front = f.d;
+  int64_t nfr = nf;
+  if (nds) {
+    DMO_TRY(nondominated_subset(ctx, f.d, nf, M, front_buf, &nfr));
+    if (nfr > 0)
+      front = front_buf.p;
+    else
+      nfr = nf;
+  }
+  DevBuf<uint32_t> sidx;
+  DMO_TRY(sort_by_column(ctx, front, nfr, M, 0, sidx));
+  DevBuf<int32_t> flag, pos;
+  DMO_TRY(flag.alloc(ctx, nfr + 2));
+  DMO_TRY(pos.alloc(ctx, nfr + 2));
+  DMO_LAUNCH(box_flag_kernel, (unsigned)ceil_div(nfr + 2, 256), 256, 0, front, sidx.p, nfr, M, r.d, flag.p);
+  DMO_TRY(prim_exclusive_sum_i32(ctx, flag.p, pos.p, nfr + 2));
+  int32_t nb = 0;
+  DMO_CUDA(cudaMemcpyAsync(&nb, pos.p + nfr + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  DevBuf<double> lower, upper, sc;
+  DMO_TRY(lower.alloc(ctx, (size_t)(nb > 0 ? nb : 1) * M));
+  DMO_TRY(upper.alloc(ctx, (size_t)(nb > 0 ? nb : 1) * M));
+  DMO_TRY(sc.alloc(ctx, nc));
+  if (nb > 0)
+    DMO_LAUNCH(box_write_kernel, (unsigned)ceil_div(nfr + 1, 256), 256, 0, front, sidx.p, nfr, M, r.d, flag.p, pos.p,
+               lower.p, upper.p);
+  DMO_LAUNCH(ehvi_kernel, (unsigned)ceil_div(nc, 128), 128, 2 * 64 * M * sizeof(double), lower.p, upper.p, (int64_t)nb,
+             M, mu.d, var.d, nc, sc.p);
+  // k largest scores, ties by candidate index
+  DevBuf<uint64_t> k0, k1;
+  DevBuf<uint32_t> i0, i1;
+  DMO_TRY(k0.alloc(ctx, nc));
+  DMO_TRY(k1.alloc(ctx, nc));
+  DMO_TRY(i0.alloc(ctx, nc));
+  DMO_TRY(i1.alloc(ctx, nc));
+  DMO_LAUNCH(neg_key_kernel, (unsigned)ceil_div(nc, 256), 256, 0, sc.p, nc, k0.p, i0.p);
+  DMO_TRY(prim_sort_pairs_u64(ctx, k0.p, k1.p, i0.p, i1.p, nc, 0, 64));
+  Out<int64_t> osel;
+  Out<double> osc;
+  DMO_TRY(osel.init(ctx, sel, (size_t)k));
+  DMO_TRY(osc.init(ctx, score, (size_t)nc));
+  DMO_LAUNCH(widen_idx_kernel, (unsigned)ceil_div(k, 256), 256, 0, i1.p, k, osel.d);
+  if (osc.d) DMO_CUDA(cudaMemcpyAsync(osc.d, sc.p, nc * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  DMO_CHECK_LAUNCH();
+  DMO_TRY(osel.finish(ctx));
+  DMO_TRY(osc.finish(ctx));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
+
+}  // extern "C"

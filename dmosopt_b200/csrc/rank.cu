@@ -1,0 +1,363 @@
+// Non-dominated rank (replaces dmosopt/dda.py:97-152 dda_ens).
+//
+// rank_i = front index = length of the longest domination chain ending at i
+//        = 0 if nothing dominates i, else 1 + max{rank_j : j dominates i}.
+//
+// Pipeline (all on the context's stream):
+//   1. per objective: radix-sort the column, give every distinct value a dense integer id
+//      (order- and equality-preserving, so float64 inputs are ranked exactly with 32-bit compares);
+//   2. lexicographic order of the integer vectors (LSD radix passes); in that order a point can only
+//      be dominated by points before it, and identical vectors are adjacent (one "group id" each);
+//   3. one persistent kernel evaluates the chain recurrence block by block in that order:
+//      a block of T targets streams every earlier block through shared memory (coalesced 16-byte
+//      records, broadcast reads, one dominance predicate per pair), waits on a per-block "done" flag
+//      only when it catches up with its predecessor, resolves the in-block dependencies with
+//      per-thread dominator bitmasks + warp ballots (Kahn rounds), and publishes its ranks.
+//      Blocks are handed out by an atomic ticket, so a block only ever waits for blocks whose CTAs are
+//      already running (no co-residency assumption, no deadlock).
+//
+// Algorithmic bytes: 8 n M read + 4 n written; comparisons <= n^2 M / 2 (compare-throughput bound,
+// see DESIGN.md).
+#include "common.cuh"
+
+namespace {
+
+constexpr int RANK_T = 128;  // targets per block == sources per shared-memory tile
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void col_keys_kernel(const double* __restrict__ Y, int64_t n, int M, int j, uint64_t* __restrict__ keys,
+                                uint32_t* __restrict__ idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = f64_to_ordered(Y[i * M + j]);
+    idx[i] = (uint32_t)i;
+  }
+}
+
+__global__ void flag_new_u64_kernel(const uint64_t* __restrict__ skeys, int64_t n, uint32_t* __restrict__ flag) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) flag[p] = (p > 0 && skeys[p] != skeys[p - 1]) ? 1u : 0u;
+}
+
+__global__ void scatter_dense_kernel(const uint32_t* __restrict__ dense, const uint32_t* __restrict__ sidx, int64_t n,
+                                     uint32_t* __restrict__ R) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) R[sidx[p]] = dense[p];
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n,
+                                  uint32_t* __restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) out[p] = src[perm[p]];
+}
+
+// flag[p] = 1 iff the vector at sorted position p differs from the one at p-1
+__global__ void flag_new_vec_kernel(const uint32_t* __restrict__ R, const uint32_t* __restrict__ perm, int64_t n, int M,
+                                    uint32_t* __restrict__ flag) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t f = 0;
+  if (p > 0) {
+    uint32_t a = perm[p], b = perm[p - 1];
+    for (int j = 0; j < M; ++j) f |= (R[(int64_t)j * n + a] != R[(int64_t)j * n + b]) ? 1u : 0u;
+  }
+  flag[p] = f;
+}
+
+// record words: [o_1 .. o_{M-1}, gid, rank+1, pad...]; padded to W = 4*ceil((M+1)/4) words
+__global__ void build_records_kernel(const uint32_t* __restrict__ R, const uint32_t* __restrict__ perm,
+                                     const uint32_t* __restrict__ gid, int64_t n, int64_t npad, int M, int W,
+                                     uint32_t* __restrict__ rec) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npad) return;
+  uint32_t* r = rec + p * W;
+  if (p < n) {
+    uint32_t i = perm[p];
+    for (int j = 1; j < M; ++j) r[j - 1] = R[(int64_t)j * n + i];
+    r[M - 1] = gid[p];
+    for (int w = M; w < W; ++w) r[w] = 0u;
+  } else {
+    // sentinel: larger than every real id in every objective, its own group; never dominates a real point
+    for (int j = 1; j < M; ++j) r[j - 1] = 0xFFFFFFFFu;
+    r[M - 1] = 0xFFFFFFFFu - (uint32_t)(p - n);
+    for (int w = M; w < W; ++w) r[w] = 0u;
+  }
+}
+
+template <int M, int T>
+__global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* done,
+                                                       int* ticket, int* errflag) {
+  constexpr int W = 4 * ((M + 1 + 3) / 4);
+  constexpr int NV = W / 4;
+  constexpr int NW = T / 32;
+  __shared__ uint4 tile[T * NV];
+  __shared__ int sh_r1[T];
+  __shared__ uint32_t sh_final[NW];
+  __shared__ int sh_blk;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (;;) {
+    if (tid == 0) sh_blk = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int b = sh_blk;
+    __syncthreads();
+    if (b >= nblocks) return;
+    const int64_t i = (int64_t)b * T + tid;
+
+    // ---- own record -> registers and shared tile
+    uint32_t v[W];
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(rec + i * W);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        uint4 a = src[q];
+        tile[tid * NV + q] = a;
+        v[4 * q + 0] = a.x;
+        v[4 * q + 1] = a.y;
+        v[4 * q + 2] = a.z;
+        v[4 * q + 3] = a.w;
+      }
+    }
+    const uint32_t gidv = v[M - 1];
+    if (tid < NW) sh_final[tid] = 0u;
+    __syncthreads();
+
+    // ---- in-block dominator bitmask (sources earlier in the block); independent of any rank
+    uint32_t mask[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      uint32_t m = 0u;
+#pragma unroll
+      for (int s = 0; s < 32; ++s) {
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s) * NV]);
+        bool dom = (w * 32 + s < tid) && (sp[M - 1] != gidv);
+#pragma unroll
+        for (int j = 0; j < M - 1; ++j) dom = dom && (sp[j] <= v[j]);
+        m |= (dom ? 1u : 0u) << s;
+      }
+      mask[w] = m;
+    }
+    __syncthreads();
+
+    // ---- stream every earlier block: best = max over dominators of (rank + 1)
+    int best = 0;
+    for (int k = 0; k < b; ++k) {
+      if (tid == 0) {
+        unsigned spins = 0;
+        while (ld_acquire_gpu(done + k) == 0) {
+          __nanosleep(40);
+          if ((++spins & 0xFFFu) == 0u) {
+            if (spins > (1u << 22) || ld_acquire_gpu(errflag) != 0) {
+              atomicExch(errflag, 1);
+              break;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)k * T * W);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) tile[tid * NV + q] = __ldcg(src + tid * NV + q);
+      }
+      __syncthreads();
+#pragma unroll 16
+      for (int s = 0; s < T; ++s) {
+        uint32_t sw[W];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          uint4 a = tile[s * NV + q];
+          sw[4 * q + 0] = a.x;
+          sw[4 * q + 1] = a.y;
+          sw[4 * q + 2] = a.z;
+          sw[4 * q + 3] = a.w;
+        }
+        bool dom = (sw[M - 1] != gidv);
+#pragma unroll
+        for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
+        const int r1 = (int)sw[M];
+        best = dom ? max(best, r1) : best;
+      }
+      __syncthreads();
+    }
+
+    // ---- resolve the in-block chain: a target is final once all its in-block dominators are
+    bool fin = false;
+    int myrank = 0;
+    for (int round = 0; round <= T; ++round) {
+      bool ready = !fin;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) ready = ready && ((mask[w] & ~sh_final[w]) == 0u);
+      if (ready) {
+        int r = best;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          uint32_t m = mask[w];
+          while (m) {
+            int s = __ffs(m) - 1;
+            m &= m - 1;
+            r = max(r, sh_r1[w * 32 + s]);
+          }
+        }
+        myrank = r;
+        sh_r1[tid] = r + 1;
+        fin = true;
+      }
+      const unsigned newly = __ballot_sync(0xffffffffu, ready);
+      __syncthreads();
+      if (lane == 0 && newly) sh_final[warp] |= newly;
+      if (__syncthreads_and(fin ? 1 : 0)) break;
+    }
+
+    // ---- publish
+    rec[i * W + M] = (uint32_t)(myrank + 1);
+    rankS[i] = myrank;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu(done + b, 1);
+  }
+}
+
+__global__ void scatter_rank_kernel(const int* __restrict__ rankS, const uint32_t* __restrict__ perm, int64_t n,
+                                    int32_t* __restrict__ rank) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) rank[perm[p]] = rankS[p];
+}
+
+__global__ void copy_u32_to_i32_kernel(const uint32_t* __restrict__ a, int64_t n, int32_t* __restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) out[p] = (int32_t)a[p];
+}
+
+template <int M>
+int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* done, int* ticket, int* errflag) {
+  int occ = 0;
+  DMO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_chain_kernel<M, RANK_T>, RANK_T, 0));
+  if (occ < 1) occ = 1;
+  int grid = nblocks < occ * ctx->sm_count ? nblocks : occ * ctx->sm_count;
+  ProfileScope ps(ctx, "rank_chain");
+  DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), grid, RANK_T, 0, rec, nblocks, rankS, done, ticket, errflag);
+  DMO_CHECK_LAUNCH();
+  return DMO_OK;
+}
+
+int bits_for(int64_t n) {
+  int b = 1;
+  while (((int64_t)1 << b) < n) ++b;
+  return b;
+}
+
+}  // namespace
+
+int rank_nd_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_rank) {
+  if (n <= 0) return DMO_OK;
+  DMO_REQUIRE(M >= 1 && M <= 8, "rank_nd: M=%d out of range [1,8]", M);
+  DMO_REQUIRE(n < ((int64_t)1 << 31) - 4096, "rank_nd: n too large");
+  const unsigned g = (unsigned)ceil_div(n, 256);
+
+  DevBuf<uint32_t> R;  // M x n dense integer ids (SoA)
+  DMO_TRY(R.alloc(ctx, (size_t)M * n));
+  {
+    DevBuf<uint64_t> k0, k1;
+    DevBuf<uint32_t> i0, i1, flag, dense;
+    DMO_TRY(k0.alloc(ctx, n));
+    DMO_TRY(k1.alloc(ctx, n));
+    DMO_TRY(i0.alloc(ctx, n));
+    DMO_TRY(i1.alloc(ctx, n));
+    DMO_TRY(flag.alloc(ctx, n));
+    DMO_TRY(dense.alloc(ctx, n));
+    for (int j = 0; j < M; ++j) {
+      DMO_LAUNCH(col_keys_kernel, g, 256, 0, dY, n, M, j, k0.p, i0.p);
+      DMO_TRY(prim_sort_pairs_u64(ctx, k0.p, k1.p, i0.p, i1.p, n, 0, 64));
+      DMO_LAUNCH(flag_new_u64_kernel, g, 256, 0, k1.p, n, flag.p);
+      DMO_TRY(prim_inclusive_sum_u32(ctx, flag.p, dense.p, n));
+      DMO_LAUNCH(scatter_dense_kernel, g, 256, 0, dense.p, i1.p, n, R.p + (size_t)j * n);
+    }
+    DMO_CHECK_LAUNCH();
+  }
+  if (M == 1) {
+    DMO_LAUNCH(copy_u32_to_i32_kernel, g, 256, 0, R.p, n, d_rank);
+    DMO_CHECK_LAUNCH();
+    return DMO_OK;
+  }
+
+  // lexicographic order of the id vectors: LSD passes, least significant objective first
+  const int bits = bits_for(n);
+  DevBuf<uint32_t> permA, permB, keyA, keyB;
+  DMO_TRY(permA.alloc(ctx, n));
+  DMO_TRY(permB.alloc(ctx, n));
+  DMO_TRY(keyA.alloc(ctx, n));
+  DMO_TRY(keyB.alloc(ctx, n));
+  DMO_TRY(prim_iota_u32(ctx, permA.p, n));
+  uint32_t* pin = permA.p;
+  uint32_t* pout = permB.p;
+  for (int j = M - 1; j >= 0; --j) {
+    DMO_LAUNCH(gather_u32_kernel, g, 256, 0, R.p + (size_t)j * n, pin, n, keyA.p);
+    DMO_TRY(prim_sort_pairs_u32(ctx, keyA.p, keyB.p, pin, pout, n, 0, bits));
+    uint32_t* t = pin;
+    pin = pout;
+    pout = t;
+  }
+  const uint32_t* perm = pin;
+
+  // group ids (identical vectors share one)
+  DevBuf<uint32_t> gid;
+  DMO_TRY(gid.alloc(ctx, n));
+  DMO_LAUNCH(flag_new_vec_kernel, g, 256, 0, R.p, perm, n, M, keyA.p);
+  DMO_TRY(prim_inclusive_sum_u32(ctx, keyA.p, gid.p, n));
+
+  const int W = 4 * ((M + 1 + 3) / 4);
+  const int64_t nblocks = ceil_div(n, RANK_T);
+  const int64_t npad = nblocks * RANK_T;
+  DevBuf<uint32_t> rec;
+  DevBuf<int> rankS, sync;
+  DMO_TRY(rec.alloc(ctx, (size_t)npad * W));
+  DMO_TRY(rankS.alloc(ctx, npad));
+  DMO_TRY(sync.alloc(ctx, nblocks + 2));
+  DMO_CUDA(cudaMemsetAsync(sync.p, 0, (nblocks + 2) * sizeof(int), ctx->stream));
+  DMO_LAUNCH(build_records_kernel, (unsigned)ceil_div(npad, 256), 256, 0, R.p, perm, gid.p, n, npad, M, W, rec.p);
+  int* done = sync.p;
+  int* ticket = sync.p + nblocks;
+  int* errflag = sync.p + nblocks + 1;
+  switch (M) {
+    case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
+    case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
+    case 4: DMO_TRY(launch_chain<4>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
+    case 5: DMO_TRY(launch_chain<5>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
+    case 6: DMO_TRY(launch_chain<6>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
+    case 7: DMO_TRY(launch_chain<7>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
+    default: DMO_TRY(launch_chain<8>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
+  }
+  DMO_LAUNCH(scatter_rank_kernel, g, 256, 0, rankS.p, perm, n, d_rank);
+  DMO_CHECK_LAUNCH();
+  int herr = 0;
+  DMO_CUDA(cudaMemcpyAsync(&herr, errflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (herr) return dmo_fail(ctx, DMO_ERR_INTERNAL, "rank_nd: chain kernel watchdog tripped");
+  return DMO_OK;
+}
+
+extern "C" int dmo_rank_nd(dmo_ctx* ctx, const double* Y, int64_t n, int M, int32_t* rank) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(n >= 0 && M >= 1, "rank_nd: bad shape n=%lld M=%d", (long long)n, M);
+  if (n == 0) return DMO_OK;
+  DMO_REQUIRE(Y && rank, "rank_nd: null pointer");
+  In<double> y;
+  Out<int32_t> r;
+  DMO_TRY(y.init(ctx, Y, (size_t)n * M));
+  DMO_TRY(r.init(ctx, rank, (size_t)n));
+  DMO_TRY(rank_nd_device(ctx, y.d, n, M, r.d));
+  DMO_TRY(r.finish(ctx));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}

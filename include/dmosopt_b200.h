@@ -1,0 +1,198 @@
+/*
+ * dmosopt_b200 -- C ABI of the B200-native surrogate-generation hot path.
+ *
+ * The reference (dmosopt @ 5cd63e4c) is pure Python and has NO foreign-function
+ * interface; this header is new surface that sits directly under the Python
+ * plugin classes (dmosopt_b200.NSGA2 / AGEMOEA / SMPSO / CMAES, GPR_Matern ...)
+ * which dmosopt loads by import path (dmosopt/config.py:5-11,
+ * dmosopt/MOASMO.py:256-259,516-519).  Every entry point names the reference
+ * function it replaces (file:line relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C, no C++ / torch types; every function returns an int status
+ *     (DMO_OK == 0) and never throws; dmo_last_error(ctx) gives the message.
+ *   - matrices are row-major (C order), double unless stated; index outputs
+ *     are int64 (numpy intp), ranks int32.
+ *   - every array pointer may be HOST memory (pageable or pinned) or DEVICE
+ *     memory of the context's GPU; the library detects which
+ *     (cudaPointerGetAttributes) and stages host buffers through the
+ *     context's stream.  The caller owns all buffers; the library owns only
+ *     its context, its stream-ordered scratch memory and the objects it
+ *     creates (dmo_gp).
+ *   - one context per GPU and per calling thread (not re-entrant); all work is
+ *     issued on the context's own stream and calls return after the results
+ *     are in the caller's buffers (host outputs) or enqueued (device outputs;
+ *     call dmo_synchronize before reading them from another stream).
+ */
+#ifndef DMOSOPT_B200_H
+#define DMOSOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMO_OK 0
+#define DMO_ERR_CUDA 1        /* a CUDA runtime call or kernel failed           */
+#define DMO_ERR_ARG 2         /* bad shape / null pointer / unsupported size    */
+#define DMO_ERR_STATE 3       /* object used before it was initialised          */
+#define DMO_ERR_UNSUPPORTED 4 /* valid request that this build does not cover   */
+#define DMO_ERR_INTERNAL 5    /* watchdog / consistency check tripped           */
+
+/* distance metrics of MOEA.sortMO (dmosopt/MOEA.py:256-266) */
+#define DMO_METRIC_NONE 0
+#define DMO_METRIC_CROWDING 1  /* indicators.crowding_distance_metric  */
+#define DMO_METRIC_EUCLIDEAN 2 /* indicators.euclidean_distance_metric */
+
+/* stationary kernels of the sklearn surrogates (dmosopt/model.py:1227-1229, 1318-1320) */
+#define DMO_KERNEL_MATERN52 0
+#define DMO_KERNEL_RBF 1
+
+/* arithmetic used for the GP posterior variance contraction */
+#define DMO_GP_FP64 0   /* CUDA-core float64 everywhere: matches sklearn to ~1e-10               */
+#define DMO_GP_TENSOR 1 /* tcgen05 split-fp16 (3 MMAs / product), fp32 accumulate in TMEM        */
+
+typedef struct dmo_ctx dmo_ctx;
+typedef struct dmo_gp dmo_gp;
+
+/* ---- context ----------------------------------------------------------- */
+int dmo_version(void);
+int dmo_create(int device, dmo_ctx** out);
+int dmo_destroy(dmo_ctx* ctx);
+const char* dmo_last_error(dmo_ctx* ctx);
+int dmo_synchronize(dmo_ctx* ctx);
+void* dmo_stream(dmo_ctx* ctx);             /* the context's cudaStream_t */
+int64_t dmo_launch_count(dmo_ctx* ctx);     /* kernels launched by this context so far */
+int dmo_sm_count(dmo_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream (bench.py times kernels with it) */
+int dmo_timer_begin(dmo_ctx* ctx);
+int dmo_timer_end(dmo_ctx* ctx, float* elapsed_ms);
+/* pinned host memory for callers that want asynchronous staging */
+int dmo_host_alloc(void** out, uint64_t bytes);
+int dmo_host_free(void* p);
+/* device memory for callers that keep populations resident */
+int dmo_device_alloc(dmo_ctx* ctx, void** out, uint64_t bytes);
+int dmo_device_free(dmo_ctx* ctx, void* p);
+int dmo_memcpy(dmo_ctx* ctx, void* dst, const void* src, uint64_t bytes); /* any direction, stream ordered + sync */
+/* bytes staged so far between host buffers and the GPU by this context */
+int dmo_transfer_bytes(dmo_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
+/* per-kernel CUDA-event timers: enable(1) clears and starts recording, report() writes "name ms count" lines */
+int dmo_profile_enable(dmo_ctx* ctx, int on);
+int dmo_profile_report(dmo_ctx* ctx, char* buf, uint64_t cap);
+/* in-place float64 -> float32 -> float64 rounding of a device array (the reference's float32 state arrays,
+ * dmosopt/NSGA2.py:228-230 + dmosopt/MOASMO.py:64), for callers that keep the population resident */
+int dmo_round_f32(dmo_ctx* ctx, double* a, int64_t n);
+/* writes zeros through a scratch buffer larger than L2 (bench L2 flush) */
+int dmo_flush_l2(dmo_ctx* ctx);
+
+/* ---- A1/A2: non-dominated rank ------------------------------------------
+ * replaces dda.dda_ens (dmosopt/dda.py:97-152), the rank used by every sortMO.
+ * Y (n, M) -> rank (n,), the canonical Pareto front index; identical vectors are
+ * mutually non-dominating (dda.py:108-115).  Equal to dda_ens whenever
+ * objective 0 is tie-free.  1 <= M <= 8. */
+int dmo_rank_nd(dmo_ctx* ctx, const double* Y, int64_t n, int M, int32_t* rank);
+
+/* ---- A3/A4: distance metrics ---------------------------------------------
+ * replace indicators.crowding_distance_metric (dmosopt/indicators.py:12-51) and
+ * indicators.euclidean_distance_metric (:54-62).  Bit-identical float64. */
+int dmo_crowding_distance(dmo_ctx* ctx, const double* Y, int64_t n, int M, double* D);
+int dmo_euclidean_distance(dmo_ctx* ctx, const double* Y, int64_t n, int M, double* D);
+
+/* ---- A5: sortMO / orderMO / remove_worst ----------------------------------
+ * dmosopt/MOEA.py:242-347, 398-423.
+ * dmo_order_mo: perm = np.lexsort((-extra_k..., -ydist, rank)); outputs are in sorted
+ *   order.  extra_desc_keys: n_extra host-evaluated x-metrics (feasibility rank,
+ *   NSGA2.py:47-49), each (n,), least-significant first; may be NULL.
+ *   rank_sorted / dist_sorted may be NULL.
+ * dmo_remove_worst: the first `keep` rows of that order gathered from X (n,d) / Y (n,M). */
+int dmo_order_mo(dmo_ctx* ctx, const double* Y, int64_t n, int M, int metric,
+                 const double* const* extra_desc_keys, int n_extra,
+                 int64_t* perm, int32_t* rank_sorted, double* dist_sorted);
+int dmo_remove_worst(dmo_ctx* ctx, const double* X, const double* Y, int64_t n, int d, int M,
+                     int metric, const double* const* extra_desc_keys, int n_extra, int64_t keep,
+                     double* X_out, double* Y_out, int32_t* rank_out, int64_t* perm_out);
+
+/* ---- A6: tournament selection ---------------------------------------------
+ * replaces MOEA.tournament_selection (dmosopt/MOEA.py:375-395): candidates ordered by
+ * lexsort(metrics) (rank primary; AGE-MOEA adds -crowd_dist as secondary,
+ * AGEMOEA.py:140-142), P(i-th best) ~ p (1-p)^i, poolsize draws WITHOUT replacement.
+ * Implemented in log space (Gumbel-top-k), so it does not underflow for pop > 2150.
+ * crowd may be NULL.  u_out (pop,) optionally receives the uniforms used, in candidate
+ * order position (for distribution / replay tests). */
+int dmo_tournament(dmo_ctx* ctx, const int32_t* rank, const double* crowd, int64_t pop,
+                   int64_t poolsize, uint64_t seed, uint64_t stream_id,
+                   int64_t* pool_idx, double* u_out);
+
+/* ---- A7/A8: variation operators with explicit uniforms (kernel-level parity) ----
+ * MOEA.mutation (dmosopt/MOEA.py:191-212) and MOEA.crossover_sbx (:215-239) applied
+ * row-wise: parents / u / children (n, d); di_* / xlb / xub (d,). */
+int dmo_mutation_u(dmo_ctx* ctx, const double* parents, const double* u, int64_t n, int d,
+                   const double* di_mutation, const double* xlb, const double* xub,
+                   double mutation_rate, double* children);
+int dmo_sbx_u(dmo_ctx* ctx, const double* parent1, const double* parent2, const double* u,
+              int64_t n, int d, const double* di_crossover, const double* xlb, const double* xub,
+              double* child1, double* child2);
+
+/* ---- A9: NSGA-II / AGE-MOEA offspring generation ----------------------------
+ * replaces the serial loop of NSGA2.generate_strategy (dmosopt/NSGA2.py:142-178; same
+ * loop in AGEMOEA.py:144-180): iteration t emits an SBX pair w.p. crossover_prob and
+ * then a mutant w.p. mutation_prob, until count >= popsize-1.  The control flow is
+ * planned in parallel from counter-based Philox4x32-10 draws (seed, stream_id).
+ * pop_x (npop, d); pool_idx (poolsize,) rows of pop_x forming the mating pool.
+ * x_gen has room for popsize+1 rows; child_kind (popsize+1,) gets 0/1 = SBX child 1/2,
+ * 2 = mutant; n_children the number of rows produced.
+ * draws (optional, may be NULL): receives the random draws actually used so the CPU
+ * oracle can replay them: layout documented in dmosopt_b200/_lib.py (nsga2_generate). */
+int dmo_nsga2_generate(dmo_ctx* ctx, const double* pop_x, int64_t npop, int d,
+                       const int64_t* pool_idx, int64_t poolsize, int64_t popsize,
+                       double crossover_prob, double mutation_prob, double mutation_rate,
+                       const double* di_crossover, const double* di_mutation,
+                       const double* xlb, const double* xub, uint64_t seed, uint64_t stream_id,
+                       double* x_gen, int32_t* child_kind, int64_t* n_children, double* draws);
+
+/* ---- A18: exact-GP posterior (GPR_Matern / GPR_RBF predict) -------------------
+ * replaces GPR_Matern.predict / .evaluate (dmosopt/model.py:1254-1275; GPR_RBF :1343-1364),
+ * i.e. per objective sklearn GaussianProcessRegressor.predict(return_std=True) ** 2.
+ * dmo_gp_create uploads the posterior state once per epoch:
+ *   X_train (N,d) normalised inputs; alpha (M,N); L (M,N,N) lower Cholesky factors of
+ *   K + noise I (factor_is_inverse = 0) or their inverses L^-1 (factor_is_inverse = 1);
+ *   constant (M,), length_scale (M,d) (isotropic = the scalar repeated), noise (M,),
+ *   y_mean (M,), y_std (M,), xlb / xub (d,) raw input bounds.
+ * dmo_gp_predict: X (P,d) raw inputs -> mean (P,M), var (P,M) (var may be NULL). */
+int dmo_gp_create(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const double* X_train,
+                  const double* alpha, const double* factor, int factor_is_inverse,
+                  const double* constant, const double* length_scale, const double* noise,
+                  const double* y_mean, const double* y_std, const double* xlb, const double* xub,
+                  dmo_gp** out);
+int dmo_gp_destroy(dmo_ctx* ctx, dmo_gp* gp);
+int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double* mean,
+                   double* var, int precision);
+
+/* ---- A16: exact hypervolume ---------------------------------------------------
+ * replaces hv.AdaptiveHyperVolume.compute_hypervolume(..., 'box') (dmosopt/hv.py:123-189)
+ * -> HyperVolumeBoxDecomposition.compute_hypervolume (dmosopt/hv_box_decomposition.py:86-304)
+ * and indicators.Hypervolume._do (dmosopt/indicators.py:244-256).  Minimisation; points not
+ * strictly inside ref are ignored (hv.py:159).  True hypervolume (see DESIGN.md for the
+ * reference's <=0-coordinate defect).  1 <= M <= 5 (M >= 4 is O(n^(M-1))). */
+int dmo_hypervolume(dmo_ctx* ctx, const double* F, int64_t n, int M, const double* ref, double* out);
+
+/* ---- A17: HV-improvement (EHVI) candidate selection -----------------------------
+ * replaces indicators.HypervolumeImprovement._do (dmosopt/indicators.py:295-313) ->
+ * HyperVolumeBoxDecomposition.select_candidates / _compute_batch_ehvi /
+ * _decompose_dominated_space (dmosopt/hv_box_decomposition.py:306-437).
+ * F (nf,M): the chosen set (its rank-0 subset is taken when nds != 0); means / variances (nc,M);
+ * sel (k,) indices of the k largest scores (ties by index); score (nc,) may be NULL. */
+int dmo_ehvi_select(dmo_ctx* ctx, const double* F, int64_t nf, const double* means,
+                    const double* variances, int64_t nc, int M, const double* ref, int nds,
+                    int64_t k, int64_t* sel, double* score);
+
+/* ---- A21: duplicate rows ---------------------------------------------------------
+ * replaces MOEA.get_duplicates (dmosopt/MOEA.py:426-437) at its default eps = 1e-16:
+ * is_dup[i] = 1 iff an earlier row j < i has ||x_i - x_j||_2 <= eps. */
+int dmo_get_duplicates(dmo_ctx* ctx, const double* X, int64_t n, int d, double eps, uint8_t* is_dup);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMOSOPT_B200_H */

@@ -1,0 +1,147 @@
+"""Oracle-backed stand-in for ``dmosopt_b200._lib`` -- TEST SEAM ONLY.
+
+The product has no CPU path.  To exercise the *host* logic of the plugins (argument marshalling,
+state handling, dtype flow, the unmodified MOASMO.epoch driving them) in a container without a GPU,
+tests monkeypatch the thin ``_lib`` functions with these NumPy implementations built on ``oracle/``.
+"""
+
+import numpy as np
+
+from oracle import dda, gp, hv, indicators, moea, nsga2
+
+METRIC_NONE, METRIC_CROWDING, METRIC_EUCLIDEAN = 0, 1, 2
+
+
+def rank_nd(Y):
+    return dda.rank_canonical(np.asarray(Y, dtype=np.float64)).astype(np.intp)
+
+
+def crowding_distance(Y):
+    return indicators.crowding_distance_metric(np.asarray(Y, dtype=np.float64))
+
+
+def euclidean_distance(Y):
+    return indicators.euclidean_distance_metric(np.asarray(Y, dtype=np.float64))
+
+
+def _order(Y, metric, extra):
+    Y = np.asarray(Y, dtype=np.float64)
+    rank = rank_nd(Y)
+    keys = [-np.asarray(e, dtype=np.float64) for e in (extra or [])]
+    dist = None
+    if metric == METRIC_CROWDING:
+        dist = crowding_distance(Y)
+    elif metric == METRIC_EUCLIDEAN:
+        dist = euclidean_distance(Y)
+    if dist is not None:
+        keys.append(-dist)
+    perm = np.lexsort(keys + [rank])
+    return perm, rank, dist
+
+
+def order_mo(Y, metric=METRIC_NONE, extra_desc_keys=None):
+    perm, rank, dist = _order(Y, metric, extra_desc_keys)
+    return perm.astype(np.int64), rank[perm], (None if dist is None else dist[perm])
+
+
+def remove_worst(X, Y, keep, metric=METRIC_NONE, extra_desc_keys=None):
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    perm, rank, _ = _order(Y, metric, extra_desc_keys)
+    perm = perm[:keep]
+    return X[perm], Y[perm], rank[perm], perm.astype(np.int64)
+
+
+def _rng(seed, stream_id):
+    return np.random.default_rng([int(seed) & (2**63 - 1), int(stream_id)])
+
+
+def tournament(rank, poolsize, seed, stream_id, crowd=None, return_uniforms=False):
+    rank = np.asarray(rank)
+    u = _rng(seed, stream_id).random(rank.shape[0])
+    u = np.clip(u, 1e-300, 1 - 1e-16)
+    metrics = (rank,) if crowd is None else (-np.asarray(crowd), rank)
+    pool = moea.tournament_selection_gumbel(u, poolsize, *metrics).astype(np.int64)
+    return (pool, u) if return_uniforms else pool
+
+
+def mutation_u(parents, u, di_mutation, xlb, xub, mutation_rate):
+    return moea.mutation_u(np.atleast_2d(parents), np.atleast_2d(u), di_mutation, np.asarray(xlb), np.asarray(xub), mutation_rate)
+
+
+def sbx_u(parent1, parent2, u, di_crossover, xlb, xub):
+    return moea.crossover_sbx_u(np.atleast_2d(parent1), np.atleast_2d(parent2), np.atleast_2d(u), di_crossover, np.asarray(xlb), np.asarray(xub))
+
+
+def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, mutation_rate, di_crossover, di_mutation, xlb, xub, seed, stream_id, return_draws=False):
+    pop_x = np.asarray(pop_x, dtype=np.float64)
+    d = pop_x.shape[1]
+    T = 2 * popsize + 64
+    r = _rng(seed, stream_id)
+    poolsize = len(pool_idx)
+    u_cross, u_mut = r.random(T), r.random(T)
+    i1 = r.integers(0, poolsize, size=T)
+    i2 = r.integers(0, max(poolsize - 1, 1), size=T)
+    i2 = np.where(i2 >= i1, i2 + 1, i2) if poolsize > 1 else i2
+    pair = np.stack((i1, i2), axis=1)
+    single = r.integers(0, poolsize, size=T)
+    u_genes = r.random((T, 2, d))
+    pool = pop_x[np.asarray(pool_idx)]
+    x_gen, cidx, midx = nsga2.generate_given_draws(pool, u_cross, u_mut, pair, single, u_genes, popsize, np.asarray(di_crossover), np.asarray(di_mutation),
+                                                   np.asarray(xlb), np.asarray(xub), mutation_rate, crossover_prob, mutation_prob)
+    kind = np.full(x_gen.shape[0], 2, dtype=np.int32)
+    kind[cidx[0::2]] = 0
+    kind[cidx[1::2]] = 1
+    if return_draws:
+        return x_gen, kind, {"u_cross": u_cross, "u_mut": u_mut, "pair": pair, "single": single, "u_genes": u_genes}
+    return x_gen, kind
+
+
+class GPHandle:
+    def __init__(self, X_train, alpha, factor, constant, length_scale, noise, y_mean, y_std, xlb, xub, kernel=0, factor_is_inverse=False):
+        assert not factor_is_inverse
+        self.st = gp.GPState(X_train=np.asarray(X_train, float), xlb=np.asarray(xlb, float), xub=np.asarray(xub, float))
+        self.M = len(alpha)
+        for m in range(self.M):
+            self.st.objectives.append(gp.GPObjective(np.asarray(alpha[m]), np.asarray(factor[m]), float(constant[m]), np.asarray(length_scale[m]),
+                                                     float(noise[m]), float(y_mean[m]), float(y_std[m]), int(kernel)))
+
+    def predict(self, X, return_var=True, precision=0):
+        mean, var = gp.predict(self.st, X)
+        return mean, (var if return_var else None)
+
+    def close(self):
+        pass
+
+
+def hypervolume(F, ref):
+    return hv.hypervolume(np.atleast_2d(F), ref)
+
+
+def ehvi_select(F, means, variances, ref, k, nds=True, return_scores=False):
+    F = np.asarray(F, dtype=np.float64)
+    if nds:
+        r0 = dda.rank_canonical(F)
+        if np.any(r0 == 0):
+            F = F[r0 == 0]
+    sel, score = hv.select_candidates(F, means, variances, ref, k)
+    return (sel.astype(np.int64), score) if return_scores else sel.astype(np.int64)
+
+
+def get_duplicates(X, eps=1e-16):
+    return moea.get_duplicates(X, eps)
+
+
+FUNCTIONS = ["rank_nd", "crowding_distance", "euclidean_distance", "order_mo", "remove_worst", "tournament", "mutation_u", "sbx_u",
+             "nsga2_generate", "GPHandle", "hypervolume", "ehvi_select", "get_duplicates"]
+
+
+def install(monkeypatch):
+    """Patch dmosopt_b200._lib in place for one test."""
+    import sys
+
+    from dmosopt_b200 import _lib
+
+    me = sys.modules[__name__]
+    for name in FUNCTIONS:
+        monkeypatch.setattr(_lib, name, getattr(me, name))

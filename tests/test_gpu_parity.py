@@ -1,0 +1,380 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference's golden vectors.
+
+Bars (BASELINE.json north_star): bit-exact front membership / rank indices / permutations; GP posterior and
+hypervolume within 1e-5 relative (the float64 path is held to far tighter bounds, written at each assert).
+"""
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, sort_rows
+from oracle import dda, gp, hv, indicators, moea, nsga2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from dmosopt_b200 import _lib
+
+    _lib.context()
+    return _lib
+
+
+def cases(g):
+    return range(int(g["ncases"]))
+
+
+# ------------------------------------------------------------------------------------------ A1/A2 rank
+def test_rank_golden(L):
+    g = load_golden("dda")
+    assert list(L.rank_nd(g["ex_Y"])) == [0, 2, 1, 1, 0, 0]  # reference tests/test_dda.py:162-171
+    for k in cases(g):
+        Y = g[f"c{k}_Y"]
+        r = L.rank_nd(Y)
+        assert np.array_equal(r, g[f"c{k}_rank_ns"]), k  # canonical rank: always
+        if len(np.unique(Y[:, 0])) == len(np.unique(Y, axis=0)):
+            assert np.array_equal(r, g[f"c{k}_rank"]), k  # == dda_ens when objective 0 is tie-free
+    assert list(L.rank_nd(g["quirk_Y"])) == [1, 0]
+
+
+@pytest.mark.parametrize("n,M", [(1, 2), (2, 3), (127, 2), (128, 3), (129, 3), (1000, 2), (3000, 3), (2500, 4), (2000, 5), (1500, 8), (777, 1)])
+def test_rank_random_vs_oracle(L, n, M):
+    rng = np.random.default_rng(n * 10 + M)
+    Y = rng.random((n, M))
+    assert np.array_equal(L.rank_nd(Y), dda.rank_canonical(Y))
+
+
+def test_rank_edge_cases(L):
+    rng = np.random.default_rng(3)
+    # all identical -> one front
+    Y = np.tile(rng.random((1, 3)), (300, 1))
+    assert np.all(L.rank_nd(Y) == 0)
+    # a total order (worst case for the chain): ranks 0..n-1, shuffled input
+    n = 1500
+    base = np.arange(n, dtype=np.float64)
+    perm = rng.permutation(n)
+    Y = np.column_stack((base, base * 2.0, base + 0.5))[perm]
+    assert np.array_equal(L.rank_nd(Y), perm)
+    # heavy ties (integer grid) and negative / signed-zero values
+    Y = rng.integers(-2, 3, size=(800, 3)).astype(np.float64)
+    Y[Y == 0] = -0.0
+    assert np.array_equal(L.rank_nd(Y), dda.rank_canonical(Y))
+    # float32-rounded parents stacked with float64 children (MOASMO dtype flow)
+    Yp = rng.random((400, 2)).astype(np.float32).astype(np.float64)
+    Yc = rng.random((400, 2))
+    Y = np.vstack((Yc, Yp))
+    assert np.array_equal(L.rank_nd(Y), dda.rank_canonical(Y))
+    # near-single-front sphere
+    x = rng.random((2000, 3))
+    Y = x / np.linalg.norm(x, axis=1, keepdims=True) * (1 + 1e-3 * rng.random((2000, 1)))
+    assert np.array_equal(L.rank_nd(Y), dda.rank_canonical(Y))
+
+
+def test_rank_full_size_property(L):
+    """BASELINE config C3 merged set: n = 131072, M = 3; checked through the chain identity on a sample."""
+    rng = np.random.default_rng(20260921)
+    n, M = 131072, 3
+    Y = rng.random((n, M))
+    r = L.rank_nd(Y)
+    assert r.min() == 0
+    idx = rng.choice(n, size=300, replace=False)
+    for i in idx:
+        dom = np.all(Y <= Y[i], axis=1) & np.any(Y < Y[i], axis=1)
+        expect = (r[dom].max() + 1) if dom.any() else 0
+        assert r[i] == expect
+    # every front index up to the maximum is populated
+    assert len(np.unique(r)) == r.max() + 1
+
+
+# ------------------------------------------------------------------------------------------ A3/A4
+def test_distance_metrics_golden_bit_exact(L):
+    g = load_golden("distance")
+    for k in cases(g):
+        Y = g[f"c{k}_Y"]
+        assert np.array_equal(L.crowding_distance(Y), g[f"c{k}_crowd"]), k
+        assert np.array_equal(L.euclidean_distance(Y), g[f"c{k}_eucl"]), k
+
+
+@pytest.mark.parametrize("n,M", [(5000, 2), (20000, 3), (9999, 5), (300, 8)])
+def test_distance_metrics_random_bit_exact(L, n, M):
+    rng = np.random.default_rng(n + M)
+    Y = rng.standard_normal((n, M)) * rng.uniform(0.1, 100, size=(1, M))
+    assert np.array_equal(L.crowding_distance(Y), indicators.crowding_distance_metric(Y))
+    assert np.array_equal(L.euclidean_distance(Y), indicators.euclidean_distance_metric(Y))
+
+
+# ------------------------------------------------------------------------------------------ A5
+def test_sortmo_golden(L):
+    g = load_golden("sortmo")
+    codes = {"none": L.METRIC_NONE, "crowding": L.METRIC_CROWDING, "euclidean": L.METRIC_EUCLIDEAN}
+    for k in cases(g):
+        code = codes[str(g[f"c{k}_metric"])]
+        x, y, pop = g[f"c{k}_x"], g[f"c{k}_y"], int(g[f"c{k}_pop"])
+        perm, rank, dist = L.order_mo(y, code)
+        assert np.array_equal(perm, g[f"c{k}_perm_full"]), k
+        assert np.array_equal(rank, g[f"c{k}_rank_full"]), k
+        xs, ys, rk, pm = L.remove_worst(x, y, pop, code)
+        assert np.array_equal(xs, g[f"c{k}_xs"]) and np.array_equal(ys, g[f"c{k}_ys"])
+        assert np.array_equal(rk, g[f"c{k}_rank"]) and np.array_equal(pm, g[f"c{k}_perm"])
+
+
+def test_sortmo_extra_keys_and_stability(L):
+    rng = np.random.default_rng(8)
+    n = 3000
+    y = rng.integers(0, 5, size=(n, 2)).astype(float)  # many equal ranks -> stability matters
+    extra = rng.integers(0, 3, size=n).astype(float)
+    perm, rank, _ = L.order_mo(y, L.METRIC_NONE, [extra])
+    r = dda.rank_canonical(y)
+    assert np.array_equal(perm, np.lexsort((-extra, r)))
+    perm2, _, dist = L.order_mo(y, L.METRIC_EUCLIDEAN, [extra])
+    e = indicators.euclidean_distance_metric(y)
+    assert np.array_equal(perm2, np.lexsort((-extra, -e, r)))
+
+
+# ------------------------------------------------------------------------------------------ A7/A8
+def test_variation_operators_golden(L):
+    g = load_golden("variation")
+    for k in cases(g):
+        xlb, xub = g[f"c{k}_xlb"], g[f"c{k}_xub"]
+        mut = L.mutation_u(g[f"c{k}_p1"], g[f"c{k}_um"], g[f"c{k}_dim"], xlb, xub, float(g[f"c{k}_rate"]))
+        np.testing.assert_allclose(mut, g[f"c{k}_mut"], rtol=1e-13, atol=1e-15)
+        c1, c2 = L.sbx_u(g[f"c{k}_p1"], g[f"c{k}_p2"], g[f"c{k}_uc"], g[f"c{k}_dic"], xlb, xub)
+        np.testing.assert_allclose(c1, g[f"c{k}_c1"], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(c2, g[f"c{k}_c2"], rtol=1e-13, atol=1e-15)
+
+
+# ------------------------------------------------------------------------------------------ A6
+def test_tournament_replay_and_distribution(L):
+    g = load_golden("tournament")
+    for k in cases(g):
+        rank, crowd, pool = g[f"c{k}_rank"], g[f"c{k}_crowd"], int(g[f"c{k}_pool"])
+        pop = rank.shape[0]
+        trials = 4000
+        cnt = np.zeros(pop)
+        cnt2 = np.zeros(pop)
+        for t in range(trials):
+            idx, u = L.tournament(rank, pool, seed=1234 + k, stream_id=t, return_uniforms=True)
+            if t < 50:  # exact replay of the kernel's own uniforms on the oracle
+                assert np.array_equal(idx, moea.tournament_selection_gumbel(u, pool, rank))
+                assert len(set(idx.tolist())) == pool and np.all((u > 0) & (u < 1))
+            cnt[idx] += 1
+            cnt2[L.tournament(rank, pool, seed=99 + k, stream_id=t, crowd=crowd)] += 1
+        tol = 4.5 * 0.5 / np.sqrt(trials)
+        assert np.max(np.abs(cnt / trials - g[f"c{k}_freq_rank"])) < tol, k
+        assert np.max(np.abs(cnt2 / trials - g[f"c{k}_freq_rank_crowd"])) < tol, k
+    # reproducible, and scales past the reference's pop ~ 2150 limit
+    rank = np.random.default_rng(0).integers(0, 50, size=65536)
+    a = L.tournament(rank, 32768, 7, 1)
+    b = L.tournament(rank, 32768, 7, 1)
+    assert np.array_equal(a, b) and len(np.unique(a)) == 32768
+    order = np.lexsort((rank,))
+    pos = np.empty(65536, dtype=int)
+    pos[order] = np.arange(65536)
+    assert pos[a].max() < 32768 + 200  # the pool is the better half up to a short geometric tail
+
+
+# ------------------------------------------------------------------------------------------ A9
+def test_nsga2_generate_replay_against_oracle(L):
+    rng = np.random.default_rng(11)
+    for pop, d in [(40, 6), (201, 30), (64, 12)]:
+        xlb, xub = -rng.random(d), 1 + rng.random(d)
+        pop_x = xlb + rng.random((pop, d)) * (xub - xlb)
+        pool_idx = rng.permutation(pop)[: pop // 2]
+        dic, dim = np.full(d, 1.0), np.full(d, 20.0)
+        x_gen, kind, dr = L.nsga2_generate(pop_x, pool_idx, pop, 0.9, 0.1, 1.0 / d, dic, dim, xlb, xub, seed=5, stream_id=3, return_draws=True)
+        xo, cidx, midx = nsga2.generate_given_draws(pop_x[pool_idx], dr["u_cross"], dr["u_mut"], dr["pair"], dr["single"], dr["u_genes"], pop, dic, dim,
+                                                    xlb, xub, 1.0 / d)
+        assert x_gen.shape == xo.shape and pop - 1 <= x_gen.shape[0] <= pop + 1
+        np.testing.assert_allclose(x_gen, xo, rtol=1e-13, atol=1e-15)
+        assert np.array_equal(np.flatnonzero(kind < 2), cidx) and np.array_equal(np.flatnonzero(kind == 2), midx)
+        assert np.all(dr["pair"][:, 0] != dr["pair"][:, 1])
+        assert dr["pair"].min() >= 0 and dr["pair"].max() < len(pool_idx)
+        # same (seed, stream) -> same offspring; another stream -> different
+        x2, _ = L.nsga2_generate(pop_x, pool_idx, pop, 0.9, 0.1, 1.0 / d, dic, dim, xlb, xub, seed=5, stream_id=3)
+        x3, _ = L.nsga2_generate(pop_x, pool_idx, pop, 0.9, 0.1, 1.0 / d, dic, dim, xlb, xub, seed=5, stream_id=4)
+        assert np.array_equal(x_gen, x2) and not np.array_equal(x_gen[:20], x3[:20])
+
+
+def test_nsga2_generate_count_distribution(L):
+    g = load_golden("nsga2")
+    rng = np.random.default_rng(2)
+    k = 0
+    pop = g[f"c{k}_init_px"].shape[0]
+    d = g[f"c{k}_init_px"].shape[1]
+    pop_x = rng.random((pop, d))
+    pool_idx = np.arange(pop // 2)
+    hist = np.zeros(pop + 2)
+    ncross = []
+    for t in range(1500):
+        xg, kind = L.nsga2_generate(pop_x, pool_idx, pop, 0.9, 0.1, 1.0 / d, np.ones(d), np.full(d, 20.0), np.zeros(d), np.ones(d), 77, t)
+        hist[xg.shape[0]] += 1
+        ncross.append(np.count_nonzero(kind == 0))
+    ref = g[f"c{k}_count_hist"] / g[f"c{k}_count_hist"].sum()
+    assert hist[: pop - 1].sum() == 0
+    assert np.max(np.abs(hist / hist.sum() - ref)) < 0.12
+    assert abs(np.mean(ncross) - float(g[f"c{k}_ncross_mean"])) < 0.03 * pop
+
+
+# ------------------------------------------------------------------------------------------ A18 GP
+def _handle_from_golden(L, g, k, inverse=False):
+    from scipy.linalg import solve_triangular
+
+    kind = L.KERNEL_MATERN52 if str(g[f"c{k}_kind"]) == "matern" else L.KERNEL_RBF
+    factor = g[f"c{k}_L"]
+    if inverse:
+        factor = np.stack([solve_triangular(Lm, np.eye(Lm.shape[0]), lower=True) for Lm in factor])
+    return L.GPHandle(g[f"c{k}_Xtrain"], g[f"c{k}_alpha"], factor, g[f"c{k}_const"], g[f"c{k}_ls"], g[f"c{k}_noise"], g[f"c{k}_ymean"],
+                      g[f"c{k}_ystd"], g[f"c{k}_xlb"], g[f"c{k}_xub"], kernel=kind, factor_is_inverse=inverse)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gp_predict_golden_fp64(L, inverse):
+    g = load_golden("gp")
+    for k in cases(g):
+        h = _handle_from_golden(L, g, k, inverse)
+        mean, var = h.predict(g[f"c{k}_xtest"])
+        scale = np.maximum(np.abs(g[f"c{k}_mean"]), g[f"c{k}_ystd"][None, :])
+        assert np.max(np.abs(mean - g[f"c{k}_mean"]) / scale) < 1e-8, k  # north-star bar: 1e-5
+        prior = (g[f"c{k}_const"] + g[f"c{k}_noise"]) * g[f"c{k}_ystd"] ** 2
+        assert np.max(np.abs(var - g[f"c{k}_var"]) / prior[None, :]) < 1e-8, k
+        big = g[f"c{k}_var"] > 1e-3 * prior[None, :]
+        assert np.max(np.abs(var - g[f"c{k}_var"])[big] / g[f"c{k}_var"][big]) < 1e-5, k
+        m2, v2 = h.predict(g[f"c{k}_xtest"], return_var=False)
+        assert v2 is None and np.array_equal(m2, mean)
+        h.close()
+
+
+def test_gp_predict_baseline_shape_vs_oracle(L):
+    """N_train = 4096, d = 30, M = 3 (BASELINE C3 model size), 700 candidates, fixed initial theta."""
+    rng = np.random.default_rng(20260921 + 3)
+    N, d, M, P = 4096, 30, 3, 700
+    xlb, xub = np.zeros(d), np.ones(d)
+    Xtr = rng.random((N, d))
+    g_ = ((Xtr[:, 2:] - 0.5) ** 2).sum(axis=1)
+    Ytr = np.column_stack(((1 + g_) * np.cos(Xtr[:, 0] * np.pi / 2) * np.cos(Xtr[:, 1] * np.pi / 2),
+                           (1 + g_) * np.cos(Xtr[:, 0] * np.pi / 2) * np.sin(Xtr[:, 1] * np.pi / 2), (1 + g_) * np.sin(Xtr[:, 0] * np.pi / 2)))
+    st = gp.fit_fixed(Xtr, Ytr, xlb, xub, 1.0, 0.5, 1e-6)
+    X = rng.random((P, d))
+    X[:8] = Xtr[:8] + 1e-3 * rng.standard_normal((8, d))
+    mean_o, var_o = gp.predict(st, X)
+    h = L.GPHandle(st.X_train, np.stack([o.alpha for o in st.objectives]), np.stack([o.L for o in st.objectives]), [o.constant for o in st.objectives],
+                   [np.full(d, float(o.length_scale)) for o in st.objectives], [o.noise for o in st.objectives], [o.y_mean for o in st.objectives],
+                   [o.y_std for o in st.objectives], xlb, xub)
+    mean, var = h.predict(X)
+    ystd = np.array([o.y_std for o in st.objectives])
+    assert np.max(np.abs(mean - mean_o) / np.maximum(np.abs(mean_o), ystd)) < 1e-8
+    prior = np.array([(o.constant + o.noise) * o.y_std**2 for o in st.objectives])
+    assert np.max(np.abs(var - var_o) / prior) < 1e-8
+    h.close()
+
+
+# ------------------------------------------------------------------------------------------ A16 HV
+def test_hv_known_answers_and_golden(L):
+    g = load_golden("hv")
+    for i in range(int(g["nka"])):
+        assert abs(L.hypervolume(g[f"ka{i}_P"], g[f"ka{i}_ref"]) - float(g[f"ka{i}_expected"])) < 1e-12
+    for k in cases(g):
+        P, ref = g[f"c{k}_P"], g[f"c{k}_ref"]
+        if P.shape[1] > 3:
+            continue
+        v = L.hypervolume(P, ref)
+        assert abs(v - float(g[f"c{k}_hv_adaptive"])) <= 1e-11 * max(1.0, abs(v)), k  # bar: 1e-5 relative
+    assert abs(L.hypervolume(g["quirk_P"], g["quirk_ref"]) - 4.0) < 1e-12  # true HV (reference gives 0)
+
+
+@pytest.mark.parametrize("n,M", [(400, 2), (5000, 2), (150, 3), (350, 3)])
+def test_hv_random_vs_oracle(L, n, M):
+    rng = np.random.default_rng(n + M)
+    x = rng.random((n, M))
+    P = x / np.linalg.norm(x, axis=1, keepdims=True) * (1 + 0.2 * rng.random((n, 1)))
+    P[: n // 10] = P[n // 2 : n // 2 + n // 10]  # duplicates
+    ref = np.full(M, 1.15)
+    v = L.hypervolume(P, ref)
+    assert abs(v - hv.hypervolume(P, ref)) <= 1e-11 * v
+
+
+def test_hv_edge_cases_and_properties(L):
+    assert L.hypervolume(np.array([[2.0, 2.0]]), np.array([1.0, 1.0])) == 0.0  # nothing inside ref
+    assert L.hypervolume(np.array([[1.0, 1.0, 1.0]]), np.array([1.0, 2.0, 2.0])) == 0.0  # on the boundary (hv.py:159 strict)
+    rng = np.random.default_rng(4)
+    # pop = 65536 on the DTLZ2 sphere (BASELINE C3 population): permutation invariance + monotonicity
+    x = rng.random((65536, 3))
+    P = x / np.linalg.norm(x, axis=1, keepdims=True)
+    ref = np.full(3, 1.1)
+    v = L.hypervolume(P, ref)
+    v_perm = L.hypervolume(P[rng.permutation(len(P))], ref)
+    assert abs(v - v_perm) <= 1e-12 * v
+    v_half = L.hypervolume(P[:30000], ref)
+    assert v_half <= v * (1 + 1e-14)
+    exact = 1.1**3 - np.pi / 6  # volume of the cube minus the unit-sphere octant: the front's limit
+    assert exact * 0.98 < v < exact
+
+
+# ------------------------------------------------------------------------------------------ A17 EHVI
+def test_ehvi_golden(L):
+    g = load_golden("ehvi")
+    for k in cases(g):
+        sel, score = L.ehvi_select(g[f"c{k}_chosen"], g[f"c{k}_cand"], g[f"c{k}_var"], g[f"c{k}_ref"], int(g[f"c{k}_k"]), nds=True, return_scores=True)
+        np.testing.assert_allclose(score, g[f"c{k}_ehvi"], rtol=1e-10, atol=1e-300)
+        assert np.array_equal(sel, g[f"c{k}_sel"]), k
+
+
+# ------------------------------------------------------------------------------------------ A21
+def test_duplicates(L):
+    g = load_golden("duplicates")
+    assert np.array_equal(L.get_duplicates(g["X"]), g["dup"])
+    rng = np.random.default_rng(6)
+    X = rng.random((5000, 12))
+    X[100:200] = X[3000:3100]
+    X[4000] = X[5]
+    assert np.array_equal(L.get_duplicates(X), moea.get_duplicates(X))
+
+
+# ------------------------------------------------------------------------------------------ plugins on the real library
+def test_nsga2_plugin_golden_sequence_on_gpu(L):
+    import dmosopt_b200 as b2
+
+    g = load_golden("nsga2")
+    for k in cases(g):
+        if bool(g[f"c{k}_ties"]):
+            continue
+        metric = str(g[f"c{k}_metric"])
+        metric = None if metric == "none" else metric
+        x0, y0 = g[f"c{k}_x0"], g[f"c{k}_y0"]
+        pop, d, M = g[f"c{k}_init_px"].shape[0], x0.shape[1], y0.shape[1]
+        bounds = np.column_stack((np.zeros(d), np.ones(d)))
+        opt = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=b2.Model(), distance_metric=metric)
+        opt.initialize_strategy(x0, y0, bounds, np.random.default_rng(1))
+        assert np.array_equal(opt.state.population_parm, g[f"c{k}_init_px"]) and np.array_equal(opt.state.rank, g[f"c{k}_init_rank"])
+        for gi in range(3):
+            st = {"crossover_indices": g[f"c{k}_g{gi}_cidx"], "mutation_indices": g[f"c{k}_g{gi}_midx"]}
+            opt.update(g[f"c{k}_g{gi}_xgen"], g[f"c{k}_g{gi}_ygen"], st)
+            assert np.array_equal(opt.state.population_parm, g[f"c{k}_g{gi}_px"]), (k, gi)
+            assert np.array_equal(opt.state.population_obj, g[f"c{k}_g{gi}_py"]), (k, gi)
+            assert np.array_equal(opt.state.rank, g[f"c{k}_g{gi}_rank"]), (k, gi)
+
+
+def test_surrogate_generation_loop_end_to_end(L):
+    """MOASMO.optimize's loop (dmosopt/MOASMO.py:92-122) with both plugins on the GPU: ZDT1, pop 200 (BASELINE C1)."""
+    import dmosopt_b200 as b2
+    from dmosopt_b200.driver import optimize
+
+    d, M, pop = 30, 2, 200
+    rng = np.random.default_rng(0)
+    xlb, xub = np.zeros(d), np.ones(d)
+
+    def zdt1(x):
+        g_ = 1.0 + 9.0 / (d - 1) * x[:, 1:].sum(axis=1)
+        return np.column_stack((x[:, 0], g_ * (1.0 - np.sqrt(x[:, 0] / g_))))
+
+    X = rng.random((300, d))
+    sm = b2.GPR_Matern(X, zdt1(X), d, M, xlb, xub, optimizer=None)
+    mdl = b2.Model(objective=sm)
+    opt = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=mdl, distance_metric=None)
+    res = optimize(20, opt, mdl, d, M, xlb, xub, popsize=pop, initial=(X.astype(np.float32), zdt1(X).astype(np.float32)), local_random=rng)
+    assert res.best_x.shape == (pop, d) and res.best_y.shape == (pop, M)
+    # the surrogate population must have improved: its predicted front dominates most of the initial sample
+    hv0 = L.hypervolume(zdt1(X), np.array([1.1, 8.0]))
+    hv1 = L.hypervolume(res.best_y.astype(np.float64), np.array([1.1, 8.0]))
+    assert hv1 > hv0
