@@ -287,7 +287,7 @@ def run_ours(args):
 
     def plugin_step():
         x_gen, st = opt.generate()  # MOASMO.py:105
-        y_gen = sm_e2e.evaluate(x_gen)  # MOASMO.py:114
+        y_gen, y_var = sm_e2e.predict(x_gen)  # posterior mean AND variance, as the reference computes (model.py:1254-1268)
         opt.update(x_gen, y_gen, st)  # MOASMO.py:116
         _, py = opt.population_objectives  # termination criterion reads the population ... (MOASMO.py:93-97)
         return hv_ind.do(py.astype(np.float64)), x_gen.shape[0]  # ... and computes its hypervolume

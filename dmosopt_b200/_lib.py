@@ -351,7 +351,8 @@ def mutation_u(parents, u, di_mutation, xlb, xub, mutation_rate):
     n, d = parents.shape
     di = _f64(np.broadcast_to(np.asarray(di_mutation, dtype=np.float64), (d,)))
     out = np.empty((n, d), dtype=np.float64)
-    _check(load_library().dmo_mutation_u(context(), _ptr(parents), _ptr(u), n, d, _ptr(di), _ptr(_f64(xlb)), _ptr(_f64(xub)), float(mutation_rate), _ptr(out)), "dmo_mutation_u")
+    lb, ub = _f64(xlb), _f64(xub)  # named: the arrays must outlive the call
+    _check(load_library().dmo_mutation_u(context(), _ptr(parents), _ptr(u), n, d, _ptr(di), _ptr(lb), _ptr(ub), float(mutation_rate), _ptr(out)), "dmo_mutation_u")
     return out
 
 
@@ -363,7 +364,8 @@ def sbx_u(parent1, parent2, u, di_crossover, xlb, xub):
     di = _f64(np.broadcast_to(np.asarray(di_crossover, dtype=np.float64), (d,)))
     c1 = np.empty((n, d), dtype=np.float64)
     c2 = np.empty((n, d), dtype=np.float64)
-    _check(load_library().dmo_sbx_u(context(), _ptr(p1), _ptr(p2), _ptr(u), n, d, _ptr(di), _ptr(_f64(xlb)), _ptr(_f64(xub)), _ptr(c1), _ptr(c2)), "dmo_sbx_u")
+    lb, ub = _f64(xlb), _f64(xub)
+    _check(load_library().dmo_sbx_u(context(), _ptr(p1), _ptr(p2), _ptr(u), n, d, _ptr(di), _ptr(lb), _ptr(ub), _ptr(c1), _ptr(c2)), "dmo_sbx_u")
     return c1, c2
 
 
@@ -386,10 +388,11 @@ def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, muta
     draws = np.empty(T * (5 + 2 * d), dtype=np.float64) if return_draws else None
     dic = _f64(np.broadcast_to(np.asarray(di_crossover, dtype=np.float64), (d,)))
     dim = _f64(np.broadcast_to(np.asarray(di_mutation, dtype=np.float64), (d,)))
+    lb, ub = _f64(xlb), _f64(xub)
     _check(
         load_library().dmo_nsga2_generate(
             context(), _ptr(pop_x), npop, d, _ptr(pool_idx), pool_idx.shape[0], popsize, float(crossover_prob), float(mutation_prob),
-            float(mutation_rate), _ptr(dic), _ptr(dim), _ptr(_f64(xlb)), _ptr(_f64(xub)), int(seed) & (2**64 - 1), int(stream_id),
+            float(mutation_rate), _ptr(dic), _ptr(dim), _ptr(lb), _ptr(ub), int(seed) & (2**64 - 1), int(stream_id),
             _ptr(x_gen), _ptr(kind), _ptr(nch), _ptr(draws),
         ),
         "dmo_nsga2_generate",
@@ -423,11 +426,13 @@ class GPHandle:
         for m in range(M):
             ls[m, :] = np.asarray(length_scale[m], dtype=np.float64)
         self.N, self.d, self.M = N, d, M
+        cst, nz, ym, ys, lb, ub = _f64(constant), _f64(noise), _f64(y_mean), _f64(y_std), _f64(xlb), _f64(xub)
+        assert cst.shape == (M,) and nz.shape == (M,) and ym.shape == (M,) and ys.shape == (M,) and lb.shape == (d,) and ub.shape == (d,)
         h = _vp()
         _check(
             lib.dmo_gp_create(
-                context(), N, d, M, int(kernel), _ptr(X_train), _ptr(alpha), _ptr(factor), 1 if factor_is_inverse else 0, _ptr(_f64(constant)),
-                _ptr(ls), _ptr(_f64(noise)), _ptr(_f64(y_mean)), _ptr(_f64(y_std)), _ptr(_f64(xlb)), _ptr(_f64(xub)), ctypes.byref(h),
+                context(), N, d, M, int(kernel), _ptr(X_train), _ptr(alpha), _ptr(factor), 1 if factor_is_inverse else 0, _ptr(cst),
+                _ptr(ls), _ptr(nz), _ptr(ym), _ptr(ys), _ptr(lb), _ptr(ub), ctypes.byref(h),
             ),
             "dmo_gp_create",
         )
@@ -476,8 +481,9 @@ def ehvi_select(F, means, variances, ref, k, nds=True, return_scores=False):
     k = int(min(k, nc))
     sel = np.empty(k, dtype=np.int64)
     score = np.empty(nc, dtype=np.float64) if return_scores else None
+    ref = _f64(ref)
     _check(
-        load_library().dmo_ehvi_select(context(), _ptr(F), nf, _ptr(means), _ptr(variances), nc, M, _ptr(_f64(ref)), 1 if nds else 0, k, _ptr(sel), _ptr(score)),
+        load_library().dmo_ehvi_select(context(), _ptr(F), nf, _ptr(means), _ptr(variances), nc, M, _ptr(ref), 1 if nds else 0, k, _ptr(sel), _ptr(score)),
         "dmo_ehvi_select",
     )
     return (sel, score) if return_scores else sel

@@ -239,7 +239,8 @@ def test_gp_predict_golden_fp64(L, inverse):
         prior = (g[f"c{k}_const"] + g[f"c{k}_noise"]) * g[f"c{k}_ystd"] ** 2
         assert np.max(np.abs(var - g[f"c{k}_var"]) / prior[None, :]) < 1e-8, k
         big = g[f"c{k}_var"] > 1e-3 * prior[None, :]
-        assert np.max(np.abs(var - g[f"c{k}_var"])[big] / g[f"c{k}_var"][big]) < 1e-5, k
+        if big.any():
+            assert np.max(np.abs(var - g[f"c{k}_var"])[big] / g[f"c{k}_var"][big]) < 1e-5, k
         m2, v2 = h.predict(g[f"c{k}_xtest"], return_var=False)
         assert v2 is None and np.array_equal(m2, mean)
         h.close()
