@@ -329,7 +329,7 @@ int dmo_gp_create(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const doubl
   gp->d = d;
   gp->M = M;
   gp->kernel = kernel;
-  gp->Npad = ceil_div(N, VB) * VB;
+  gp->Npad = ceil_div(N, 256) * 256;  // multiple of the fp64 tile (128) and of the tensor path's Linv tile (256)
   gp->isotropic = true;
   std::vector<double> h_inv((size_t)M * d), h_rg(d);
   for (int m = 0; m < M; ++m)

@@ -18,7 +18,8 @@ struct dmo_gp {
   // tensor path (built lazily on first DMO_GP_TENSOR predict)
   bool tensor_ready = false;
   DevBuf<uint16_t> Lhi, Llo;  // (M, Npad, Npad) fp16 split of the row-scaled L^-1
-  DevBuf<float> Lscale;       // (M, Npad) power-of-two row scales
+  DevBuf<float> Lscale;       // (M, Npad) 1 / (row scale * K_* scale), powers of two
+  DevBuf<int> Kexp;           // (M,) K_* scaling exponents
 };
 
 int gp_predict_fp64(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var);

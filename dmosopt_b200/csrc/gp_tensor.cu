@@ -1,11 +1,562 @@
-// tcgen05 split-precision path of the GP posterior variance (placeholder until the kernel lands).
+// GP posterior variance on the 5th-generation tensor cores (DMO_GP_TENSOR).
+//
+//   ||L^-1 K_*^T||^2 per candidate  ==  row sums of  D^2,   D[p][i] = sum_k K_*[p][k] * Linv[i][k]
+//
+// D is a dense (candidates x N_train) x N_train contraction, both operands k-contiguous ("TN").  It runs as
+// tcgen05.mma kind::f16 with the accumulator in TMEM:
+//   * split precision: every float operand x is carried as two fp16 numbers hi + lo (22 significand bits) after an
+//     exact power-of-two scaling (per Linv row, per objective for K_*) that keeps both halves in fp16's normal range;
+//     D accumulates hi*hi + hi*lo + lo*hi in fp32 (three MMAs per product, the lo*lo term is below fp32 resolution);
+//   * A operand = K_* tile (128 candidates x 64 k), B operand = Linv tile (256 rows x 64 k), so one TMEM lane is one
+//     candidate and the epilogue's sum of squares is a private per-thread accumulation (no cross-lane reduction);
+//   * Linv is lower triangular: the row block [256 j, 256 j + 256) only needs k < 256 (j + 1) -- half the MMAs skipped;
+//   * operand tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 2-stage shared-memory ring, completion
+//     on mbarriers; one elected thread issues the MMAs; tcgen05.commit releases the ring slots and publishes the
+//     accumulator; four epilogue warps drain TMEM with tcgen05.ld while the next row block is being multiplied
+//     (two accumulator buffers of 256 columns);
+//   * persistent CTAs (one per SM) walk the (objective, candidate block) work list.
+//
+// K_* itself and the posterior mean are produced by kstar_tensor_kernel in fp32 (relative error ~1e-6 on K_*),
+// the mean reduction is accumulated in float64 in a fixed order (deterministic).
+//
+// Accuracy contract of this path: |var - var_ref| <= 1e-5 * prior variance (tests/test_gpu_parity.py); the float64
+// path (gp.cu) is the one that matches scikit-learn to ~1e-10.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cudaTypedefs.h>
+
 #include "gp.cuh"
 
+namespace {
+
+constexpr int TM = 128;      // candidates per tile  (UMMA M, TMEM lanes)
+constexpr int TN = 256;      // Linv rows per tile   (UMMA N, TMEM columns per accumulator)
+constexpr int TK = 64;       // k elements per stage (128 bytes of fp16 = one swizzle atom row)
+constexpr int UK = 16;       // UMMA K for 16-bit inputs
+constexpr int STAGES = 2;
+constexpr int A_BYTES = TM * TK * 2;   // 16 KiB
+constexpr int B_BYTES = TN * TK * 2;   // 32 KiB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands: 96 KiB
+constexpr int NTHREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must not hang the GPU -- after ~2^22 polls the kernel flags an error and every later
+// wait falls through immediately (results are then discarded by the host)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0u) {
+      if (*abort_flag) return;
+      if (spins > (1u << 22)) {
+        *abort_flag = 1;
+        return;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): fp16 A/B (format 0), fp32 accumulate (c_format 1),
+// both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------ the GEMM
+struct GemmParams {
+  int M;           // objectives
+  int n_pb;        // candidate blocks (of TM) in this chunk
+  int n_jt;        // Linv row blocks (of TN)
+  int64_t k_rows;  // rows per objective in the K_* tensor maps (= Pc_alloc)
+  int64_t l_rows;  // rows per objective in the Linv tensor maps (= Npad)
+  const float* inv_scale;  // [M][Npad]  1 / (row scale * K_* scale)
+  double* vnorm;           // [M][vn_ld]
+  int64_t vn_ld;
+  int* abort_flag;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+    gp_var_tc_kernel(const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl,
+                     const __grid_constant__ CUtensorMap map_lh, const __grid_constant__ CUtensorMap map_ll,
+                     const GemmParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned tile area (SWIZZLE_128B atoms are 1024 B)
+  uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(tiles + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;      // [2]  MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2]  epilogue -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  volatile int* abort_flag = prm.abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // TMEM: 512 columns = two 128 x 256 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_work = prm.M * prm.n_pb;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int m = w / prm.n_pb, pb = w - m * prm.n_pb;
+        const int a_row = (int)(m * prm.k_rows + (int64_t)pb * TM);
+        for (int jt = 0; jt < prm.n_jt; ++jt) {
+          const int b_row = (int)(m * prm.l_rows + (int64_t)jt * TN);
+          const int nkc = (jt + 1) * (TN / TK);
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1u, abort_flag);
+            uint8_t* st = tiles + (size_t)stage * STAGE_BYTES;
+            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(&map_kh, &full[stage], st, kc * TK, a_row);
+            tma_load_2d(&map_kl, &full[stage], st + A_BYTES, kc * TK, a_row);
+            tma_load_2d(&map_lh, &full[stage], st + 2 * A_BYTES, kc * TK, b_row);
+            tma_load_2d(&map_ll, &full[stage], st + 2 * A_BYTES + B_BYTES, kc * TK, b_row);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        for (int jt = 0; jt < prm.n_jt; ++jt) {
+          mbar_wait(&acc_empty[acc], acc_phase ^ 1u, abort_flag);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * TN;
+          const int nkc = (jt + 1) * (TN / TK);
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&full[stage], phase, abort_flag);  // TMA bytes have landed
+            tc_fence_after();
+            const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
+            const uint64_t a_hi = make_sdesc(sa), a_lo = make_sdesc(sa + A_BYTES);
+            const uint64_t b_hi = make_sdesc(sa + 2 * A_BYTES), b_lo = make_sdesc(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < TK / UK; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UK * 2) >> 4);  // +32 bytes per UMMA_K inside the swizzle atom
+              tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kc | ks) ? 1u : 0u);
+              tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+              tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1u);
+            }
+            tc_commit(&empty[stage]);  // ring slot reusable once these MMAs have read it
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          tc_commit(&acc_full[acc]);  // accumulator complete
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue: TMEM -> registers -> sum of squares
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;  // candidate within the tile
+    uint32_t acc = 0, acc_phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int m = w / prm.n_pb, pb = w - m * prm.n_pb;
+      const float* isc = prm.inv_scale + (int64_t)m * prm.l_rows;
+      double total = 0.0;
+      for (int jt = 0; jt < prm.n_jt; ++jt) {
+        mbar_wait(&acc_full[acc], acc_phase, abort_flag);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
+        float part = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          uint32_t r[32];
+          tc_ld_32x32(t_addr + c0, r);
+          tc_wait_ld();
+          const float* sc = isc + jt * TN + c0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float t = __uint_as_float(r[e]) * __ldg(sc + e);
+            part = fmaf(t, t, part);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        total += (double)part;
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      prm.vnorm[(int64_t)m * prm.vn_ld + (int64_t)pb * TM + row] = total;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ operand preparation
+// Linv row -> scaled fp16 hi / lo.  One block per (objective, row).
+__global__ void split_linv_kernel(const double* __restrict__ Linv, int64_t Npad, int M, const int* __restrict__ k_exp,
+                                  uint16_t* __restrict__ Lh, uint16_t* __restrict__ Ll, float* __restrict__ inv_scale) {
+  const int64_t row = blockIdx.x;  // m * Npad + i
+  const int m = (int)(row / Npad);
+  const double* src = Linv + row * Npad;
+  __shared__ double red[256];
+  double mx = 0.0;
+  for (int64_t k = threadIdx.x; k < Npad; k += blockDim.x) mx = fmax(mx, fabs(src[k]));
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  mx = red[0];
+  int e = 0;
+  if (mx > 0.0) e = 13 - ilogb(mx);  // scaled row maximum lands in [2^13, 2^14): far from fp16 overflow (65504)
+  const double s = scalbn(1.0, e);
+  for (int64_t k = threadIdx.x; k < Npad; k += blockDim.x) {
+    const float x = (float)(src[k] * s);  // power-of-two scaling is exact; float keeps 24 bits
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    Lh[row * Npad + k] = __half_as_ushort(h);
+    Ll[row * Npad + k] = __half_as_ushort(l);
+  }
+  if (threadIdx.x == 0) inv_scale[row] = (mx > 0.0) ? (float)scalbn(1.0, -e - k_exp[m]) : 0.f;
+}
+
+constexpr int KT_TN = 128, KT_TP = 32, KT_DMAX = 64;
+
+__device__ __forceinline__ float stationary_f(float s2, int kind) {
+  if (kind == DMO_KERNEL_MATERN52) {
+    const float K = sqrtf(s2) * 2.2360679774997896f;
+    return (1.0f + K + K * K * (1.0f / 3.0f)) * expf(-K);
+  }
+  return expf(-0.5f * s2);
+}
+
+// K_* in fp32 -> scaled fp16 hi / lo, plus deterministic partial sums of the posterior mean.
+template <bool ISO>
+__global__ void __launch_bounds__(KT_TN)
+    kstar_tensor_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, int64_t Pcpad,
+                        const double* __restrict__ Xt, int64_t N, int d, int M, int kind,
+                        const double* __restrict__ inv_ls, const double* __restrict__ constant,
+                        const int* __restrict__ k_exp, const double* __restrict__ alpha, int64_t ldk, int64_t plane,
+                        uint16_t* __restrict__ Kh, uint16_t* __restrict__ Kl, double* __restrict__ mean_part) {
+  extern __shared__ float sxf[];  // [KT_TP][d]
+  __shared__ double wsum[KT_TN / 32][KT_TP][4];
+  const int64_t n = (int64_t)blockIdx.x * KT_TN + threadIdx.x;
+  const int64_t pt0 = (int64_t)blockIdx.y * KT_TP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < KT_TP * d; t += KT_TN) {
+    int64_t p = p_base + pt0 + t / d;
+    sxf[t] = (p < P) ? (float)Xn[p * d + (t % d)] : 0.f;
+  }
+  float xt[KT_DMAX];
+#pragma unroll
+  for (int j = 0; j < KT_DMAX; ++j) xt[j] = (j < d && n < N) ? (float)Xt[n * d + j] : 0.f;
+  __syncthreads();
+  for (int q = 0; q < KT_TP; ++q) {
+    const int64_t pl = pt0 + q;
+    const float* xc = sxf + q * d;
+    float s_iso = 0.f;
+    if (ISO) {
+#pragma unroll
+      for (int j = 0; j < KT_DMAX; ++j)
+        if (j < d) {
+          const float df = xc[j] - xt[j];
+          s_iso = fmaf(df, df, s_iso);
+        }
+    }
+    for (int m = 0; m < M; ++m) {
+      float s2;
+      if (ISO) {
+        const float il = (float)inv_ls[m * d];
+        s2 = s_iso * il * il;
+      } else {
+        s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < KT_DMAX; ++j)
+          if (j < d) {
+            const float df = (xc[j] - xt[j]) * (float)inv_ls[m * d + j];
+            s2 = fmaf(df, df, s2);
+          }
+      }
+      const float kv = (n < N) ? (float)constant[m] * stationary_f(s2, kind) : 0.f;
+      const float ks = scalbnf(kv, k_exp[m]);
+      const __half h = __float2half_rn(ks);
+      const __half l = __float2half_rn(ks - __half2float(h));
+      if (pl < Pcpad && n < ldk) {
+        Kh[m * plane + pl * ldk + n] = __half_as_ushort(h);
+        Kl[m * plane + pl * ldk + n] = __half_as_ushort(l);
+      }
+      double t = (n < N) ? (double)kv * alpha[(int64_t)m * N + n] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0 && m < 4) wsum[warp][q][m] = t;
+    }
+  }
+  __syncthreads();
+  // fixed-order combination of the 4 warps -> one partial per (train block, candidate, objective)
+  for (int t = threadIdx.x; t < KT_TP * M; t += KT_TN) {
+    const int q = t / M, m = t - q * M;
+    const int64_t pl = pt0 + q;
+    if (pl < Pcpad && m < 4) {
+      double s = 0.0;
+      for (int w = 0; w < KT_TN / 32; ++w) s += wsum[w][q][m];
+      mean_part[((int64_t)blockIdx.x * Pcpad + pl) * M + m] = s;
+    }
+  }
+}
+
+__global__ void mean_finish_kernel(const double* __restrict__ part, int nblk, int64_t Pc, int64_t Pcpad, int M,
+                                   const double* __restrict__ ymean, const double* __restrict__ ystd, int64_t p_base,
+                                   double* __restrict__ mean) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Pc * M) return;
+  int64_t pl = t / M;
+  int m = (int)(t - pl * M);
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += part[((int64_t)b * Pcpad + pl) * M + m];
+  mean[(p_base + pl) * M + m] = ystd[m] * s + ymean[m];
+}
+
+__global__ void var_finish_tc_kernel(const double* __restrict__ vnorm, int64_t Pc, int64_t ld, int M,
+                                     const double* __restrict__ constant, const double* __restrict__ noise,
+                                     const double* __restrict__ ystd, int64_t p_base, double* __restrict__ var) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Pc * M) return;
+  int64_t pl = t / M;
+  int m = (int)(t - pl * M);
+  double v = (constant[m] + noise[m]) - vnorm[(int64_t)m * ld + pl];
+  if (v < 0.0) v = 0.0;
+  double sd = sqrt(v * (ystd[m] * ystd[m]));
+  var[(p_base + pl) * M + m] = sd * sd;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+// 2-D fp16 tensor [rows][cols] (cols contiguous), box = box_rows x 64 columns, 128-byte swizzle
+int make_map(dmo_ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return dmo_fail(ctx, DMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return dmo_fail(ctx, DMO_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return DMO_OK;
+}
+
+int prepare_tensor_state(dmo_ctx* ctx, dmo_gp* gp) {
+  if (gp->tensor_ready) return DMO_OK;
+  const int M = gp->M;
+  const int64_t Npad = gp->Npad;
+  std::vector<int> kexp(M);
+  for (int m = 0; m < M; ++m) {
+    double c = gp->h_constant[m];
+    kexp[m] = (c > 0.0) ? 13 - ilogb(c) : 13;  // scaled K_* <= 2^14
+  }
+  DMO_TRY(gp->Kexp.alloc(ctx, M));
+  DMO_CUDA(cudaMemcpyAsync(gp->Kexp.p, kexp.data(), M * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));  // kexp is a stack vector
+  DMO_TRY(gp->Lhi.alloc(ctx, (size_t)M * Npad * Npad));
+  DMO_TRY(gp->Llo.alloc(ctx, (size_t)M * Npad * Npad));
+  DMO_TRY(gp->Lscale.alloc(ctx, (size_t)M * Npad));
+  DMO_LAUNCH(split_linv_kernel, (unsigned)(M * Npad), 256, 0, gp->Linv.p, Npad, M, gp->Kexp.p, gp->Lhi.p, gp->Llo.p,
+             gp->Lscale.p);
+  DMO_CHECK_LAUNCH();
+  gp->tensor_ready = true;
+  return DMO_OK;
+}
+
+}  // namespace
+
 int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var) {
-  (void)gp;
-  (void)dXn;
-  (void)P;
-  (void)d_mean;
-  (void)d_var;
-  return dmo_fail(ctx, DMO_ERR_UNSUPPORTED, "gp_predict: the tensor path is not built into this library");
+  const int64_t N = gp->N, Npad = gp->Npad;
+  const int M = gp->M, d = gp->d;
+  DMO_REQUIRE(M <= 4, "gp_predict(tensor): at most 4 objectives per model (got %d)", M);
+  DMO_REQUIRE(Npad % TN == 0, "gp_predict(tensor): internal padding error");
+  DMO_TRY(prepare_tensor_state(ctx, gp));
+  // candidate chunk: K_* hi/lo (2 x M x Pc x Npad fp16) within ~6 GiB
+  int64_t Pc_max = ((int64_t)6 << 30) / ((int64_t)M * Npad * 4);
+  Pc_max = (Pc_max / TM) * TM;
+  if (Pc_max < TM) Pc_max = TM;
+  const int64_t Pc_alloc = P < Pc_max ? ceil_div(P, TM) * TM : Pc_max;
+  const int nblk = (int)(Npad / KT_TN);
+  DevBuf<uint16_t> Kh, Kl;
+  DevBuf<double> mpart, vnorm;
+  DevBuf<int> abort_flag;
+  DMO_TRY(Kh.alloc(ctx, (size_t)M * Pc_alloc * Npad));
+  DMO_TRY(Kl.alloc(ctx, (size_t)M * Pc_alloc * Npad));
+  DMO_TRY(mpart.alloc(ctx, (size_t)nblk * Pc_alloc * M));
+  DMO_TRY(vnorm.alloc(ctx, (size_t)M * Pc_alloc));
+  DMO_TRY(abort_flag.alloc(ctx, 1));
+  DMO_CUDA(cudaMemsetAsync(abort_flag.p, 0, sizeof(int), ctx->stream));
+  CUtensorMap map_kh, map_kl, map_lh, map_ll;
+  DMO_TRY(make_map(ctx, &map_kh, Kh.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, TM));
+  DMO_TRY(make_map(ctx, &map_kl, Kl.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, TM));
+  DMO_TRY(make_map(ctx, &map_lh, gp->Lhi.p, (uint64_t)M * Npad, (uint64_t)Npad, TN));
+  DMO_TRY(make_map(ctx, &map_ll, gp->Llo.p, (uint64_t)M * Npad, (uint64_t)Npad, TN));
+  DMO_CUDA(cudaFuncSetAttribute(gp_var_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  const int64_t kplane = Pc_alloc * Npad;
+  for (int64_t p_base = 0; p_base < P; p_base += Pc_alloc) {
+    const int64_t Pc = (P - p_base) < Pc_alloc ? (P - p_base) : Pc_alloc;
+    const int64_t Pcpad = ceil_div(Pc, TM) * TM;
+    {
+      ProfileScope ps(ctx, "gp_kstar");
+      dim3 gk((unsigned)nblk, (unsigned)ceil_div(Pcpad, KT_TP));
+      size_t smem = (size_t)KT_TP * d * sizeof(float);
+      if (gp->isotropic)
+        DMO_LAUNCH(kstar_tensor_kernel<true>, gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel,
+                   gp->inv_ls.p, gp->constant.p, gp->Kexp.p, gp->alpha.p, Npad, kplane, Kh.p, Kl.p, mpart.p);
+      else
+        DMO_LAUNCH(kstar_tensor_kernel<false>, gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel,
+                   gp->inv_ls.p, gp->constant.p, gp->Kexp.p, gp->alpha.p, Npad, kplane, Kh.p, Kl.p, mpart.p);
+    }
+    {
+      ProfileScope ps(ctx, "gp_mean");
+      DMO_LAUNCH(mean_finish_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, mpart.p, nblk, Pc, Pcpad, M, gp->ymean.p,
+                 gp->ystd.p, p_base, d_mean);
+    }
+    if (d_var) {
+      GemmParams prm;
+      prm.M = M;
+      prm.n_pb = (int)(Pcpad / TM);
+      prm.n_jt = (int)(Npad / TN);
+      prm.k_rows = Pc_alloc;
+      prm.l_rows = Npad;
+      prm.inv_scale = gp->Lscale.p;
+      prm.vnorm = vnorm.p;
+      prm.vn_ld = Pc_alloc;
+      prm.abort_flag = abort_flag.p;
+      const int n_work = prm.M * prm.n_pb;
+      const int grid = n_work < ctx->sm_count ? n_work : ctx->sm_count;
+      {
+        ProfileScope ps(ctx, "gp_var");
+        DMO_LAUNCH(gp_var_tc_kernel, grid, NTHREADS, GEMM_SMEM, map_kh, map_kl, map_lh, map_ll, prm);
+      }
+      DMO_LAUNCH(var_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, Pc, Pc_alloc, M,
+                 gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
+    }
+  }
+  DMO_CHECK_LAUNCH();
+  int h_abort = 0;
+  DMO_CUDA(cudaMemcpyAsync(&h_abort, abort_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_abort) return dmo_fail(ctx, DMO_ERR_INTERNAL, "gp_predict(tensor): pipeline watchdog tripped");
+  return DMO_OK;
 }

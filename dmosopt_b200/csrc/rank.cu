@@ -18,6 +18,8 @@
 //
 // Algorithmic bytes: 8 n M read + 4 n written; comparisons <= n^2 M / 2 (compare-throughput bound,
 // see DESIGN.md).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -150,11 +152,11 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
 
     // ---- stream every earlier block: best = max over dominators of (rank + 1)
     int best = 0;
-    for (int k = 0; k < b; ++k) {
+    auto wait_done = [&](int k) {
       if (tid == 0) {
         unsigned spins = 0;
         while (ld_acquire_gpu(done + k) == 0) {
-          __nanosleep(40);
+          __nanosleep(20);
           if ((++spins & 0xFFFu) == 0u) {
             if (spins > (1u << 22) || ld_acquire_gpu(errflag) != 0) {
               atomicExch(errflag, 1);
@@ -164,6 +166,9 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
         }
       }
       __syncthreads();
+    };
+    for (int k = 0; k < b - 1; ++k) {
+      wait_done(k);
       {
         const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)k * T * W);
 #pragma unroll
@@ -186,6 +191,44 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
         for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
         const int r1 = (int)sw[M];
         best = dom ? max(best, r1) : best;
+      }
+      __syncthreads();
+    }
+    // The predecessor block is the critical dependency: its dominance pattern does not depend on its ranks, so it is
+    // evaluated into a bitmask BEFORE waiting for its "done" flag; once the flag is up only the set bits are visited.
+    if (b > 0) {
+      const int k = b - 1;
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)k * T * W);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) tile[tid * NV + q] = src[tid * NV + q];  // static words only (ids, group)
+      }
+      __syncthreads();
+      uint32_t pmask[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        uint32_t mm = 0u;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+          const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s) * NV]);
+          bool dom = (sp[M - 1] != gidv);
+#pragma unroll
+          for (int j = 0; j < M - 1; ++j) dom = dom && (sp[j] <= v[j]);
+          mm |= (dom ? 1u : 0u) << s;
+        }
+        pmask[w] = mm;
+      }
+      wait_done(k);
+      sh_r1[tid] = (int)__ldcg(rec + ((int64_t)k * T + tid) * W + M);  // rank + 1 of the predecessor block
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        uint32_t mm = pmask[w];
+        while (mm) {
+          const int s = __ffs(mm) - 1;
+          mm &= mm - 1;
+          best = max(best, sh_r1[w * 32 + s]);
+        }
       }
       __syncthreads();
     }
@@ -243,6 +286,11 @@ int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* done
   int occ = 0;
   DMO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_chain_kernel<M, RANK_T>, RANK_T, 0));
   if (occ < 1) occ = 1;
+  // fewer co-resident CTAs per SM shorten the serial chain (the block on the critical path shares its SM's issue
+  // slots with the others); DMO_RANK_OCC overrides for tuning
+  int cap = 6;
+  if (const char* e = getenv("DMO_RANK_OCC")) cap = atoi(e);
+  if (cap >= 1 && occ > cap) occ = cap;
   int grid = nblocks < occ * ctx->sm_count ? nblocks : occ * ctx->sm_count;
   ProfileScope ps(ctx, "rank_chain");
   DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), grid, RANK_T, 0, rec, nblocks, rankS, done, ticket, errflag);

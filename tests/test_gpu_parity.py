@@ -270,6 +270,42 @@ def test_gp_predict_baseline_shape_vs_oracle(L):
     h.close()
 
 
+def _baseline_gp(N, d, M, seed):
+    rng = np.random.default_rng(seed)
+    xlb, xub = np.zeros(d), np.ones(d)
+    Xtr = rng.random((N, d))
+    Ytr = np.column_stack([np.sin(3 * Xtr[:, :4].sum(axis=1) + k) + Xtr[:, 4 + k] ** 2 for k in range(M)])
+    st = gp.fit_fixed(Xtr, Ytr, xlb, xub, 1.0, 0.5, 1e-6)
+    return rng, xlb, xub, Xtr, st
+
+
+def _handle_from_state(L, st, d):
+    return L.GPHandle(st.X_train, np.stack([o.alpha for o in st.objectives]), np.stack([o.L for o in st.objectives]), [o.constant for o in st.objectives],
+                      [np.full(d, float(o.length_scale)) for o in st.objectives], [o.noise for o in st.objectives], [o.y_mean for o in st.objectives],
+                      [o.y_std for o in st.objectives], st.xlb, st.xub)
+
+
+@pytest.mark.parametrize("N,d,M,P", [(300, 30, 3, 200), (1000, 12, 2, 517), (2048, 30, 3, 1500)])
+def test_gp_predict_tensor_path(L, N, d, M, P):
+    """tcgen05 split-fp16 path: |var - var_ref| <= 1e-5 * prior variance, |mean - mean_ref| <= 1e-5 * max(|mean|, y_std)."""
+    rng, xlb, xub, Xtr, st = _baseline_gp(N, d, M, 100 + N)
+    X = rng.random((P, d))
+    X[:6] = np.clip(Xtr[:6] + 2e-3 * rng.standard_normal((6, d)), 0, 1)  # small posterior variance rows
+    mean_o, var_o = gp.predict(st, X)
+    h = _handle_from_state(L, st, d)
+    mean64, var64 = h.predict(X, precision=L.GP_FP64)
+    mean, var = h.predict(X, precision=L.GP_TENSOR)
+    ystd = np.array([o.y_std for o in st.objectives])
+    prior = np.array([(o.constant + o.noise) * o.y_std**2 for o in st.objectives])
+    assert np.max(np.abs(var64 - var_o) / prior) < 1e-8
+    err_v = np.max(np.abs(var - var_o) / prior)
+    err_m = np.max(np.abs(mean - mean_o) / np.maximum(np.abs(mean_o), ystd))
+    print(f"tensor path N={N} d={d}: var err/prior {err_v:.2e}, mean rel err {err_m:.2e}")
+    assert err_v < 1e-5, err_v
+    assert err_m < 1e-5, err_m
+    h.close()
+
+
 # ------------------------------------------------------------------------------------------ A16 HV
 def test_hv_known_answers_and_golden(L):
     g = load_golden("hv")
