@@ -1,0 +1,240 @@
+"""MO-CMA-ES optimizer plugin on the B200 path.
+
+Drop-in for ``dmosopt.CMAES.CMAES`` (dmosopt/CMAES.py:26-537), selected by ``optimizer_name="dmosopt_b200.CMAES"``.
+
+  generate_strategy : non-dominated rank of the parents (dmo_rank_nd), parent draw, then
+                      x = x_p + sigma_p * (A_p @ z) for lambda*mu offspring (dmo_cmaes_sample; CMAES.py:231-271)
+  _select           : rank of offspring + parents, whole fronts first, the overflowing front split by the
+                      hypervolume-improvement score (dmo_ehvi_select; CMAES.py:167-229)
+  update_strategy   : success-rate / step-size recurrences (vectorised on the host, O(n) scalars) and the rank-one
+                      Cholesky updates of all chosen offspring in one batch (dmo_cmaes_update_cholesky;
+                      CMAES.py:273-414, 489-537)
+"""
+
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .MOEA import MOEA, Struct, remove_duplicates, remove_worst
+from .NSGA2 import population_diversity
+from .indicators import HypervolumeImprovement
+
+
+def sortMO(x, y, x_distance_metrics=None):
+    """CMAES.sortMO (CMAES.py:455-486): (perm, rank) with rank in the original order."""
+    rank = _lib.rank_nd(y)
+    keys = []
+    if x_distance_metrics:
+        rmax = int(rank.max())
+        for fn in x_distance_metrics:
+            dist = np.zeros_like(rank)
+            for front in range(rmax + 1):
+                idx = rank == front
+                dist[idx] = fn(x[idx, :])
+            keys.append(-dist)
+    return np.lexsort(keys + [rank]), rank
+
+
+class CMAES(MOEA):
+    def __init__(
+        self,
+        popsize: int,
+        nInput: int,
+        nOutput: int,
+        model: Optional[Any] = None,
+        distance_metric: Optional[Any] = None,
+        optimize_mean_variance: bool = False,
+        **kwargs,
+    ):
+        super().__init__(name="CMAES", popsize=popsize, nInput=nInput, nOutput=nOutput, **kwargs)
+        self.model = model
+        self.x_distance_metrics = None
+        if getattr(self.model, "feasibility", None) is not None:
+            self.x_distance_metrics = [self.model.feasibility.rank]
+        if np.isscalar(self.opt_params.di_mutation):
+            self.opt_params.di_mutation = np.asarray([self.opt_params.di_mutation] * nInput)
+        self.state = None
+        self.indicator = HypervolumeImprovement
+        self.optimize_mean_variance = optimize_mean_variance
+
+    @property
+    def default_parameters(self) -> Dict[str, Any]:
+        """CMAES.py:82-120."""
+        nInput, nOutput, popsize = self.nInput, self.nOutput, self.popsize
+        ptarg = 1.0 / (5.0 + 0.5)
+        return {
+            "sigma": 0.001,
+            "mu": popsize // 2,
+            "lambda_": 1,
+            "d": 1.0 + nOutput / 2.0,
+            "ptarg": ptarg,
+            "cp": ptarg / (1.0 + ptarg),
+            "cc": 2.0 / (nInput + 2.0),
+            "ccov": 2.0 / (nInput**2 + 6.0),
+            "pthresh": 0.44,
+            "di_mutation": 30.0,
+            "max_population_size": 600,
+            "min_population_size": 100,
+            "adaptive_population_size": False,
+        }
+
+    def initialize_state(self, x, y, bounds, local_random=None, **params):
+        """CMAES.py:122-165."""
+        dim, n = self.nInput, self.opt_params.popsize
+        p = self.opt_params
+        sigmas = np.asarray([p.sigma * (1.0 / (p.di_mutation + 1.0))] * n)
+        A = np.stack([np.identity(dim) for _ in range(n)])
+        Ainv = np.stack([np.identity(dim) for _ in range(n)])
+        pc = np.zeros((n, dim))
+        psucc = np.asarray([p.ptarg] * n)
+        order, rank = sortMO(x, y, self.x_distance_metrics)
+        idx = order[:n]
+        return Struct(bounds=bounds, parents_x=x[idx].copy(), parents_y=y[idx].copy(), sigmas=sigmas, A=A, Ainv=Ainv, pc=pc,
+                      psucc=psucc, rank=rank[idx].copy())
+
+    def _select(self, candidates_x, candidates_y, candidates_ps, candidates_inds):
+        """CMAES.py:167-229."""
+        popsize = self.opt_params.popsize
+        n = candidates_x.shape[0]
+        if n <= popsize:
+            return np.ones(n, dtype=bool), np.zeros(n, dtype=bool), _lib.rank_nd(candidates_y)
+        order, rank = sortMO(candidates_x, candidates_y, self.x_distance_metrics)
+        order_inv = np.argsort(order)
+        chosen = np.zeros(n, dtype=bool)
+        not_chosen = np.zeros(n, dtype=bool)
+        mid_front = None
+        full = False
+        chosen_count = 0
+        for r in range(int(np.max(rank)) + 1):
+            front_r = order_inv[np.argwhere(rank == r).ravel()]  # (sic) the reference maps fronts through order_inv (:190)
+            if chosen_count + len(front_r) <= popsize and not full:
+                chosen[front_r] = True
+                chosen_count += len(front_r)
+            elif mid_front is None and chosen_count < popsize:
+                mid_front = front_r.copy()
+                full = True
+            else:
+                not_chosen[front_r] = True
+        k = popsize - chosen_count
+        if k > 0:
+            ref = np.max(candidates_y, axis=0) + 1
+            indicator = self.indicator(ref_point=ref, nds=True)
+            assert len(mid_front) > 0
+            if chosen_count > 0:
+                selected = indicator.do(candidates_y[chosen], candidates_y[mid_front, :], np.ones_like(candidates_y[mid_front, :]), k)
+            else:
+                selected = np.arange(k)
+            assert len(selected) == k
+            chosen[mid_front[selected]] = True
+            mask = np.ones(len(mid_front), dtype=bool)
+            mask[selected] = False
+            not_chosen[mid_front[mask]] = True
+        return chosen, not_chosen, rank
+
+    def generate_strategy(self, **params):
+        """CMAES.py:231-271."""
+        rng = self.local_random
+        st = self.state
+        dim, mu, lambda_ = self.nInput, self.opt_params.mu, self.opt_params.lambda_
+        arz = rng.normal(size=(lambda_ * mu, dim))
+        order, rank = sortMO(st.parents_x, st.parents_y, self.x_distance_metrics)
+        parent_selection, count = [], 0
+        for r in range(int(np.max(rank)) + 1):
+            front_r = np.argwhere(rank == r).ravel()
+            parent_selection.append(front_r)
+            count += len(front_r)
+            if count >= mu:
+                break
+        parent_selection = np.concatenate(parent_selection)[:mu]
+        js = rng.choice(len(parent_selection), size=lambda_ * mu)
+        p_idx = parent_selection[js]
+        individuals = _lib.cmaes_sample(st.parents_x, st.sigmas, st.A, p_idx, arz)
+        xrng = self.bounds[:, 1] - self.bounds[:, 0]
+        x_new = (individuals / np.max(np.abs(individuals))) * xrng + self.bounds[:, 0]  # (sic) global rescale, CMAES.py:269-270
+        return x_new, {"p_idx": p_idx}
+
+    def update_strategy(self, x_gen, y_gen, state, **params):
+        """CMAES.py:273-414."""
+        st, p = self.state, self.opt_params
+        dim = self.nInput
+        p_idxs = np.asarray(state["p_idx"])
+        xlb, xub = self.bounds[:, 0], self.bounds[:, 1]
+        parents_x = st.parents_x
+        P, C = parents_x.shape[0], x_gen.shape[0]
+        candidates_x = np.vstack((x_gen, parents_x))
+        candidates_y = np.vstack((y_gen, st.parents_y))
+        is_off = np.concatenate((np.ones(C, dtype=bool), np.zeros(P, dtype=bool)))
+        pidx = np.concatenate((p_idxs, np.arange(P, dtype=np.int_)))
+        chosen, not_chosen, rank = self._select(candidates_x, candidates_y, is_off, pidx)
+        cp, cc, ccov, d, ptarg, pthresh = p.cp, p.cc, p.ccov, p.d, p.ptarg, p.pthresh
+        fac = lambda ps: np.exp((ps - ptarg) / (d * (1.0 - ptarg)))  # noqa: E731
+
+        # ---- chosen offspring: their own strategy parameters start from the parent's (copied before any update)
+        ch_off = np.flatnonzero(chosen & is_off)
+        par = pidx[ch_off]
+        off_psucc = (1.0 - cp) * st.psucc[par] + cp
+        last_steps = st.sigmas[par].copy()
+        off_sigmas = last_steps * fac(off_psucc)[:, None]
+        off_A, off_Ainv, off_pc = st.A[par], st.Ainv[par], st.pc[par]
+        if len(ch_off) > 0:
+            z = np.divide(candidates_x[ch_off] - parents_x[par], xub - xlb) / last_steps
+            off_A, off_Ainv, off_pc = _lib.cmaes_update_cholesky(off_A, off_Ainv, off_pc, z, off_psucc, cc, ccov, pthresh)
+
+        # ---- parents: one success event per chosen offspring (ascending candidate index), then one failure event per
+        # not-chosen offspring; the recurrences are sequential per parent, so they are applied event-rank by event-rank
+        new_psucc, new_sig = st.psucc.copy(), st.sigmas.copy()
+        nc_off = np.flatnonzero(not_chosen & is_off)
+        ev_parent = np.concatenate((par, pidx[nc_off]))
+        ev_success = np.concatenate((np.ones(len(par), dtype=bool), np.zeros(len(nc_off), dtype=bool)))
+        if len(ev_parent) > 0:
+            order = np.argsort(ev_parent, kind="stable")
+            ep, es = ev_parent[order], ev_success[order]
+            first = np.r_[True, ep[1:] != ep[:-1]]
+            start = np.maximum.accumulate(np.where(first, np.arange(len(ep)), 0))
+            k_in_parent = np.arange(len(ep)) - start
+            for k in range(int(k_in_parent.max()) + 1):
+                sel = k_in_parent == k
+                q = ep[sel]
+                new_psucc[q] = (1.0 - cp) * new_psucc[q] + np.where(es[sel], cp, 0.0)
+                new_sig[q] = new_sig[q] * fac(new_psucc[q])[:, None]
+        st.psucc, st.sigmas = new_psucc, new_sig
+
+        # ---- assemble the next parent set (CMAES.py:385-411)
+        ch = np.flatnonzero(chosen)
+        ch_is_off = is_off[ch]
+        slot = np.full(candidates_x.shape[0], -1, dtype=int)
+        slot[ch_off] = np.arange(len(ch_off))
+        src_par = pidx[ch]
+        sigmas_n = st.sigmas[src_par].copy()
+        A_n, Ainv_n, pc_n, psucc_n = st.A[src_par].copy(), st.Ainv[src_par].copy(), st.pc[src_par].copy(), st.psucc[src_par].copy()
+        if len(ch_off) > 0:
+            o = slot[ch[ch_is_off]]
+            sigmas_n[ch_is_off] = off_sigmas[o]
+            A_n[ch_is_off], Ainv_n[ch_is_off], pc_n[ch_is_off], psucc_n[ch_is_off] = off_A[o], off_Ainv[o], off_pc[o], off_psucc[o]
+        st.parents_x = candidates_x[chosen]
+        st.parents_y = candidates_y[chosen]
+        st.rank = rank[chosen]
+        st.sigmas, st.A, st.Ainv, st.pc, st.psucc = sigmas_n, A_n, Ainv_n, pc_n, psucc_n
+        if p.adaptive_population_size:
+            self.update_population_size()
+
+    def get_population_strategy(self):
+        """CMAES.py:416-430."""
+        x, y = remove_duplicates(self.state.parents_x.copy(), self.state.parents_y.copy())
+        if len(x) > 0:
+            x, y, _ = remove_worst(x, y, self.popsize)
+        return x, y
+
+    def update_population_size(self):
+        """CMAES.py:432-452."""
+        p = self.opt_params
+        diversity, cd_spread = population_diversity(self.state.rank, self.state.parents_y)
+        if diversity < 0.1 or cd_spread < 2.0:
+            new_size = min(p.max_population_size, int(p.popsize * 1.1))
+        elif diversity > 0.4 and cd_spread > 1.0:
+            new_size = max(p.min_population_size, int(p.popsize * 0.9))
+        else:
+            new_size = p.popsize
+        p.popsize = new_size
+        p.mu = p.popsize // 2

@@ -67,6 +67,11 @@ _SIGNATURES = {
     "dmo_hypervolume": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp, ctypes.POINTER(_c_dbl)]),
     "dmo_ehvi_select": (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp, _c_int, _c_i64, _vp, _vp]),
     "dmo_get_duplicates": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_dbl, _vp]),
+    "dmo_age_survival": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _c_dbl, _vp, _c_int, _vp]),
+    "dmo_smpso_velocity": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _vp]),
+    "dmo_mutate_groups": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _c_u64, _c_u64, _vp, _vp]),
+    "dmo_cmaes_sample": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp]),
+    "dmo_cmaes_update_cholesky": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl]),
 }
 
 _lib = None
@@ -496,3 +501,76 @@ def get_duplicates(X, eps=1e-16):
     out = np.empty(n, dtype=np.uint8)
     _check(load_library().dmo_get_duplicates(context(), _ptr(X), n, d, float(eps), _ptr(out)), "dmo_get_duplicates")
     return out.astype(bool)
+
+
+# --------------------------------------------------------------------------- A11 AGE-MOEA
+def age_survival(yn, nn, p, extreme):
+    """Greedy part of AGEMOEA.survival_score (dmosopt/AGEMOEA.py:398-428) -> crowding values (m,)."""
+    yn = _f64(yn)
+    nn = _f64(nn)
+    m, M = yn.shape
+    ext = np.ascontiguousarray(extreme, dtype=np.int32)
+    crowd = np.empty(m, dtype=np.float64)
+    _check(load_library().dmo_age_survival(context(), _ptr(yn), _ptr(nn), m, M, float(p), _ptr(ext), ext.shape[0], _ptr(crowd)), "dmo_age_survival")
+    return crowd
+
+
+# --------------------------------------------------------------------------- A12 SMPSO
+def smpso_velocity(position, velocity, leader1, leader2, w, c1, r1, c2, r2, chi, xlb, xub):
+    f32_diff = 1 if (np.asarray(leader1).dtype == np.float32 and np.asarray(position).dtype == np.float32) else 0
+    pos = np.ascontiguousarray(position, dtype=np.float32)
+    vel = _f64(velocity)
+    l1 = _f64(leader1)
+    l2 = _f64(leader2)
+    n, d = pos.shape
+    lb, ub = _f64(xlb), _f64(xub)
+    out = np.empty((n, d), dtype=np.float64)
+    _check(
+        load_library().dmo_smpso_velocity(context(), _ptr(pos), _ptr(vel), _ptr(l1), _ptr(l2), f32_diff, n, d, float(w), float(c1), float(r1), float(c2), float(r2),
+                                          float(chi), _ptr(lb), _ptr(ub), _ptr(out)),
+        "dmo_smpso_velocity",
+    )
+    return out
+
+
+def mutate_groups(pop_x, group_size, n_groups, per_group, di_mutation, xlb, xub, mutation_rate, seed, stream_id, return_parents=False):
+    pop_x = _f64(pop_x)
+    d = pop_x.shape[1]
+    total = int(n_groups) * int(per_group)
+    di = _f64(np.broadcast_to(np.asarray(di_mutation, dtype=np.float64), (d,)))
+    lb, ub = _f64(xlb), _f64(xub)
+    out = np.empty((total, d), dtype=np.float64)
+    par = np.empty(total, dtype=np.int64) if return_parents else None
+    _check(
+        load_library().dmo_mutate_groups(context(), _ptr(pop_x), int(group_size), int(n_groups), int(per_group), d, _ptr(di), _ptr(lb), _ptr(ub),
+                                         float(mutation_rate), int(seed) & (2**64 - 1), int(stream_id), _ptr(out), _ptr(par)),
+        "dmo_mutate_groups",
+    )
+    return (out, par) if return_parents else out
+
+
+# --------------------------------------------------------------------------- A13 / A15 CMAES
+def cmaes_sample(parents_x, sigmas, A, p_idx, z):
+    px = _f64(parents_x)
+    sg = _f64(sigmas)
+    A = _f64(A)
+    z = _f64(z)
+    pi = np.ascontiguousarray(p_idx, dtype=np.int64)
+    n, d = z.shape
+    cols = 1 if sg.ndim == 1 else sg.shape[1]
+    out = np.empty((n, d), dtype=np.float64)
+    _check(load_library().dmo_cmaes_sample(context(), _ptr(px), _ptr(sg), cols, _ptr(A), px.shape[0], _ptr(pi), _ptr(z), n, d, _ptr(out)), "dmo_cmaes_sample")
+    return out
+
+
+def cmaes_update_cholesky(A, Ainv, pc, z, psucc, cc, ccov, pthresh):
+    """Batched CMAES.updateCholesky (dmosopt/CMAES.py:489-537); returns new (A, Ainv, pc)."""
+    A = np.array(A, dtype=np.float64, order="C")
+    Ainv = np.array(Ainv, dtype=np.float64, order="C")
+    pc = np.array(pc, dtype=np.float64, order="C")
+    z = _f64(z)
+    ps = _f64(psucc)
+    n, d = pc.shape
+    _check(load_library().dmo_cmaes_update_cholesky(context(), _ptr(A), _ptr(Ainv), _ptr(pc), _ptr(z), _ptr(ps), n, d, float(cc), float(ccov), float(pthresh)),
+           "dmo_cmaes_update_cholesky")
+    return A, Ainv, pc

@@ -335,29 +335,34 @@ __device__ __forceinline__ float stationary_f(float s2, int kind) {
   return expf(-0.5f * s2);
 }
 
-// K_* in fp32 -> scaled fp16 hi / lo, plus deterministic partial sums of the posterior mean.
+// K_* in fp32 -> scaled fp16 hi / lo.  One thread per training point, KT_TP candidates per block.
 template <bool ISO>
 __global__ void __launch_bounds__(KT_TN)
     kstar_tensor_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, int64_t Pcpad,
                         const double* __restrict__ Xt, int64_t N, int d, int M, int kind,
                         const double* __restrict__ inv_ls, const double* __restrict__ constant,
-                        const int* __restrict__ k_exp, const double* __restrict__ alpha, int64_t ldk, int64_t plane,
-                        uint16_t* __restrict__ Kh, uint16_t* __restrict__ Kl, double* __restrict__ mean_part) {
-  extern __shared__ float sxf[];  // [KT_TP][d]
-  __shared__ double wsum[KT_TN / 32][KT_TP][4];
+                        const int* __restrict__ k_exp, int64_t ldk, int64_t plane, uint16_t* __restrict__ Kh,
+                        uint16_t* __restrict__ Kl) {
+  extern __shared__ float sxf[];  // [KT_TP][d] candidate tile, then [M][d] 1/l, [M] c * 2^kexp
+  float* s_il = sxf + KT_TP * d;
+  float* s_c = s_il + 4 * d;
   const int64_t n = (int64_t)blockIdx.x * KT_TN + threadIdx.x;
   const int64_t pt0 = (int64_t)blockIdx.y * KT_TP;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int t = threadIdx.x; t < KT_TP * d; t += KT_TN) {
     int64_t p = p_base + pt0 + t / d;
     sxf[t] = (p < P) ? (float)Xn[p * d + (t % d)] : 0.f;
   }
+  for (int t = threadIdx.x; t < M * d; t += KT_TN) s_il[t] = (float)inv_ls[t];
+  if (threadIdx.x < M) s_c[threadIdx.x] = scalbnf((float)constant[threadIdx.x], k_exp[threadIdx.x]);
   float xt[KT_DMAX];
 #pragma unroll
   for (int j = 0; j < KT_DMAX; ++j) xt[j] = (j < d && n < N) ? (float)Xt[n * d + j] : 0.f;
   __syncthreads();
+  if (n >= ldk) return;
+  const bool live = n < N;
   for (int q = 0; q < KT_TP; ++q) {
     const int64_t pl = pt0 + q;
+    if (pl >= Pcpad) break;
     const float* xc = sxf + q * d;
     float s_iso = 0.f;
     if (ISO) {
@@ -371,53 +376,51 @@ __global__ void __launch_bounds__(KT_TN)
     for (int m = 0; m < M; ++m) {
       float s2;
       if (ISO) {
-        const float il = (float)inv_ls[m * d];
+        const float il = s_il[m * d];
         s2 = s_iso * il * il;
       } else {
         s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < KT_DMAX; ++j)
           if (j < d) {
-            const float df = (xc[j] - xt[j]) * (float)inv_ls[m * d + j];
+            const float df = (xc[j] - xt[j]) * s_il[m * d + j];
             s2 = fmaf(df, df, s2);
           }
       }
-      const float kv = (n < N) ? (float)constant[m] * stationary_f(s2, kind) : 0.f;
-      const float ks = scalbnf(kv, k_exp[m]);
+      const float ks = live ? s_c[m] * stationary_f(s2, kind) : 0.f;  // c * k(r), scaled by 2^kexp (exact)
       const __half h = __float2half_rn(ks);
       const __half l = __float2half_rn(ks - __half2float(h));
-      if (pl < Pcpad && n < ldk) {
-        Kh[m * plane + pl * ldk + n] = __half_as_ushort(h);
-        Kl[m * plane + pl * ldk + n] = __half_as_ushort(l);
-      }
-      double t = (n < N) ? (double)kv * alpha[(int64_t)m * N + n] : 0.0;
-      t = warp_sum(t);
-      if (lane == 0 && m < 4) wsum[warp][q][m] = t;
-    }
-  }
-  __syncthreads();
-  // fixed-order combination of the 4 warps -> one partial per (train block, candidate, objective)
-  for (int t = threadIdx.x; t < KT_TP * M; t += KT_TN) {
-    const int q = t / M, m = t - q * M;
-    const int64_t pl = pt0 + q;
-    if (pl < Pcpad && m < 4) {
-      double s = 0.0;
-      for (int w = 0; w < KT_TN / 32; ++w) s += wsum[w][q][m];
-      mean_part[((int64_t)blockIdx.x * Pcpad + pl) * M + m] = s;
+      Kh[m * plane + pl * ldk + n] = __half_as_ushort(h);
+      Kl[m * plane + pl * ldk + n] = __half_as_ushort(l);
     }
   }
 }
 
-__global__ void mean_finish_kernel(const double* __restrict__ part, int nblk, int64_t Pc, int64_t Pcpad, int M,
-                                   const double* __restrict__ ymean, const double* __restrict__ ystd, int64_t p_base,
-                                   double* __restrict__ mean) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= Pc * M) return;
-  int64_t pl = t / M;
-  int m = (int)(t - pl * M);
+// mean[p][m] = y_std * sum_n K_*[p][n] alpha[n] + y_mean from the split K_* (hi + lo = 22 bits): HBM-bound pass,
+// one warp per (objective, candidate) row, float64 accumulation in a fixed order
+__global__ void mean_split_kernel(const uint16_t* __restrict__ Kh, const uint16_t* __restrict__ Kl, int64_t Pc, int64_t N,
+                                  int64_t ldk, int64_t plane, int M, const int* __restrict__ k_exp,
+                                  const double* __restrict__ alpha, const double* __restrict__ ymean,
+                                  const double* __restrict__ ystd, int64_t p_base, double* __restrict__ mean) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= Pc * M) return;
+  const int m = (int)(w / Pc);
+  const int64_t pl = w - (int64_t)m * Pc;
+  const uint32_t* rh = reinterpret_cast<const uint32_t*>(Kh + m * plane + pl * ldk);
+  const uint32_t* rl = reinterpret_cast<const uint32_t*>(Kl + m * plane + pl * ldk);
+  const double* a = alpha + (int64_t)m * N;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += part[((int64_t)b * Pcpad + pl) * M + m];
-  mean[(p_base + pl) * M + m] = ystd[m] * s + ymean[m];
+  for (int64_t n2 = lane; 2 * n2 < N; n2 += 32) {  // two fp16 values per 32-bit load
+    const uint32_t h = rh[n2], l = rl[n2];
+    const float k0 = __half2float(__ushort_as_half((uint16_t)(h & 0xFFFFu))) + __half2float(__ushort_as_half((uint16_t)(l & 0xFFFFu)));
+    const float k1 = __half2float(__ushort_as_half((uint16_t)(h >> 16))) + __half2float(__ushort_as_half((uint16_t)(l >> 16)));
+    const int64_t n = 2 * n2;
+    s += (double)k0 * a[n];
+    if (n + 1 < N) s += (double)k1 * a[n + 1];
+  }
+  s = warp_sum(s);
+  if (lane == 0) mean[(p_base + pl) * M + m] = ystd[m] * scalbn(s, -k_exp[m]) + ymean[m];
 }
 
 __global__ void var_finish_tc_kernel(const double* __restrict__ vnorm, int64_t Pc, int64_t ld, int M,
@@ -498,11 +501,10 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   const int64_t Pc_alloc = P < Pc_max ? ceil_div(P, TM) * TM : Pc_max;
   const int nblk = (int)(Npad / KT_TN);
   DevBuf<uint16_t> Kh, Kl;
-  DevBuf<double> mpart, vnorm;
+  DevBuf<double> vnorm;
   DevBuf<int> abort_flag;
   DMO_TRY(Kh.alloc(ctx, (size_t)M * Pc_alloc * Npad));
   DMO_TRY(Kl.alloc(ctx, (size_t)M * Pc_alloc * Npad));
-  DMO_TRY(mpart.alloc(ctx, (size_t)nblk * Pc_alloc * M));
   DMO_TRY(vnorm.alloc(ctx, (size_t)M * Pc_alloc));
   DMO_TRY(abort_flag.alloc(ctx, 1));
   DMO_CUDA(cudaMemsetAsync(abort_flag.p, 0, sizeof(int), ctx->stream));
@@ -519,18 +521,18 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
     {
       ProfileScope ps(ctx, "gp_kstar");
       dim3 gk((unsigned)nblk, (unsigned)ceil_div(Pcpad, KT_TP));
-      size_t smem = (size_t)KT_TP * d * sizeof(float);
+      size_t smem = (size_t)(KT_TP * d + 4 * d + 4) * sizeof(float);
       if (gp->isotropic)
         DMO_LAUNCH(kstar_tensor_kernel<true>, gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel,
-                   gp->inv_ls.p, gp->constant.p, gp->Kexp.p, gp->alpha.p, Npad, kplane, Kh.p, Kl.p, mpart.p);
+                   gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p);
       else
         DMO_LAUNCH(kstar_tensor_kernel<false>, gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel,
-                   gp->inv_ls.p, gp->constant.p, gp->Kexp.p, gp->alpha.p, Npad, kplane, Kh.p, Kl.p, mpart.p);
+                   gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p);
     }
     {
       ProfileScope ps(ctx, "gp_mean");
-      DMO_LAUNCH(mean_finish_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, mpart.p, nblk, Pc, Pcpad, M, gp->ymean.p,
-                 gp->ystd.p, p_base, d_mean);
+      DMO_LAUNCH(mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane, M,
+                 gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
     }
     if (d_var) {
       GemmParams prm;

@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
   constexpr int NV = W / 4;
   constexpr int NW = T / 32;
   __shared__ uint4 tile[T * NV];
-  __shared__ int sh_r1[T];
-  __shared__ uint32_t sh_final[NW];
+  __shared__ __align__(16) int sh_r1[T];
+  __shared__ uint32_t sh_final[2 * NW];
+  __shared__ uint32_t sh_new[2 * NW];
   __shared__ int sh_blk;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -130,7 +131,6 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
       }
     }
     const uint32_t gidv = v[M - 1];
-    if (tid < NW) sh_final[tid] = 0u;
     __syncthreads();
 
     // ---- in-block dominator bitmask (sources earlier in the block); independent of any rank
@@ -221,52 +221,69 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
       wait_done(k);
       sh_r1[tid] = (int)__ldcg(rec + ((int64_t)k * T + tid) * W + M);  // rank + 1 of the predecessor block
       __syncthreads();
+      // independent broadcast loads + predicated max: no load-latency chain on the critical path
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
-        uint32_t mm = pmask[w];
-        while (mm) {
-          const int s = __ffs(mm) - 1;
-          mm &= mm - 1;
-          best = max(best, sh_r1[w * 32 + s]);
+        const uint32_t mm = pmask[w];
+#pragma unroll
+        for (int s4 = 0; s4 < 8; ++s4) {
+          const int4 rr = *reinterpret_cast<const int4*>(&sh_r1[w * 32 + s4 * 4]);
+          best = ((mm >> (s4 * 4 + 0)) & 1u) ? max(best, rr.x) : best;
+          best = ((mm >> (s4 * 4 + 1)) & 1u) ? max(best, rr.y) : best;
+          best = ((mm >> (s4 * 4 + 2)) & 1u) ? max(best, rr.z) : best;
+          best = ((mm >> (s4 * 4 + 3)) & 1u) ? max(best, rr.w) : best;
         }
       }
       __syncthreads();
     }
 
-    // ---- resolve the in-block chain: a target is final once all its in-block dominators are
+    // ---- resolve the in-block chain.  Round t: every thread folds in the dominators that became final in round
+    // t-1 (a handful of bits), and becomes final itself once all its in-block dominators are.  Double-buffered
+    // bit words -> one barrier per round.
     bool fin = false;
-    int myrank = 0;
+    int r = best;
+    if (tid < 2 * NW) {
+      sh_final[tid] = 0u;  // [2][NW]
+      sh_new[tid] = 0u;
+    }
+    __syncthreads();
     for (int round = 0; round <= T; ++round) {
+      const int cur = round & 1, nxt = cur ^ 1;
       bool ready = !fin;
+      uint32_t fw = 0u;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) ready = ready && ((mask[w] & ~sh_final[w]) == 0u);
-      if (ready) {
-        int r = best;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          uint32_t m = mask[w];
-          while (m) {
-            int s = __ffs(m) - 1;
-            m &= m - 1;
-            r = max(r, sh_r1[w * 32 + s]);
-          }
+      for (int w = 0; w < NW; ++w) {
+        const uint32_t f = sh_final[cur * NW + w];
+        uint32_t mm = mask[w] & sh_new[cur * NW + w];
+        while (mm) {
+          const int s = __ffs(mm) - 1;
+          mm &= mm - 1;
+          r = max(r, sh_r1[w * 32 + s]);
         }
-        myrank = r;
+        ready = ready && ((mask[w] & ~f) == 0u);
+        if (w == warp) fw = f;
+      }
+      if (ready) {
         sh_r1[tid] = r + 1;
         fin = true;
       }
       const unsigned newly = __ballot_sync(0xffffffffu, ready);
-      __syncthreads();
-      if (lane == 0 && newly) sh_final[warp] |= newly;
+      if (lane == 0) {
+        sh_new[nxt * NW + warp] = newly;
+        sh_final[nxt * NW + warp] = fw | newly;
+      }
       if (__syncthreads_and(fin ? 1 : 0)) break;
     }
+    const int myrank = r;
 
     // ---- publish
     rec[i * W + M] = (uint32_t)(myrank + 1);
     rankS[i] = myrank;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) st_release_gpu(done + b, 1);
+    __syncthreads();  // all ranks of the block are written (bar.sync orders them before thread 0's release)
+    if (tid == 0) {
+      __threadfence();
+      st_release_gpu(done + b, 1);
+    }
   }
 }
 

@@ -192,6 +192,41 @@ int dmo_ehvi_select(dmo_ctx* ctx, const double* F, int64_t nf, const double* mea
  * is_dup[i] = 1 iff an earlier row j < i has ||x_i - x_j||_2 <= eps. */
 int dmo_get_duplicates(dmo_ctx* ctx, const double* X, int64_t n, int d, double eps, uint8_t* is_dup);
 
+/* ---- A11: AGE-MOEA survival score (greedy part) -------------------------------------
+ * replaces the O(m^2) greedy loop of AGEMOEA.survival_score (dmosopt/AGEMOEA.py:398-428):
+ * yn (m,M) normalised front, nn (m,) = ||yn_i||_p, extreme (n_ext,) pre-selected corner solutions;
+ * crowd (m,): inf for the extremes, else the sum of the two smallest distances
+ * ||yn_s - yn_r||_p / nn[s] to the already selected set at the moment r is selected. */
+int dmo_age_survival(dmo_ctx* ctx, const double* yn, const double* nn, int64_t m, int M, double p,
+                     const int32_t* extreme, int n_ext, double* crowd);
+
+/* ---- A12: SMPSO --------------------------------------------------------------------------
+ * dmo_smpso_velocity: SMPSO.velocity_vector (dmosopt/SMPSO.py:316-348) for one swarm given its scalar
+ *   draws: position (n,d) float32 state, velocity (n,d), the two leader rows (d,) -> out (n,d);
+ *   f32_difference != 0 forms (leader - position) in float32 (both operands float32 in NumPy), else float64.
+ * dmo_mutate_groups: per_group polynomial mutants per group (swarm), parents drawn uniformly inside each
+ *   group of group_size rows of pop_x (SMPSO.py:167-182; MOEA.mutation, MOEA.py:191-212), Philox draws.
+ *   children (n_groups*per_group, d); parent_rows (n_groups*per_group,) may be NULL. */
+int dmo_smpso_velocity(dmo_ctx* ctx, const float* position, const double* velocity, const double* leader1,
+                       const double* leader2, int f32_difference, int64_t n, int d, double w, double c1,
+                       double r1, double c2, double r2, double chi, const double* xlb, const double* xub,
+                       double* out);
+int dmo_mutate_groups(dmo_ctx* ctx, const double* pop_x, int64_t group_size, int64_t n_groups,
+                      int64_t per_group, int d, const double* di_mutation, const double* xlb,
+                      const double* xub, double mutation_rate, uint64_t seed, uint64_t stream_id,
+                      double* children, int64_t* parent_rows);
+
+/* ---- A13 / A15: MO-CMA-ES ----------------------------------------------------------------
+ * dmo_cmaes_sample: individuals[i] = x_p + sigma_p * (A_p @ z_i), p = p_idx[i] (dmosopt/CMAES.py:263-267);
+ *   sigmas (n_parents, sigma_cols) with sigma_cols = 1 or d, A (n_parents,d,d), z (n,d).
+ * dmo_cmaes_update_cholesky: CMAES.updateCholesky (dmosopt/CMAES.py:489-537) for n individuals at once,
+ *   in place on A / Ainv (n,d,d) and pc (n,d); z (n,d), psucc (n,). */
+int dmo_cmaes_sample(dmo_ctx* ctx, const double* parents_x, const double* sigmas, int sigma_cols,
+                     const double* A, int64_t n_parents, const int64_t* p_idx, const double* z, int64_t n,
+                     int d, double* individuals);
+int dmo_cmaes_update_cholesky(dmo_ctx* ctx, double* A, double* Ainv, double* pc, const double* z,
+                              const double* psucc, int64_t n, int d, double cc, double ccov, double pthresh);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,8 +132,66 @@ def get_duplicates(X, eps=1e-16):
     return moea.get_duplicates(X, eps)
 
 
+def age_survival(yn, nn, p, extreme):
+    """Greedy loop of AGEMOEA.survival_score restated with the kernel's incremental two-smallest update."""
+    from oracle import agemoea
+
+    yn = np.asarray(yn, dtype=np.float64)
+    m = yn.shape[0]
+    dist = agemoea.minkowski(yn, yn, p) / np.asarray(nn)[:, None]
+    crowd = np.zeros(m)
+    selected = np.zeros(m, dtype=bool)
+    selected[np.asarray(extreme)] = True
+    crowd[selected] = np.inf
+    remaining = [i for i in range(m) if not selected[i]]
+    while remaining:
+        sel = np.flatnonzero(selected)
+        D = dist[np.ix_(sel, remaining)].T
+        score = np.partition(D, 1, axis=1)[:, :2].sum(axis=1) if D.shape[1] > 1 else D[:, 0]
+        j = int(np.argmax(score))
+        best = remaining.pop(j)
+        selected[best] = True
+        crowd[best] = score[j]
+    return crowd
+
+
+def smpso_velocity(position, velocity, leader1, leader2, w, c1, r1, c2, r2, chi, xlb, xub):
+    pos = np.asarray(position)
+    d1 = np.asarray(np.asarray(leader1) - pos, dtype=np.float64)  # NumPy's own dtype promotion
+    d2 = np.asarray(np.asarray(leader2) - pos, dtype=np.float64)
+    delta = (np.asarray(xub, float) - np.asarray(xlb, float)) / 2
+    out = (w * np.asarray(velocity, dtype=np.float64) + c1 * r1 * d1 + c2 * r2 * d2) * chi
+    return np.clip(out, -delta, delta)
+
+
+def mutate_groups(pop_x, group_size, n_groups, per_group, di_mutation, xlb, xub, mutation_rate, seed, stream_id, return_parents=False):
+    pop_x = np.asarray(pop_x, dtype=np.float64)
+    d = pop_x.shape[1]
+    r = _rng(seed, stream_id)
+    total = n_groups * per_group
+    pi = r.integers(0, group_size, size=total) + np.repeat(np.arange(n_groups), per_group) * group_size
+    u = r.random((total, d))
+    out = moea.mutation_u(pop_x[pi], u, np.asarray(di_mutation), np.asarray(xlb), np.asarray(xub), mutation_rate)
+    return (out, pi) if return_parents else out
+
+
+def cmaes_sample(parents_x, sigmas, A, p_idx, z):
+    p_idx = np.asarray(p_idx)
+    return np.asarray(parents_x)[p_idx] + np.asarray(sigmas)[p_idx] * np.einsum("ijk,ik->ij", np.asarray(A)[p_idx], np.asarray(z))
+
+
+def cmaes_update_cholesky(A, Ainv, pc, z, psucc, cc, ccov, pthresh):
+    from oracle import cmaes
+
+    A, Ainv, pc = np.array(A, dtype=float), np.array(Ainv, dtype=float), np.array(pc, dtype=float)
+    for i in range(pc.shape[0]):
+        A[i], Ainv[i], pc[i] = cmaes.update_cholesky(A[i], Ainv[i], np.asarray(z)[i], float(np.asarray(psucc)[i]), pc[i], cc, ccov, pthresh)
+    return A, Ainv, pc
+
+
 FUNCTIONS = ["rank_nd", "crowding_distance", "euclidean_distance", "order_mo", "remove_worst", "tournament", "mutation_u", "sbx_u",
-             "nsga2_generate", "GPHandle", "hypervolume", "ehvi_select", "get_duplicates"]
+             "nsga2_generate", "GPHandle", "hypervolume", "ehvi_select", "get_duplicates", "age_survival", "smpso_velocity", "mutate_groups",
+             "cmaes_sample", "cmaes_update_cholesky"]
 
 
 def install(monkeypatch):

@@ -562,8 +562,68 @@ def gen_cmaes(rng):
     save("cmaes", **out)
 
 
+def gen_plugins(rng):
+    """Full update steps of the reference AGEMOEA / SMPSO / CMAES plugins on recorded offspring."""
+    out = {}
+    d, M, pop = 8, 3, 40
+    bounds = np.column_stack((np.zeros(d), np.ones(d)))
+    W = rng.random((d, M))
+    f = lambda x: dtlz2(x, M) + 0.01 * (x @ W)  # noqa: E731  (tie-free objectives)
+    # ---- AGEMOEA: initialize + two updates (set-level parity: row order inside a front is unstable in the reference)
+    x0 = rng.random((pop + 10, d))
+    y0 = f(x0).astype(np.float32)
+    opt = AGEMOEA.AGEMOEA(popsize=pop, nInput=d, nOutput=M, model=model_mod.Model())
+    out["age_x0"], out["age_y0"] = x0.copy(), y0.copy()  # the reference keeps views of its inputs and writes into them
+    opt.initialize_strategy(x0, y0, bounds, np.random.default_rng(3))
+    out["age_init_rank"], out["age_init_cd"] = opt.state.rank.copy(), opt.state.crowd_dist.copy()
+    for g in range(2):
+        xg = np.clip(opt.state.population_parm + 0.05 * rng.standard_normal((pop, d)), 0, 1)
+        yg = f(xg)
+        opt.update(xg, yg, {})
+        out[f"age_g{g}_xgen"], out[f"age_g{g}_ygen"] = xg, yg
+        out[f"age_g{g}_px"], out[f"age_g{g}_py"] = opt.state.population_parm.copy(), opt.state.population_obj.copy()
+        out[f"age_g{g}_rank"], out[f"age_g{g}_cd"] = opt.state.rank.copy(), opt.state.crowd_dist.copy()
+    # ---- SMPSO: initialize (velocity from the generator) + one update with a fresh generator
+    pop_s, sw = 24, 5
+    x0 = rng.random((pop_s * sw, d))
+    y0 = f(x0).astype(np.float32)
+    opt = SMPSO.SMPSO(popsize=pop_s, nInput=d, nOutput=M, model=model_mod.Model(), distance_metric=None)
+    opt.initialize_strategy(x0, y0, bounds, np.random.default_rng(11))
+    out["smpso_x0"], out["smpso_y0"] = x0, y0
+    out["smpso_init_px"], out["smpso_init_py"], out["smpso_init_vel"] = opt.state.population_parm.copy(), opt.state.population_obj.copy(), opt.state.velocity.copy()
+    xg, _ = opt.generate()
+    out["smpso_xgen_shape"] = np.array(xg.shape)
+    out["smpso_xgen_positions"] = xg.reshape(sw, 2 * pop_s, d)[:, :pop_s].copy()  # deterministic half of x_gen
+    yg = f(xg.astype(np.float64))
+    opt.local_random = np.random.default_rng(12)
+    opt.update(xg, yg, {})
+    out["smpso_xgen"], out["smpso_ygen"] = xg, yg
+    out["smpso_g0_px"], out["smpso_g0_py"], out["smpso_g0_vel"] = opt.state.population_parm.copy(), opt.state.population_obj.copy(), opt.state.velocity.copy()
+    out["smpso_g0_ranks"] = np.stack(opt.state.ranks)
+    out["smpso_succ"] = np.array(opt.state.successful_children)
+    # ---- CMAES: initialize + two full updates on recorded offspring / parent indices
+    popc = 30
+    x0 = rng.random((popc + 8, d))
+    y0 = f(x0)
+    opt = CMAES.CMAES(popsize=popc, nInput=d, nOutput=M, model=model_mod.Model(), distance_metric=None)
+    opt.initialize_strategy(x0, y0, bounds, np.random.default_rng(21))
+    out["cma_x0"], out["cma_y0"] = x0, y0
+    out["cma_init_px"], out["cma_init_sig"] = opt.state.parents_x.copy(), opt.state.sigmas.copy()
+    for g in range(3):
+        xg, stg = opt.generate()
+        yg = f(xg)
+        if g == 0:  # sampling golden: record the normal draws by replaying the generator
+            out["cma_g0_parents_x"], out["cma_g0_sigmas"], out["cma_g0_A"] = opt.state.parents_x.copy(), opt.state.sigmas.copy(), opt.state.A.copy()
+        opt.update(xg, yg, stg)
+        out[f"cma_g{g}_xgen"], out[f"cma_g{g}_ygen"], out[f"cma_g{g}_pidx"] = xg, yg, stg["p_idx"]
+        out[f"cma_g{g}_px"], out[f"cma_g{g}_py"] = opt.state.parents_x.copy(), opt.state.parents_y.copy()
+        out[f"cma_g{g}_sig"], out[f"cma_g{g}_A"], out[f"cma_g{g}_Ainv"] = opt.state.sigmas.copy(), opt.state.A.copy(), opt.state.Ainv.copy()
+        out[f"cma_g{g}_pc"], out[f"cma_g{g}_psucc"], out[f"cma_g{g}_rank"] = opt.state.pc.copy(), opt.state.psucc.copy(), opt.state.rank.copy()
+    save("plugins", **out)
+
+
 def main():
-    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes"]
+    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes", "plugins"]
     gens = {
         "dda": gen_dda,
         "distance": gen_distance,
@@ -578,6 +638,7 @@ def main():
         "agemoea": gen_agemoea,
         "smpso": gen_smpso,
         "cmaes": gen_cmaes,
+        "plugins": gen_plugins,
     }
     for i, name in enumerate(which):
         gens[name](np.random.default_rng(20260921 + i * 0 + sum(map(ord, name))))

@@ -415,3 +415,95 @@ def test_surrogate_generation_loop_end_to_end(L):
     hv0 = L.hypervolume(zdt1(X), np.array([1.1, 8.0]))
     hv1 = L.hypervolume(res.best_y.astype(np.float64), np.array([1.1, 8.0]))
     assert hv1 > hv0
+
+
+# ------------------------------------------------------------------------------------------ A11 / A12 / A13-A15 kernels
+def test_age_survival_vs_oracle(L):
+    from oracle import agemoea
+
+    g = load_golden("agemoea")
+    for k in cases(g):
+        fy = g[f"c{k}_front_y"]
+        m, M = fy.shape
+        if m < M:
+            continue
+        ideal = fy.min(axis=0)
+        yf = fy - ideal
+        ext = agemoea.corner_solutions(yf)
+        nz = agemoea.hyperplane_normalization(yf, ext)
+        yn = yf / nz
+        p = agemoea.geometry_p(yn, ext)
+        nn = np.linalg.norm(yn, p, axis=1)
+        crowd = L.age_survival(yn, nn, p, ext)
+        _, _, cd = agemoea.survival_score(fy, ideal)
+        np.testing.assert_allclose(crowd, cd, rtol=1e-10)
+        np.testing.assert_allclose(np.sort(crowd), np.sort(g[f"c{k}_ss_cd"]), rtol=1e-10)
+    # a large, nearly flat front (the expensive case of SURVEY section 6: 13.4 s on the CPU at m = 800)
+    rng = np.random.default_rng(5)
+    x = rng.random((3000, 3))
+    fy = x / np.linalg.norm(x, axis=1, keepdims=True)
+    ideal = fy.min(axis=0)
+    yf = fy - ideal
+    ext = agemoea.corner_solutions(yf)
+    nz = agemoea.hyperplane_normalization(yf, ext)
+    yn = yf / nz
+    p = agemoea.geometry_p(yn, ext)
+    crowd = L.age_survival(yn, np.linalg.norm(yn, p, axis=1), p, ext)
+    assert np.isinf(crowd[ext]).all() and np.isfinite(np.delete(crowd, ext)).all() and (np.delete(crowd, ext) > 0).all()
+
+
+def test_smpso_kernels(L):
+    from oracle import smpso as osm
+
+    g = load_golden("smpso")
+    for k in cases(g):
+        u5 = g[f"c{k}_u5"]
+        w, c1, c2 = 0.1 + 0.4 * u5[2], 1.5 + u5[3], 1.5 + u5[4]
+        chi = osm.constriction(c1, c2)
+        i1, i2 = int(g[f"c{k}_ints"][0]), int(g[f"c{k}_ints"][1])
+        if g[f"c{k}_crowd"][i1] < g[f"c{k}_crowd"][i2]:
+            i1, i2 = i2, i1
+        v = L.smpso_velocity(g[f"c{k}_pos"], g[f"c{k}_vel"], g[f"c{k}_arch"][i1], g[f"c{k}_arch"][i2], w, c1, u5[0], c2, u5[1], chi, g[f"c{k}_xlb"], g[f"c{k}_xub"])
+        np.testing.assert_allclose(v, g[f"c{k}_vout"], rtol=1e-13, atol=1e-15)
+    # grouped mutation: parents stay inside their swarm, children inside the bounds, reproducible per (seed, stream)
+    rng = np.random.default_rng(1)
+    pop, sw, d = 50, 5, 7
+    X = rng.random((pop * sw, d))
+    a, par = L.mutate_groups(X, pop, sw, pop, np.full(d, 20.0), np.zeros(d), np.ones(d), 1.0 / d, 3, 9, return_parents=True)
+    b = L.mutate_groups(X, pop, sw, pop, np.full(d, 20.0), np.zeros(d), np.ones(d), 1.0 / d, 3, 9)
+    assert np.array_equal(a, b) and a.shape == (pop * sw, d) and np.all((a >= 0) & (a <= 1))
+    assert np.array_equal(par // pop, np.repeat(np.arange(sw), pop))
+    assert np.abs(a - X[par]).max() < 0.6 and np.mean(np.abs(a - X[par]) > 0) > 0.9  # every gene is perturbed (MOEA.py:204-210)
+    counts = np.bincount(par % pop, minlength=pop)
+    assert counts.max() < 20  # roughly uniform parent draws
+
+
+def test_cmaes_kernels(L):
+    from oracle import cmaes as ocm
+
+    rng = np.random.default_rng(2)
+    npar, n, d = 40, 64, 9
+    px = rng.random((npar, d))
+    sig = rng.random((npar, d)) * 0.01
+    A = np.eye(d)[None] + 0.1 * rng.standard_normal((npar, d, d))
+    pidx = rng.integers(0, npar, size=n)
+    z = rng.standard_normal((n, d))
+    out = L.cmaes_sample(px, sig, A, pidx, z)
+    np.testing.assert_allclose(out, px[pidx] + sig[pidx] * np.einsum("ijk,ik->ij", A[pidx], z), rtol=1e-13, atol=1e-15)
+    Ainv = np.linalg.inv(A)
+    pc = rng.standard_normal((npar, d)) * 0.1
+    ps = rng.uniform(0.1, 0.7, size=npar)
+    zz = rng.standard_normal((npar, d))
+    A2, B2, pc2 = L.cmaes_update_cholesky(A, Ainv, pc, zz, ps, 2.0 / (d + 2), 2.0 / (d * d + 6), 0.44)
+    for i in range(npar):
+        a, b, c = ocm.update_cholesky(A[i], Ainv[i], zz[i], ps[i], pc[i], 2.0 / (d + 2), 2.0 / (d * d + 6), 0.44)
+        np.testing.assert_allclose(A2[i], a, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(B2[i], b, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(pc2[i], c, rtol=1e-13, atol=1e-15)
+
+
+def test_age_smpso_cmaes_plugins_golden_on_gpu(L):
+    import dmosopt_b200 as b2
+    from test_host_plugins import _run_plugin_goldens
+
+    _run_plugin_goldens(b2)

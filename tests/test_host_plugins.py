@@ -92,6 +92,73 @@ def test_gpr_matern_plugin_matches_reference_predictions(fake):
         assert len(sm.evaluate(g[f"c{k}_xtest"])) == 2
 
 
+def _run_plugin_goldens(b2):
+    """Shared by the CPU (oracle-backed seam) and GPU runs: reference plugin state sequences (tests/golden/plugins.npz)."""
+    from conftest import sort_rows
+
+    g = load_golden("plugins")
+    d, M = 8, 3
+    bounds = np.column_stack((np.zeros(d), np.ones(d)))
+    # ---- AGE-MOEA: the selected set, ranks and crowding values (row order inside a front is unstable in the reference)
+    pop = g["age_g0_px"].shape[0]
+    opt = b2.AGEMOEA(popsize=pop, nInput=d, nOutput=M, model=b2.Model())
+    opt.initialize_strategy(g["age_x0"], g["age_y0"], bounds, np.random.default_rng(3))
+    assert np.array_equal(np.sort(opt.state.rank), np.sort(g["age_init_rank"]))
+    np.testing.assert_allclose(np.sort(opt.state.crowd_dist), np.sort(g["age_init_cd"]), rtol=1e-5)
+    # from here on continue from the reference's own state (its initial row order is implementation defined)
+    for gi in range(2):
+        opt.update(g[f"age_g{gi}_xgen"], g[f"age_g{gi}_ygen"], {})
+        assert np.array_equal(sort_rows(opt.state.population_parm), sort_rows(g[f"age_g{gi}_px"])), gi
+        assert np.array_equal(sort_rows(opt.state.population_obj), sort_rows(g[f"age_g{gi}_py"])), gi
+        assert np.array_equal(np.sort(opt.state.rank), np.sort(g[f"age_g{gi}_rank"]))
+        np.testing.assert_allclose(np.sort(opt.state.crowd_dist), np.sort(g[f"age_g{gi}_cd"]), rtol=1e-5)
+        opt.state.population_parm[:] = g[f"age_g{gi}_px"]
+        opt.state.population_obj[:] = g[f"age_g{gi}_py"]
+        opt.state.rank[:] = g[f"age_g{gi}_rank"]
+        opt.state.crowd_dist[:] = g[f"age_g{gi}_cd"]
+    x_gen, _ = opt.generate()
+    assert pop - 1 <= x_gen.shape[0] <= pop + 1
+    # ---- SMPSO: exact state after initialize and after one update driven by the same NumPy generator
+    pop_s = g["smpso_init_px"].shape[0] // 5
+    opt = b2.SMPSO(popsize=pop_s, nInput=d, nOutput=M, model=b2.Model(), distance_metric=None)
+    opt.initialize_strategy(g["smpso_x0"], g["smpso_y0"], bounds, np.random.default_rng(11))
+    assert np.array_equal(opt.state.population_parm, g["smpso_init_px"]) and np.array_equal(opt.state.population_obj, g["smpso_init_py"])
+    assert np.array_equal(opt.state.velocity, g["smpso_init_vel"])
+    xg, _ = opt.generate()
+    assert list(xg.shape) == list(g["smpso_xgen_shape"]) and xg.dtype == g["smpso_xgen"].dtype
+    assert np.array_equal(xg.reshape(5, 2 * pop_s, d)[:, :pop_s], g["smpso_xgen_positions"])
+    assert np.all(xg >= 0) and np.all(xg <= 1)
+    opt.local_random = np.random.default_rng(12)
+    opt.update(g["smpso_xgen"], g["smpso_ygen"], {})
+    np.testing.assert_allclose(opt.state.velocity, g["smpso_g0_vel"], rtol=1e-13, atol=1e-15)
+    assert np.array_equal(opt.state.population_parm, g["smpso_g0_px"]) and np.array_equal(opt.state.population_obj, g["smpso_g0_py"])
+    assert np.array_equal(np.stack(opt.state.ranks), g["smpso_g0_ranks"]) and opt.state.successful_children == int(g["smpso_succ"])
+    # ---- MO-CMA-ES: three full updates on the recorded offspring
+    popc = g["cma_init_px"].shape[0]
+    opt = b2.CMAES(popsize=popc, nInput=d, nOutput=M, model=b2.Model(), distance_metric=None)
+    opt.initialize_strategy(g["cma_x0"], g["cma_y0"], bounds, np.random.default_rng(21))
+    assert np.array_equal(opt.state.parents_x, g["cma_init_px"]) and np.array_equal(opt.state.sigmas, g["cma_init_sig"])
+    for gi in range(3):
+        opt.update(g[f"cma_g{gi}_xgen"], g[f"cma_g{gi}_ygen"], {"p_idx": g[f"cma_g{gi}_pidx"]})
+        assert np.array_equal(opt.state.parents_x, g[f"cma_g{gi}_px"]), gi
+        assert np.array_equal(opt.state.parents_y, g[f"cma_g{gi}_py"]) and np.array_equal(opt.state.rank, g[f"cma_g{gi}_rank"])
+        np.testing.assert_allclose(opt.state.psucc, g[f"cma_g{gi}_psucc"], rtol=1e-13)
+        np.testing.assert_allclose(opt.state.sigmas, g[f"cma_g{gi}_sig"], rtol=1e-13)
+        np.testing.assert_allclose(opt.state.A, g[f"cma_g{gi}_A"], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(opt.state.Ainv, g[f"cma_g{gi}_Ainv"], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(opt.state.pc, g[f"cma_g{gi}_pc"], rtol=1e-12, atol=1e-15)
+    x_new, stg = opt.generate()
+    assert x_new.shape == (opt.opt_params.mu, d) and len(stg["p_idx"]) == opt.opt_params.mu
+    px, py = opt.population_objectives
+    assert px.shape[1] == d and py.shape[1] == M
+
+
+def test_age_smpso_cmaes_plugins_reproduce_reference(fake):
+    import dmosopt_b200 as b2
+
+    _run_plugin_goldens(b2)
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "dmosopt")), reason="reference checkout not present")
 def test_plugins_drop_into_unmodified_moasmo_epoch(fake):
     """The reference's own MOASMO.epoch (dmosopt/MOASMO.py:196-470) drives the plugins by import path."""
