@@ -128,7 +128,10 @@ class MOEA(object):
 
     def generate(self, **params):
         x, state = self.generate_strategy(**params)
-        return np.clip(x, self.bounds[:, 0], self.bounds[:, 1]), state
+        lb, ub = self.bounds[:, 0], self.bounds[:, 1]
+        if isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.writeable:
+            return np.clip(x, lb, ub, out=x), state  # same values as MOEA.py:155, without a second 8*P*d byte buffer
+        return np.clip(x, lb, ub), state
 
     def update(self, x, y, state, **params):
         self.update_strategy(x, y, state, **params)

@@ -85,9 +85,12 @@ class NSGA2(MOEA):
         """NSGA2.py:84-114."""
         x, y, rank, _ = sortMO(x, y, x_distance_metrics=self.x_distance_metrics, y_distance_metrics=self.y_distance_metrics)
         n = self.opt_params.popsize
+        # same values / dtypes as the reference's slices; the parameter matrix is kept in page-locked memory because it
+        # crosses the PCIe bus twice per generation (generate, update)
+        px = _lib.pinned_like(x[:n])
         return Struct(
             bounds=bounds,
-            population_parm=x[:n],
+            population_parm=px,
             population_obj=y[:n],
             rank=rank[:n],
             successful_crossovers=0,
@@ -120,19 +123,29 @@ class NSGA2(MOEA):
         """NSGA2.py:187-236."""
         st = self.state
         popsize = self.opt_params.popsize
-        population_parm = np.vstack((x_gen, st.population_parm))
-        population_obj = np.vstack((y_gen, st.population_obj))
-        population_parm, population_obj, rank, perm = remove_worst(
-            population_parm, population_obj, popsize,
-            x_distance_metrics=self.x_distance_metrics, y_distance_metrics=self.y_distance_metrics, return_perm=True,
-        )
+        builtin = self.x_distance_metrics is None and (self.y_distance_metrics is None or self.y_distance_metrics[0] in ("crowding", "euclidean"))
+        if builtin and not self.opt_params.adaptive_population_size:
+            # children stacked over parents (NSGA2.py:205-206) on the device; survivors land directly in the state array
+            code = {None: _lib.METRIC_NONE, "crowding": _lib.METRIC_CROWDING, "euclidean": _lib.METRIC_EUCLIDEAN}[
+                None if self.y_distance_metrics is None else self.y_distance_metrics[0]]
+            out_x = st.population_parm if st.population_parm.dtype == np.float64 and st.population_parm.shape[0] == popsize else None
+            population_parm, population_obj, rank, perm = _lib.remove_worst_pair(
+                x_gen, y_gen, st.population_parm, st.population_obj, popsize, code, out_X=out_x)
+        else:
+            population_parm = np.vstack((x_gen, st.population_parm))
+            population_obj = np.vstack((y_gen, st.population_obj))
+            population_parm, population_obj, rank, perm = remove_worst(
+                population_parm, population_obj, popsize,
+                x_distance_metrics=self.x_distance_metrics, y_distance_metrics=self.y_distance_metrics, return_perm=True,
+            )
         st.successful_crossovers += np.count_nonzero(np.isin(state["crossover_indices"], perm, assume_unique=True)) / 2
         st.successful_mutations += np.count_nonzero(np.isin(state["mutation_indices"], perm, assume_unique=True))
         if self.opt_params.adaptive_population_size:
             st.population_parm, st.population_obj, st.rank = population_parm, population_obj, rank
             self.update_population_size()
         else:
-            st.population_parm[:] = population_parm
+            if population_parm is not st.population_parm:
+                st.population_parm[:] = population_parm
             st.population_obj[:] = population_obj
             st.rank[:] = rank
         if self.opt_params.adaptive_operator_rates:

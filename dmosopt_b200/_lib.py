@@ -54,6 +54,7 @@ _SIGNATURES = {
     "dmo_euclidean_distance": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp]),
     "dmo_order_mo": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp]),
     "dmo_remove_worst": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp, _c_int, _c_i64, _vp, _vp, _vp, _vp]),
+    "dmo_remove_worst_pair": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _c_i64, _vp, _vp, _vp, _vp]),
     "dmo_tournament": (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_u64, _c_u64, _vp, _vp]),
     "dmo_mutation_u": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _vp]),
     "dmo_sbx_u": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _vp, _vp]),
@@ -268,6 +269,17 @@ def pinned_empty(shape, dtype=np.float64):
     return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
 
 
+def pinned_like(a):
+    """Page-locked copy of ``a`` (same dtype / values); falls back to a plain copy when no context exists yet."""
+    a = np.asarray(a)
+    try:
+        out = pinned_empty(a.shape, a.dtype)
+    except DmoError:
+        return np.array(a, copy=True)
+    out[...] = a
+    return out
+
+
 # --------------------------------------------------------------------------- A1/A2
 def rank_nd(Y):
     """dda.dda_ens (dmosopt/dda.py:97-152) -> int64 rank array (canonical non-dominated rank)."""
@@ -331,6 +343,29 @@ def remove_worst(X, Y, keep, metric=METRIC_NONE, extra_desc_keys=None):
     _check(
         load_library().dmo_remove_worst(context(), _ptr(X), _ptr(Y), n, d, M, metric, tab, nex, keep, _ptr(Xo), _ptr(Yo), _ptr(rank), _ptr(perm)),
         "dmo_remove_worst",
+    )
+    return Xo, Yo, rank.astype(np.intp), perm
+
+
+def remove_worst_pair(Xa, Ya, Xb, Yb, keep, metric=METRIC_NONE, out_X=None):
+    """remove_worst(vstack(Xa, Xb), vstack(Ya, Yb), keep) without the host-side concatenation.
+
+    ``out_X`` (optional, float64 C-contiguous (keep, d)) receives the surviving rows directly; it may be ``Xb`` itself.
+    """
+    Xa, Ya, Xb, Yb = _f64(Xa), _f64(Ya), _f64(Xb), _f64(Yb)
+    na, d = Xa.shape
+    nb = Xb.shape[0]
+    M = Ya.shape[1]
+    keep = int(min(keep, na + nb))
+    if out_X is not None and (out_X.dtype != np.float64 or not out_X.flags.c_contiguous or out_X.shape != (keep, d)):
+        out_X = None
+    Xo = out_X if out_X is not None else np.empty((keep, d), dtype=np.float64)
+    Yo = np.empty((keep, M), dtype=np.float64)
+    rank = np.empty(keep, dtype=np.int32)
+    perm = np.empty(keep, dtype=np.int64)
+    _check(
+        load_library().dmo_remove_worst_pair(context(), _ptr(Xa), _ptr(Ya), na, _ptr(Xb), _ptr(Yb), nb, d, M, metric, keep, _ptr(Xo), _ptr(Yo), _ptr(rank), _ptr(perm)),
+        "dmo_remove_worst_pair",
     )
     return Xo, Yo, rank.astype(np.intp), perm
 

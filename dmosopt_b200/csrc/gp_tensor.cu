@@ -325,7 +325,7 @@ __global__ void split_linv_kernel(const double* __restrict__ Linv, int64_t Npad,
   if (threadIdx.x == 0) inv_scale[row] = (mx > 0.0) ? (float)scalbn(1.0, -e - k_exp[m]) : 0.f;
 }
 
-constexpr int KT_TN = 128, KT_TP = 32, KT_DMAX = 64;
+constexpr int KT_TN = 128, KT_TP = 32;
 
 __device__ __forceinline__ float stationary_f(float s2, int kind) {
   if (kind == DMO_KERNEL_MATERN52) {
@@ -335,18 +335,20 @@ __device__ __forceinline__ float stationary_f(float s2, int kind) {
   return expf(-0.5f * s2);
 }
 
-// K_* in fp32 -> scaled fp16 hi / lo.  One thread per training point, KT_TP candidates per block.
-template <bool ISO>
+// K_* in fp32 -> scaled fp16 hi / lo.  Each thread owns two adjacent training points (their coordinates live in
+// registers, results leave as packed half2), a block covers 256 training points x KT_TP candidates; the candidate
+// tile is read from shared memory as broadcasts.
+template <bool ISO, int DMAX>
 __global__ void __launch_bounds__(KT_TN)
     kstar_tensor_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, int64_t Pcpad,
                         const double* __restrict__ Xt, int64_t N, int d, int M, int kind,
                         const double* __restrict__ inv_ls, const double* __restrict__ constant,
                         const int* __restrict__ k_exp, int64_t ldk, int64_t plane, uint16_t* __restrict__ Kh,
                         uint16_t* __restrict__ Kl) {
-  extern __shared__ float sxf[];  // [KT_TP][d] candidate tile, then [M][d] 1/l, [M] c * 2^kexp
+  extern __shared__ float sxf[];  // [KT_TP][d] candidate tile, then [4][d] 1/l, [4] c * 2^kexp
   float* s_il = sxf + KT_TP * d;
   float* s_c = s_il + 4 * d;
-  const int64_t n = (int64_t)blockIdx.x * KT_TN + threadIdx.x;
+  const int64_t n0 = ((int64_t)blockIdx.x * KT_TN + threadIdx.x) * 2;
   const int64_t pt0 = (int64_t)blockIdx.y * KT_TP;
   for (int t = threadIdx.x; t < KT_TP * d; t += KT_TN) {
     int64_t p = p_base + pt0 + t / d;
@@ -354,44 +356,57 @@ __global__ void __launch_bounds__(KT_TN)
   }
   for (int t = threadIdx.x; t < M * d; t += KT_TN) s_il[t] = (float)inv_ls[t];
   if (threadIdx.x < M) s_c[threadIdx.x] = scalbnf((float)constant[threadIdx.x], k_exp[threadIdx.x]);
-  float xt[KT_DMAX];
+  float xa[DMAX], xb[DMAX];
 #pragma unroll
-  for (int j = 0; j < KT_DMAX; ++j) xt[j] = (j < d && n < N) ? (float)Xt[n * d + j] : 0.f;
+  for (int j = 0; j < DMAX; ++j) {
+    xa[j] = (j < d && n0 < N) ? (float)Xt[n0 * d + j] : 0.f;
+    xb[j] = (j < d && n0 + 1 < N) ? (float)Xt[(n0 + 1) * d + j] : 0.f;
+  }
   __syncthreads();
-  if (n >= ldk) return;
-  const bool live = n < N;
+  if (n0 >= ldk) return;
+  const bool live_a = n0 < N, live_b = n0 + 1 < N;
+  uint32_t* Kh32 = reinterpret_cast<uint32_t*>(Kh);
+  uint32_t* Kl32 = reinterpret_cast<uint32_t*>(Kl);
   for (int q = 0; q < KT_TP; ++q) {
     const int64_t pl = pt0 + q;
     if (pl >= Pcpad) break;
     const float* xc = sxf + q * d;
-    float s_iso = 0.f;
+    float sa = 0.f, sb = 0.f;
     if (ISO) {
 #pragma unroll
-      for (int j = 0; j < KT_DMAX; ++j)
+      for (int j = 0; j < DMAX; ++j)
         if (j < d) {
-          const float df = xc[j] - xt[j];
-          s_iso = fmaf(df, df, s_iso);
+          const float c = xc[j];
+          const float da = c - xa[j], db = c - xb[j];
+          sa = fmaf(da, da, sa);
+          sb = fmaf(db, db, sb);
         }
     }
     for (int m = 0; m < M; ++m) {
-      float s2;
+      float ra, rb;
       if (ISO) {
         const float il = s_il[m * d];
-        s2 = s_iso * il * il;
+        ra = sa * il * il;
+        rb = sb * il * il;
       } else {
-        s2 = 0.f;
+        ra = rb = 0.f;
 #pragma unroll
-        for (int j = 0; j < KT_DMAX; ++j)
+        for (int j = 0; j < DMAX; ++j)
           if (j < d) {
-            const float df = (xc[j] - xt[j]) * s_il[m * d + j];
-            s2 = fmaf(df, df, s2);
+            const float c = xc[j], il = s_il[m * d + j];
+            const float da = (c - xa[j]) * il, db = (c - xb[j]) * il;
+            ra = fmaf(da, da, ra);
+            rb = fmaf(db, db, rb);
           }
       }
-      const float ks = live ? s_c[m] * stationary_f(s2, kind) : 0.f;  // c * k(r), scaled by 2^kexp (exact)
-      const __half h = __float2half_rn(ks);
-      const __half l = __float2half_rn(ks - __half2float(h));
-      Kh[m * plane + pl * ldk + n] = __half_as_ushort(h);
-      Kl[m * plane + pl * ldk + n] = __half_as_ushort(l);
+      const float ka = live_a ? s_c[m] * stationary_f(ra, kind) : 0.f;  // c * k(r), scaled by 2^kexp (exact)
+      const float kb = live_b ? s_c[m] * stationary_f(rb, kind) : 0.f;
+      const __half2 h = __floats2half2_rn(ka, kb);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(ka - hf.x, kb - hf.y);
+      const int64_t o = (m * plane + pl * ldk + n0) >> 1;
+      Kh32[o] = *reinterpret_cast<const uint32_t*>(&h);
+      Kl32[o] = *reinterpret_cast<const uint32_t*>(&l);
     }
   }
 }
@@ -499,7 +514,6 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   Pc_max = (Pc_max / TM) * TM;
   if (Pc_max < TM) Pc_max = TM;
   const int64_t Pc_alloc = P < Pc_max ? ceil_div(P, TM) * TM : Pc_max;
-  const int nblk = (int)(Npad / KT_TN);
   DevBuf<uint16_t> Kh, Kl;
   DevBuf<double> vnorm;
   DevBuf<int> abort_flag;
@@ -520,14 +534,23 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
     const int64_t Pcpad = ceil_div(Pc, TM) * TM;
     {
       ProfileScope ps(ctx, "gp_kstar");
-      dim3 gk((unsigned)nblk, (unsigned)ceil_div(Pcpad, KT_TP));
+      dim3 gk((unsigned)(Npad / (2 * KT_TN)), (unsigned)ceil_div(Pcpad, KT_TP));
       size_t smem = (size_t)(KT_TP * d + 4 * d + 4) * sizeof(float);
-      if (gp->isotropic)
-        DMO_LAUNCH(kstar_tensor_kernel<true>, gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel,
-                   gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p);
-      else
-        DMO_LAUNCH(kstar_tensor_kernel<false>, gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel,
-                   gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p);
+#define KSTAR_LAUNCH(ISO_, DM_)                                                                                      \
+  DMO_LAUNCH((kstar_tensor_kernel<ISO_, DM_>), gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel, \
+             gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p)
+      if (gp->isotropic) {
+        if (d <= 32)
+          KSTAR_LAUNCH(true, 32);
+        else
+          KSTAR_LAUNCH(true, 64);
+      } else {
+        if (d <= 32)
+          KSTAR_LAUNCH(false, 32);
+        else
+          KSTAR_LAUNCH(false, 64);
+      }
+#undef KSTAR_LAUNCH
     }
     {
       ProfileScope ps(ctx, "gp_mean");

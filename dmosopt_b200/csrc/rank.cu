@@ -94,16 +94,35 @@ __global__ void build_records_kernel(const uint32_t* __restrict__ R, const uint3
   }
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c == 0 ? a.x : c == 1 ? a.y : c == 2 ? a.z : a.w; }
+
+// The rank word of a record (rank + 1, 0 = not yet final) is its own ready flag: a 4-byte store is atomic and carries
+// no other data, so publication needs neither fences nor a separate flag, and consumers simply poll the word.
 template <int M, int T>
-__global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* done,
-                                                       int* ticket, int* errflag) {
+__global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
+                                                       int* errflag) {
   constexpr int W = 4 * ((M + 1 + 3) / 4);
   constexpr int NV = W / 4;
   constexpr int NW = T / 32;
+  constexpr int RQ = M / 4, RC = M % 4;  // uint4 / component holding the rank word
   __shared__ uint4 tile[T * NV];
   __shared__ __align__(16) int sh_r1[T];
-  __shared__ uint32_t sh_final[2 * NW];
-  __shared__ uint32_t sh_new[2 * NW];
   __shared__ int sh_blk;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -150,29 +169,25 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
     }
     __syncthreads();
 
-    // ---- stream every earlier block: best = max over dominators of (rank + 1)
+    // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
     int best = 0;
-    auto wait_done = [&](int k) {
-      if (tid == 0) {
+    for (int k = 0; k < b - 1; ++k) {
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
+        uint4 a[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) a[q] = ld_relaxed_v4(src + q);
         unsigned spins = 0;
-        while (ld_acquire_gpu(done + k) == 0) {
+        while (word_of(a[RQ], RC) == 0u) {  // not final yet (only ever true close to the diagonal)
           __nanosleep(20);
-          if ((++spins & 0xFFFu) == 0u) {
-            if (spins > (1u << 22) || ld_acquire_gpu(errflag) != 0) {
-              atomicExch(errflag, 1);
-              break;
-            }
+          a[RQ] = ld_relaxed_v4(src + RQ);
+          if ((++spins & 0xFFFu) == 0u && (spins > (1u << 22) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
+            atomicExch(errflag, 1);
+            break;
           }
         }
-      }
-      __syncthreads();
-    };
-    for (int k = 0; k < b - 1; ++k) {
-      wait_done(k);
-      {
-        const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)k * T * W);
 #pragma unroll
-        for (int q = 0; q < NV; ++q) tile[tid * NV + q] = __ldcg(src + tid * NV + q);
+        for (int q = 0; q < NV; ++q) tile[tid * NV + q] = a[q];
       }
       __syncthreads();
 #pragma unroll 16
@@ -194,8 +209,8 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
       }
       __syncthreads();
     }
-    // The predecessor block is the critical dependency: its dominance pattern does not depend on its ranks, so it is
-    // evaluated into a bitmask BEFORE waiting for its "done" flag; once the flag is up only the set bits are visited.
+    // ---- the predecessor block is the critical dependency: its dominance pattern does not depend on its ranks, so it
+    // is evaluated into a bitmask BEFORE its ranks are awaited; afterwards only a predicated max over 128 ranks remains
     if (b > 0) {
       const int k = b - 1;
       {
@@ -218,10 +233,20 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
         }
         pmask[w] = mm;
       }
-      wait_done(k);
-      sh_r1[tid] = (int)__ldcg(rec + ((int64_t)k * T + tid) * W + M);  // rank + 1 of the predecessor block
+      {
+        const uint32_t* rw = rec + ((int64_t)k * T + tid) * W + M;
+        uint32_t r1 = ld_relaxed_u32(rw);
+        unsigned spins = 0;
+        while (r1 == 0u) {
+          r1 = ld_relaxed_u32(rw);
+          if ((++spins & 0xFFFFu) == 0u && (spins > (1u << 24) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
+            atomicExch(errflag, 1);
+            break;
+          }
+        }
+        sh_r1[tid] = (int)r1;
+      }
       __syncthreads();
-      // independent broadcast loads + predicated max: no load-latency chain on the critical path
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
         const uint32_t mm = pmask[w];
@@ -237,52 +262,48 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
       __syncthreads();
     }
 
-    // ---- resolve the in-block chain.  Round t: every thread folds in the dominators that became final in round
-    // t-1 (a handful of bits), and becomes final itself once all its in-block dominators are.  Double-buffered
-    // bit words -> one barrier per round.
-    bool fin = false;
+    // ---- in-block chain, warp by warp.  Warp w first folds in the (now final) ranks of warps < w, then resolves its own
+    // 32 points with ballots and shuffles only (a lane is final once all its in-warp dominators are), publishes its
+    // ranks at once -- so the successor block can start consuming them while warps w+1.. are still working.
     int r = best;
-    if (tid < 2 * NW) {
-      sh_final[tid] = 0u;  // [2][NW]
-      sh_new[tid] = 0u;
-    }
-    __syncthreads();
-    for (int round = 0; round <= T; ++round) {
-      const int cur = round & 1, nxt = cur ^ 1;
-      bool ready = !fin;
-      uint32_t fw = 0u;
+    for (int w = 0; w < NW; ++w) {
+      if (warp == w) {
 #pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const uint32_t f = sh_final[cur * NW + w];
-        uint32_t mm = mask[w] & sh_new[cur * NW + w];
-        while (mm) {
-          const int s = __ffs(mm) - 1;
-          mm &= mm - 1;
-          r = max(r, sh_r1[w * 32 + s]);
+        for (int ww = 0; ww < NW; ++ww)
+          if (ww < w) {
+            const uint32_t mm = mask[ww];
+#pragma unroll
+            for (int s4 = 0; s4 < 8; ++s4) {
+              const int4 rr = *reinterpret_cast<const int4*>(&sh_r1[ww * 32 + s4 * 4]);
+              r = ((mm >> (s4 * 4 + 0)) & 1u) ? max(r, rr.x) : r;
+              r = ((mm >> (s4 * 4 + 1)) & 1u) ? max(r, rr.y) : r;
+              r = ((mm >> (s4 * 4 + 2)) & 1u) ? max(r, rr.z) : r;
+              r = ((mm >> (s4 * 4 + 3)) & 1u) ? max(r, rr.w) : r;
+            }
+          }
+        uint32_t mw = 0u;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww)
+          if (ww == w) mw = mask[ww];
+        uint32_t finalm = 0u;
+        bool fin = false;
+        for (int round = 0; round < 33 && finalm != 0xFFFFFFFFu; ++round) {
+          const bool ready = !fin && ((mw & ~finalm) == 0u);
+          unsigned newly = __ballot_sync(0xffffffffu, ready);
+          if (ready) fin = true;
+          finalm |= newly;
+          while (newly) {
+            const int s = __ffs(newly) - 1;
+            newly &= newly - 1;
+            const int rs = __shfl_sync(0xffffffffu, r, s) + 1;
+            if ((mw >> s) & 1u) r = max(r, rs);
+          }
         }
-        ready = ready && ((mask[w] & ~f) == 0u);
-        if (w == warp) fw = f;
-      }
-      if (ready) {
         sh_r1[tid] = r + 1;
-        fin = true;
+        st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: rank word doubles as the ready flag
+        rankS[i] = r;
       }
-      const unsigned newly = __ballot_sync(0xffffffffu, ready);
-      if (lane == 0) {
-        sh_new[nxt * NW + warp] = newly;
-        sh_final[nxt * NW + warp] = fw | newly;
-      }
-      if (__syncthreads_and(fin ? 1 : 0)) break;
-    }
-    const int myrank = r;
-
-    // ---- publish
-    rec[i * W + M] = (uint32_t)(myrank + 1);
-    rankS[i] = myrank;
-    __syncthreads();  // all ranks of the block are written (bar.sync orders them before thread 0's release)
-    if (tid == 0) {
-      __threadfence();
-      st_release_gpu(done + b, 1);
+      __syncthreads();
     }
   }
 }
@@ -299,7 +320,7 @@ __global__ void copy_u32_to_i32_kernel(const uint32_t* __restrict__ a, int64_t n
 }
 
 template <int M>
-int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* done, int* ticket, int* errflag) {
+int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* ticket, int* errflag) {
   int occ = 0;
   DMO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_chain_kernel<M, RANK_T>, RANK_T, 0));
   if (occ < 1) occ = 1;
@@ -310,7 +331,7 @@ int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* done
   if (cap >= 1 && occ > cap) occ = cap;
   int grid = nblocks < occ * ctx->sm_count ? nblocks : occ * ctx->sm_count;
   ProfileScope ps(ctx, "rank_chain");
-  DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), grid, RANK_T, 0, rec, nblocks, rankS, done, ticket, errflag);
+  DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), grid, RANK_T, 0, rec, nblocks, rankS, ticket, errflag);
   DMO_CHECK_LAUNCH();
   return DMO_OK;
 }
@@ -390,17 +411,16 @@ int rank_nd_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_
   DMO_TRY(sync.alloc(ctx, nblocks + 2));
   DMO_CUDA(cudaMemsetAsync(sync.p, 0, (nblocks + 2) * sizeof(int), ctx->stream));
   DMO_LAUNCH(build_records_kernel, (unsigned)ceil_div(npad, 256), 256, 0, R.p, perm, gid.p, n, npad, M, W, rec.p);
-  int* done = sync.p;
   int* ticket = sync.p + nblocks;
   int* errflag = sync.p + nblocks + 1;
   switch (M) {
-    case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
-    case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
-    case 4: DMO_TRY(launch_chain<4>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
-    case 5: DMO_TRY(launch_chain<5>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
-    case 6: DMO_TRY(launch_chain<6>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
-    case 7: DMO_TRY(launch_chain<7>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
-    default: DMO_TRY(launch_chain<8>(ctx, rec.p, (int)nblocks, rankS.p, done, ticket, errflag)); break;
+    case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 4: DMO_TRY(launch_chain<4>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 5: DMO_TRY(launch_chain<5>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 6: DMO_TRY(launch_chain<6>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 7: DMO_TRY(launch_chain<7>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    default: DMO_TRY(launch_chain<8>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
   }
   DMO_LAUNCH(scatter_rank_kernel, g, 256, 0, rankS.p, perm, n, d_rank);
   DMO_CHECK_LAUNCH();

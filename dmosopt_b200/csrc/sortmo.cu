@@ -452,6 +452,55 @@ int dmo_remove_worst(dmo_ctx* ctx, const double* X, const double* Y, int64_t n, 
   return DMO_OK;
 }
 
+// dmo_remove_worst on the row-wise concatenation [A; B] without materialising it on the host: the two blocks are
+// staged into adjacent regions of one device buffer (NSGA2.update_strategy stacks children over parents, NSGA2.py:205-206)
+int dmo_remove_worst_pair(dmo_ctx* ctx, const double* Xa, const double* Ya, int64_t na, const double* Xb, const double* Yb,
+                          int64_t nb, int d, int M, int metric, int64_t keep, double* X_out, double* Y_out,
+                          int32_t* rank_out, int64_t* perm_out) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = na + nb;
+  if (n == 0) return DMO_OK;
+  DMO_REQUIRE(na >= 0 && nb >= 0 && d >= 1 && M >= 1 && (na == 0 || (Xa && Ya)) && (nb == 0 || (Xb && Yb)),
+              "remove_worst_pair: bad arguments");
+  if (keep > n) keep = n;
+  DevBuf<double> x, y;
+  DMO_TRY(x.alloc(ctx, (size_t)n * d));
+  DMO_TRY(y.alloc(ctx, (size_t)n * M));
+  auto stage = [&](double* dst, const double* src, size_t count) -> int {
+    if (count == 0) return DMO_OK;
+    DMO_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    if (!dmo_is_device_ptr(src)) ctx->h2d_bytes += count * sizeof(double);
+    return DMO_OK;
+  };
+  DMO_TRY(stage(x.p, Xa, (size_t)na * d));
+  DMO_TRY(stage(x.p + (size_t)na * d, Xb, (size_t)nb * d));
+  DMO_TRY(stage(y.p, Ya, (size_t)na * M));
+  DMO_TRY(stage(y.p + (size_t)na * M, Yb, (size_t)nb * M));
+  DevBuf<int32_t> rank;
+  DevBuf<double> dist;
+  DevBuf<uint32_t> p;
+  DMO_TRY(order_mo_device(ctx, y.p, n, M, metric, nullptr, 0, rank, dist, p));
+  Out<double> ox, oy;
+  Out<int32_t> orank;
+  Out<int64_t> op;
+  DMO_TRY(ox.init(ctx, X_out, (size_t)keep * d));
+  DMO_TRY(oy.init(ctx, Y_out, (size_t)keep * M));
+  DMO_TRY(orank.init(ctx, rank_out, (size_t)keep));
+  DMO_TRY(op.init(ctx, perm_out, (size_t)keep));
+  if (ox.d) DMO_LAUNCH(gather_rows_kernel, (unsigned)ceil_div(keep * d, 256), 256, 0, x.p, p.p, keep, d, ox.d);
+  if (oy.d) DMO_LAUNCH(gather_rows_kernel, (unsigned)ceil_div(keep * M, 256), 256, 0, y.p, p.p, keep, M, oy.d);
+  DMO_LAUNCH(gather_sorted_kernel, (unsigned)ceil_div(keep, 256), 256, 0, rank.p, (const double*)nullptr, p.p, keep,
+             op.d, orank.d, (double*)nullptr);
+  DMO_CHECK_LAUNCH();
+  DMO_TRY(ox.finish(ctx));
+  DMO_TRY(oy.finish(ctx));
+  DMO_TRY(orank.finish(ctx));
+  DMO_TRY(op.finish(ctx));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
+
 int dmo_get_duplicates(dmo_ctx* ctx, const double* X, int64_t n, int d, double eps, uint8_t* is_dup) {
   if (!ctx) return DMO_ERR_ARG;
   DMO_CUDA(cudaSetDevice(ctx->device));

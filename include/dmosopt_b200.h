@@ -113,6 +113,12 @@ int dmo_remove_worst(dmo_ctx* ctx, const double* X, const double* Y, int64_t n, 
                      int metric, const double* const* extra_desc_keys, int n_extra, int64_t keep,
                      double* X_out, double* Y_out, int32_t* rank_out, int64_t* perm_out);
 
+/* dmo_remove_worst on the row-wise concatenation [A (na rows); B (nb rows)] without building it on the host
+ * (NSGA2.update_strategy stacks the children over the parents, dmosopt/NSGA2.py:205-214). Outputs may alias B. */
+int dmo_remove_worst_pair(dmo_ctx* ctx, const double* Xa, const double* Ya, int64_t na, const double* Xb,
+                          const double* Yb, int64_t nb, int d, int M, int metric, int64_t keep,
+                          double* X_out, double* Y_out, int32_t* rank_out, int64_t* perm_out);
+
 /* ---- A6: tournament selection ---------------------------------------------
  * replaces MOEA.tournament_selection (dmosopt/MOEA.py:375-395): candidates ordered by
  * lexsort(metrics) (rank primary; AGE-MOEA adds -crowd_dist as secondary,

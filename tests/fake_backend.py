@@ -52,6 +52,14 @@ def remove_worst(X, Y, keep, metric=METRIC_NONE, extra_desc_keys=None):
     return X[perm], Y[perm], rank[perm], perm.astype(np.int64)
 
 
+def remove_worst_pair(Xa, Ya, Xb, Yb, keep, metric=METRIC_NONE, out_X=None):
+    Xo, Yo, rank, perm = remove_worst(np.vstack((Xa, Xb)), np.vstack((Ya, Yb)), keep, metric)
+    if out_X is not None and out_X.dtype == np.float64 and out_X.shape == Xo.shape:
+        out_X[:] = Xo
+        Xo = out_X
+    return Xo, Yo, rank, perm
+
+
 def _rng(seed, stream_id):
     return np.random.default_rng([int(seed) & (2**63 - 1), int(stream_id)])
 
@@ -189,7 +197,7 @@ def cmaes_update_cholesky(A, Ainv, pc, z, psucc, cc, ccov, pthresh):
     return A, Ainv, pc
 
 
-FUNCTIONS = ["rank_nd", "crowding_distance", "euclidean_distance", "order_mo", "remove_worst", "tournament", "mutation_u", "sbx_u",
+FUNCTIONS = ["rank_nd", "crowding_distance", "euclidean_distance", "order_mo", "remove_worst", "remove_worst_pair", "tournament", "mutation_u", "sbx_u",
              "nsga2_generate", "GPHandle", "hypervolume", "ehvi_select", "get_duplicates", "age_survival", "smpso_velocity", "mutate_groups",
              "cmaes_sample", "cmaes_update_cholesky"]
 
