@@ -167,6 +167,129 @@ __global__ void gather_u32_kernel2(const uint32_t* __restrict__ src, const uint3
   if (p < n) out[p] = src[sidx[p]];
 }
 
+// ---- M = 4, 5: the slicing identity applied recursively ----------------------------------------------------------
+//   HV_d(S) = sum_k (r_d - p_k[d]) * [ vol_{d-1}(box of k) - HV_{d-1}( S_k clipped to the box of k ) ],  S_k = points before k
+//   along axis d.  Unrolled to the 3-D base case this is an alternating sum over chains k1 > k2 (> k3):
+//     HV_4 = sum_k1 h1 vol3(k1)                      - sum_{k1>k2} h1 h2 E2(k1,k2)
+//     HV_5 = sum_k1 h1 vol4(k1) - sum_{k1>k2} h1 h2 vol3(k1,k2) + sum_{k1>k2>k3} h1 h2 h3 E2(k1,k2,k3)
+//   with h_i = r - (clipped coordinate along the i-th slicing axis) and E2 the exclusive xy-area of the innermost point
+//   inside the common box, against the points that precede it along every slicing axis (same sweep as hv3_kernel).
+//   Clipping (component-wise max with the outer points) is monotone, so the original per-axis orders stay valid.
+struct HvArrays {
+  const double* x;  // coordinates in x-sorted order: x = obj0, y = obj1, s[0] = obj2 (innermost slicing axis), s[1], s[2]
+  const double* y;
+  const double* s[3];
+  const uint32_t* o[3];  // total-order ids along the slicing axes
+  double rx, ry, rs[3];
+};
+
+// D = 2 (M = 4): block = (k1, tile of k2).  D = 3 (M = 5): block = (k1, tile of k3), k2 looped inside the block.
+template <int D>
+__global__ void __launch_bounds__(HV_T) hv_slice_kernel(HvArrays A, int64_t n, double* __restrict__ partial) {
+  __shared__ double sx[HV_T], sy[HV_T];
+  __shared__ uint32_t so[3][HV_T];
+  const int64_t k1 = blockIdx.x;
+  const int64_t t = (int64_t)blockIdx.y * HV_T + threadIdx.x;  // innermost chain index
+  const bool live = t < n;
+  constexpr int TOP = D - 1;  // slicing axis of k1 (outermost)
+  const double x1 = A.x[k1], y1 = A.y[k1];
+  const uint32_t o1 = A.o[TOP][k1];
+  const double h1 = A.rs[TOP] - A.s[TOP][k1];
+  double c1[3];
+  for (int a = 0; a < TOP; ++a) c1[a] = A.s[a][k1];
+  const double xt = live ? A.x[t] : 0.0, yt = live ? A.y[t] : 0.0;
+  double st[3];
+  uint32_t ot[3];
+  for (int a = 0; a < D; ++a) {
+    st[a] = live ? A.s[a][t] : 0.0;
+    ot[a] = live ? A.o[a][t] : 0u;
+  }
+  double total = 0.0;
+  const int64_t n2 = (D == 3) ? n : 1;
+  for (int64_t k2 = 0; k2 < n2; ++k2) {
+    double X = fmax(xt, x1), Y = fmax(yt, y1), hprod = h1;
+    double clipz = fmax(st[0], c1[0]);  // innermost slicing coordinate of t, clipped
+    uint32_t lim_w = 0xFFFFFFFFu;       // D == 3: order limit along axis 1 given by k2
+    bool valid = live && ot[TOP] < o1;
+    if (D == 3) {
+      const uint32_t o2v = A.o[2][k2];
+      if (!(o2v < o1)) continue;  // k2 must precede k1 along the outermost axis (uniform over the block)
+      const double x2 = A.x[k2], y2 = A.y[k2];
+      lim_w = A.o[1][k2];
+      valid = valid && ot[1] < lim_w;
+      X = fmax(X, x2);
+      Y = fmax(Y, y2);
+      clipz = fmax(clipz, A.s[0][k2]);
+      hprod *= A.rs[1] - fmax(A.s[1][k2], c1[1]);
+    }
+    double covered = 0.0, m = INFINITY, xcur = X;
+    for (int64_t t0 = 0; t0 < n; t0 += HV_T) {
+      const int64_t j = t0 + threadIdx.x;
+      __syncthreads();
+      sx[threadIdx.x] = j < n ? A.x[j] : INFINITY;
+      sy[threadIdx.x] = j < n ? A.y[j] : INFINITY;
+      for (int a = 0; a < D; ++a) so[a][threadIdx.x] = j < n ? A.o[a][j] : 0xFFFFFFFFu;
+      __syncthreads();
+      if (!valid) continue;
+      const int cnt = (int)((n - t0) < HV_T ? (n - t0) : HV_T);
+#pragma unroll 4
+      for (int s = 0; s < cnt; ++s) {
+        bool in = so[TOP][s] < o1 && so[0][s] < ot[0];
+        if (D == 3) in = in && so[1][s] < lim_w;
+        const double yj = sy[s];
+        if (in && yj < m) {
+          const double xj = fmax(sx[s], X);
+          covered += (xj - xcur) * fmax(A.ry - fmax(m, Y), 0.0);
+          xcur = xj;
+          m = yj;
+        }
+      }
+    }
+    if (valid) {
+      covered += (A.rx - xcur) * fmax(A.ry - fmax(m, Y), 0.0);
+      const double excl = (A.rx - X) * (A.ry - Y) - covered;
+      total += hprod * (A.rs[0] - clipz) * excl;
+    }
+  }
+  // deterministic block partial
+  __shared__ double ws[HV_T / 32];
+  double v = warp_sum(total);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int w = 0; w < HV_T / 32; ++w) acc += ws[w];
+    partial[(int64_t)blockIdx.x * gridDim.y + blockIdx.y] = acc;
+  }
+}
+
+// lower-order terms: sum_k1 h1 vol(k1)  [and for M = 5: sum_{k1>k2} h1 h2 vol3(k1,k2)]
+template <int D>
+__global__ void hv_volume_terms_kernel(HvArrays A, int64_t n, double* __restrict__ partial_a, double* __restrict__ partial_b) {
+  const int64_t k1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int TOP = D - 1;
+  double ta = 0.0, tb = 0.0;
+  if (k1 < n) {
+    const double h1 = A.rs[TOP] - A.s[TOP][k1];
+    double vol = (A.rx - A.x[k1]) * (A.ry - A.y[k1]);
+    for (int a = 0; a < TOP; ++a) vol *= A.rs[a] - A.s[a][k1];
+    ta = h1 * vol;
+    if (D == 3) {
+      const uint32_t o1 = A.o[2][k1];
+      for (int64_t k2 = 0; k2 < n; ++k2) {
+        if (!(A.o[2][k2] < o1)) continue;
+        const double h2 = A.rs[1] - fmax(A.s[1][k2], A.s[1][k1]);
+        const double v3 = (A.rx - fmax(A.x[k2], A.x[k1])) * (A.ry - fmax(A.y[k2], A.y[k1])) *
+                          (A.rs[0] - fmax(A.s[0][k2], A.s[0][k1]));
+        tb += h1 * h2 * v3;
+      }
+    }
+  }
+  block_sum_store(ta, partial_a);
+  __syncthreads();
+  if (D == 3) block_sum_store(tb, partial_b);
+}
+
 // ---- EHVI -----------------------------------------------------------------------------------------------
 constexpr int EH_MAXM = 8;
 
@@ -305,7 +428,7 @@ int sum_partials(dmo_ctx* ctx, DevBuf<double>& partial, int64_t nb, double* h_ou
 int hypervolume_device(dmo_ctx* ctx, const double* dF, int64_t n, int M, const double* h_ref, double* h_out) {
   *h_out = 0.0;
   if (n <= 0) return DMO_OK;
-  DMO_REQUIRE(M >= 1 && M <= 3, "hypervolume: M=%d not supported by this build (1..3)", M);
+  DMO_REQUIRE(M >= 1 && M <= 5, "hypervolume: M=%d not supported (1..5; >= 10 objectives use Monte-Carlo in the reference)", M);
   DevBuf<double> dref;
   DMO_TRY(dref.alloc(ctx, M));
   DMO_CUDA(cudaMemcpyAsync(dref.p, h_ref, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -341,6 +464,63 @@ int hypervolume_device(dmo_ctx* ctx, const double* dF, int64_t n, int M, const d
     DMO_TRY(partial.alloc(ctx, nb));
     DMO_LAUNCH(hv2_kernel, (unsigned)nb, 256, 0, Fnd.p, sx.p, n2, h_ref[0], h_ref[1], partial.p);
     DMO_TRY(sum_partials(ctx, partial, nb, h_out));
+    return DMO_OK;
+  }
+  if (M >= 4) {
+    // x-sorted coordinate arrays and per-axis order ids for the slicing axes obj2 .. obj(M-1)
+    const int D = M - 2;
+    const unsigned g4 = (unsigned)ceil_div(n2, 256);
+    DevBuf<double> xs4, ys4, sc[3];
+    DevBuf<uint32_t> so_[3], sidx_a, inv_a;
+    DMO_TRY(xs4.alloc(ctx, n2));
+    DMO_TRY(ys4.alloc(ctx, n2));
+    DMO_TRY(inv_a.alloc(ctx, n2));
+    DMO_LAUNCH(gather_col_kernel, g4, 256, 0, Fnd.p, sx.p, n2, M, 0, xs4.p);
+    DMO_LAUNCH(gather_col_kernel, g4, 256, 0, Fnd.p, sx.p, n2, M, 1, ys4.p);
+    HvArrays A;
+    A.x = xs4.p;
+    A.y = ys4.p;
+    A.rx = h_ref[0];
+    A.ry = h_ref[1];
+    for (int a = 0; a < 3; ++a) {
+      A.s[a] = nullptr;
+      A.o[a] = nullptr;
+      A.rs[a] = 0.0;
+    }
+    for (int a = 0; a < D; ++a) {
+      DMO_TRY(sc[a].alloc(ctx, n2));
+      DMO_TRY(so_[a].alloc(ctx, n2));
+      DMO_TRY(sort_by_column(ctx, Fnd.p, n2, M, 2 + a, sidx_a));
+      DMO_LAUNCH(invert_perm_kernel, g4, 256, 0, sidx_a.p, n2, inv_a.p);
+      DMO_LAUNCH(gather_u32_kernel2, g4, 256, 0, inv_a.p, sx.p, n2, so_[a].p);
+      DMO_LAUNCH(gather_col_kernel, g4, 256, 0, Fnd.p, sx.p, n2, M, 2 + a, sc[a].p);
+      A.s[a] = sc[a].p;
+      A.o[a] = so_[a].p;
+      A.rs[a] = h_ref[2 + a];
+    }
+    const int64_t tiles = ceil_div(n2, HV_T);
+    const int64_t nbv = ceil_div(n2, 256);
+    DevBuf<double> part_main, part_a, part_b;
+    DMO_TRY(part_main.alloc(ctx, (size_t)n2 * tiles));
+    DMO_TRY(part_a.alloc(ctx, nbv));
+    DMO_TRY(part_b.alloc(ctx, nbv));
+    DMO_REQUIRE(tiles <= 65535, "hypervolume: front too large for M=%d (%lld non-dominated points)", M, (long long)n2);
+    dim3 grid((unsigned)n2, (unsigned)tiles);
+    double t_main = 0.0, t_a = 0.0, t_b = 0.0;
+    {
+      ProfileScope ps(ctx, M == 4 ? "hv4" : "hv5");
+      if (M == 4) {
+        DMO_LAUNCH(hv_slice_kernel<2>, grid, HV_T, 0, A, n2, part_main.p);
+        DMO_LAUNCH(hv_volume_terms_kernel<2>, (unsigned)nbv, 256, 0, A, n2, part_a.p, part_b.p);
+      } else {
+        DMO_LAUNCH(hv_slice_kernel<3>, grid, HV_T, 0, A, n2, part_main.p);
+        DMO_LAUNCH(hv_volume_terms_kernel<3>, (unsigned)nbv, 256, 0, A, n2, part_a.p, part_b.p);
+      }
+    }
+    DMO_TRY(sum_partials(ctx, part_main, n2 * tiles, &t_main));
+    DMO_TRY(sum_partials(ctx, part_a, nbv, &t_a));
+    if (M == 5) DMO_TRY(sum_partials(ctx, part_b, nbv, &t_b));
+    *h_out = (M == 4) ? (t_a - t_main) : (t_a - t_b + t_main);
     return DMO_OK;
   }
   // M == 3

@@ -10,9 +10,10 @@
 //      be dominated by points before it, and identical vectors are adjacent (one "group id" each);
 //   3. one persistent kernel evaluates the chain recurrence block by block in that order:
 //      a block of T targets streams every earlier block through shared memory (coalesced 16-byte
-//      records, broadcast reads, one dominance predicate per pair), waits on a per-block "done" flag
-//      only when it catches up with its predecessor, resolves the in-block dependencies with
-//      per-thread dominator bitmasks + warp ballots (Kahn rounds), and publishes its ranks.
+//      records, broadcast reads, one dominance predicate per pair); the rank word of a record (rank + 1,
+//      0 = not final) is its own ready flag, so a consumer polls only when it catches up with its
+//      predecessor; in-block dependencies are resolved warp by warp with per-thread dominator bitmasks,
+//      ballots and shared-memory folds, and each warp publishes its ranks as soon as they are final.
 //      Blocks are handed out by an atomic ticket, so a block only ever waits for blocks whose CTAs are
 //      already running (no co-residency assumption, no deadlock).
 //
@@ -115,7 +116,7 @@ __device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c ==
 // The rank word of a record (rank + 1, 0 = not yet final) is its own ready flag: a 4-byte store is atomic and carries
 // no other data, so publication needs neither fences nor a separate flag, and consumers simply poll the word.
 template <int M, int T>
-__global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
+__global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
                                                        int* errflag) {
   constexpr int W = 4 * ((M + 1 + 3) / 4);
   constexpr int NV = W / 4;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       uint32_t m = 0u;
-#pragma unroll
+#pragma unroll 8
       for (int s = 0; s < 32; ++s) {
         const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s) * NV]);
         bool dom = (w * 32 + s < tid) && (sp[M - 1] != gidv);
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
         for (int q = 0; q < NV; ++q) tile[tid * NV + q] = a[q];
       }
       __syncthreads();
-#pragma unroll 16
+#pragma unroll 8
       for (int s = 0; s < T; ++s) {
         uint32_t sw[W];
 #pragma unroll
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
         uint32_t mm = 0u;
-#pragma unroll
+#pragma unroll 8
         for (int s = 0; s < 32; ++s) {
           const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s) * NV]);
           bool dom = (sp[M - 1] != gidv);
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
         const uint32_t mm = pmask[w];
-#pragma unroll
+#pragma unroll 2
         for (int s4 = 0; s4 < 8; ++s4) {
           const int4 rr = *reinterpret_cast<const int4*>(&sh_r1[w * 32 + s4 * 4]);
           best = ((mm >> (s4 * 4 + 0)) & 1u) ? max(best, rr.x) : best;
@@ -262,17 +263,21 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
       __syncthreads();
     }
 
-    // ---- in-block chain, warp by warp.  Warp w first folds in the (now final) ranks of warps < w, then resolves its own
-    // 32 points with ballots and shuffles only (a lane is final once all its in-warp dominators are), publishes its
-    // ranks at once -- so the successor block can start consuming them while warps w+1.. are still working.
+    // ---- in-block chain, warp by warp (dependencies only run from lower to higher index, so a chain crosses at most
+    // T/32 warps).  Warp w first folds in the now final ranks of warps < w, then resolves its own 32 points in
+    // mini-rounds that need only a ballot and a __syncwarp: a lane is final once all its in-warp dominators are, newly
+    // final lanes post rank + 1 to shared memory and the others fold in just those bits.  Each warp publishes its ranks
+    // at once, so the successor block can start consuming them while warps w+1.. are still working.
     int r = best;
     for (int w = 0; w < NW; ++w) {
       if (warp == w) {
+        uint32_t mw = 0u;
 #pragma unroll
-        for (int ww = 0; ww < NW; ++ww)
+        for (int ww = 0; ww < NW; ++ww) {
+          if (ww == w) mw = mask[ww];
           if (ww < w) {
             const uint32_t mm = mask[ww];
-#pragma unroll
+#pragma unroll 2
             for (int s4 = 0; s4 < 8; ++s4) {
               const int4 rr = *reinterpret_cast<const int4*>(&sh_r1[ww * 32 + s4 * 4]);
               r = ((mm >> (s4 * 4 + 0)) & 1u) ? max(r, rr.x) : r;
@@ -281,26 +286,27 @@ __global__ void __launch_bounds__(T) rank_chain_kernel(uint32_t* rec, int nblock
               r = ((mm >> (s4 * 4 + 3)) & 1u) ? max(r, rr.w) : r;
             }
           }
-        uint32_t mw = 0u;
-#pragma unroll
-        for (int ww = 0; ww < NW; ++ww)
-          if (ww == w) mw = mask[ww];
+        }
         uint32_t finalm = 0u;
         bool fin = false;
-        for (int round = 0; round < 33 && finalm != 0xFFFFFFFFu; ++round) {
+        for (int round = 0; round < 33; ++round) {
           const bool ready = !fin && ((mw & ~finalm) == 0u);
-          unsigned newly = __ballot_sync(0xffffffffu, ready);
-          if (ready) fin = true;
+          const unsigned newly = __ballot_sync(0xffffffffu, ready);
+          if (ready) {
+            sh_r1[tid] = r + 1;
+            fin = true;
+          }
           finalm |= newly;
-          while (newly) {
-            const int s = __ffs(newly) - 1;
-            newly &= newly - 1;
-            const int rs = __shfl_sync(0xffffffffu, r, s) + 1;
-            if ((mw >> s) & 1u) r = max(r, rs);
+          __syncwarp();
+          if (finalm == 0xFFFFFFFFu) break;
+          uint32_t mm = mw & newly;
+          while (mm) {
+            const int s = __ffs(mm) - 1;
+            mm &= mm - 1;
+            r = max(r, sh_r1[w * 32 + s]);
           }
         }
-        sh_r1[tid] = r + 1;
-        st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: rank word doubles as the ready flag
+        st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: the rank word doubles as the ready flag
         rankS[i] = r;
       }
       __syncthreads();
