@@ -13,22 +13,88 @@
 
 namespace {
 
-// ---- L^-1 by column-parallel forward substitution (once per epoch, not on the per-generation path)
-__global__ void trinv_kernel(const double* __restrict__ L, int64_t N, int64_t ldo, double* __restrict__ X) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t c0 = c - (threadIdx.x & 31);  // first column of this warp
-  const bool live = c < N;
-  for (int64_t i = c0; i < N; ++i) {
+// ---- L^-1 (once per epoch, not on the per-generation path): blocked recursive inversion
+//   inv([A 0; C B]) = [A^-1 0; -B^-1 C A^-1, B^-1].  The 128 x 128 diagonal blocks are inverted by forward substitution
+//   (one thread per column), then log2(N/128) levels of batched float64 GEMMs double the inverted block size.
+//   The matrix is embedded in a power-of-two multiple of 128 with an identity tail.
+constexpr int TRI_B = 128;
+
+__global__ void tri_embed_kernel(const double* __restrict__ L, int64_t N, int64_t Np, double* __restrict__ Lp) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Np * Np) return;
+  int64_t r = t / Np, c = t - r * Np;
+  Lp[t] = (r < N && c < N) ? (c <= r ? L[r * N + c] : 0.0) : (r == c ? 1.0 : 0.0);
+}
+
+// one CTA per diagonal block, one thread per column of the block (L entries are warp-uniform loads, X column-coalesced)
+__global__ void __launch_bounds__(TRI_B) tri_diag_inverse_kernel(const double* __restrict__ Lp, int64_t Np,
+                                                                 double* __restrict__ X) {
+  const int64_t base = (int64_t)blockIdx.x * TRI_B;
+  const int c = threadIdx.x;
+  const double* Lb = Lp + base * Np + base;
+  double* Xb = X + base * Np + base;
+  for (int i = 0; i < TRI_B; ++i) {
     double s = (i == c) ? 1.0 : 0.0;
-    const double* Li = L + i * N;
-    for (int64_t k = c0; k < i; ++k) {
-      double l = Li[k];                                  // broadcast
-      double x = (live && k >= c) ? X[k * ldo + c] : 0.0;  // coalesced
+    const double* Li = Lb + (int64_t)i * Np;
+    for (int k = 0; k < i; ++k) {
+      const double l = __ldg(Li + k);
+      const double x = (k >= c) ? Xb[(int64_t)k * Np + c] : 0.0;
       s -= l * x;
     }
-    if (live && i >= c) X[i * ldo + c] = s / Li[i];
-    __syncwarp();
+    Xb[(int64_t)i * Np + c] = (i >= c) ? s / __ldg(Li + i) : 0.0;
   }
+}
+
+// C = alpha * A * B, all row-major, batched over blockIdx.z; 64 x 64 tile, 16-wide k step, 256 threads x (4 x 4)
+__global__ void __launch_bounds__(256) gemm_nn_f64_kernel(const double* __restrict__ A, int64_t lda, int64_t sA,
+                                                          const double* __restrict__ B, int64_t ldb, int64_t sB,
+                                                          double* __restrict__ C, int64_t ldc, int64_t sC, int64_t Msz,
+                                                          int64_t Nsz, int64_t Ksz, double alpha) {
+  __shared__ double As[16][64 + 1];
+  __shared__ double Bs[16][64 + 1];
+  A += (int64_t)blockIdx.z * sA;
+  B += (int64_t)blockIdx.z * sB;
+  C += (int64_t)blockIdx.z * sC;
+  const int64_t m0 = (int64_t)blockIdx.y * 64, n0 = (int64_t)blockIdx.x * 64;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  double acc[4][4] = {};
+  for (int64_t k0 = 0; k0 < Ksz; k0 += 16) {
+    for (int t = tid; t < 64 * 16; t += 256) {
+      const int r = t >> 4, k = t & 15;  // A tile: 64 rows x 16 k
+      As[k][r] = A[(m0 + r) * lda + k0 + k];
+      const int kb = t >> 6, cb = t & 63;  // B tile: 16 k x 64 cols
+      Bs[kb][cb] = B[(k0 + kb) * ldb + n0 + cb];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        a[x] = As[k][ty * 4 + x];
+        b[x] = Bs[k][tx * 4 + x];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) C[(m0 + ty * 4 + x) * ldc + n0 + tx * 4 + y] = alpha * acc[x][y];
+  (void)Msz;
+  (void)Nsz;
+}
+
+__global__ void tri_extract_kernel(const double* __restrict__ X, int64_t Np, int64_t N, int64_t ldo,
+                                   double* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * N) return;
+  int64_t r = t / N, c = t - r * N;
+  out[r * ldo + c] = (c <= r) ? X[r * Np + c] : 0.0;
 }
 
 __global__ void copy_pad_kernel(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t ldo,
@@ -384,7 +450,29 @@ int dmo_gp_create(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const doubl
       if (factor_is_inverse) {
         DMO_LAUNCH(copy_pad_kernel, (unsigned)ceil_div(N * N, 256), 256, 0, src, N, N, Npad, dst);
       } else {
-        DMO_LAUNCH(trinv_kernel, (unsigned)ceil_div(N, 128), 128, 0, src, N, Npad, dst);
+        int64_t Np = TRI_B;
+        while (Np < N) Np *= 2;
+        DevBuf<double> Lp, X, T;
+        GP_TRY(Lp.alloc(ctx, (size_t)Np * Np));
+        GP_TRY(X.alloc(ctx, (size_t)Np * Np));
+        GP_TRY(T.alloc(ctx, (size_t)Np * Np / 2));
+        GP_CUDA(cudaMemsetAsync(X.p, 0, (size_t)Np * Np * sizeof(double), ctx->stream));
+        DMO_LAUNCH(tri_embed_kernel, (unsigned)ceil_div(Np * Np, 256), 256, 0, src, N, Np, Lp.p);
+        DMO_LAUNCH(tri_diag_inverse_kernel, (unsigned)(Np / TRI_B), TRI_B, 0, Lp.p, Np, X.p);
+        for (int64_t sz = TRI_B; sz < Np; sz *= 2) {
+          const int64_t pairs = Np / (2 * sz);
+          const int64_t stride = 2 * sz * Np + 2 * sz;  // next diagonal 2s x 2s block
+          dim3 grid((unsigned)(sz / 64), (unsigned)(sz / 64), (unsigned)pairs);
+          // T = C * A^-1        (C = Lp[s:2s, 0:s], A^-1 = X[0:s, 0:s])
+          DMO_LAUNCH(gemm_nn_f64_kernel, grid, 256, 0, Lp.p + sz * Np, Np, stride, X.p, Np, stride, T.p, sz, sz * sz, sz, sz,
+                     sz, 1.0);
+          // X[s:2s, 0:s] = -B^-1 * T   (B^-1 = X[s:2s, s:2s])
+          DMO_LAUNCH(gemm_nn_f64_kernel, grid, 256, 0, X.p + sz * Np + sz, Np, stride, T.p, sz, sz * sz, X.p + sz * Np, Np,
+                     stride, sz, sz, sz, -1.0);
+        }
+        DMO_LAUNCH(tri_extract_kernel, (unsigned)ceil_div(N * N, 256), 256, 0, X.p, Np, N, Npad, dst);
+        GP_CUDA(cudaGetLastError());
+        GP_CUDA(cudaStreamSynchronize(ctx->stream));
       }
     }
     GP_CUDA(cudaGetLastError());

@@ -74,6 +74,54 @@ __global__ void min_col_kernel(const double* __restrict__ F, int64_t n, double* 
   if (threadIdx.x == 0) out[0] = s[0];
 }
 
+// Non-dominated filter (rank-0 test only): points are sorted by objective 0; a target scans the sources whose
+// objective 0 is <= its own and stops at the first dominator (warp-wide early exit).  For a scattered cloud almost
+// every point finds a dominator within the first tile; for a true front it is the full n^2/2 scan.
+constexpr int ND_T = 128;
+constexpr int ND_MAXM = 8;
+__global__ void __launch_bounds__(ND_T) nondominated_flag_kernel(const double* __restrict__ F, const uint32_t* __restrict__ sidx,
+                                                                 int64_t n, int M, int32_t* __restrict__ flag) {
+  extern __shared__ double tile_nd[];  // [ND_T][M]
+  const int64_t p = (int64_t)blockIdx.x * ND_T + threadIdx.x;
+  const bool live = p < n;
+  double v[ND_MAXM];
+  const int64_t me = live ? (int64_t)sidx[p] : 0;
+  for (int j = 0; j < ND_MAXM; ++j) v[j] = (j < M && live) ? F[me * M + j] : 0.0;
+  bool dominated = !live;
+  bool done = !live;
+  for (int64_t t0 = 0; t0 < n; t0 += ND_T) {
+    if (__syncthreads_and(done ? 1 : 0)) break;
+    const int64_t q = t0 + threadIdx.x;
+    if (q < n) {
+      const int64_t src = sidx[q];
+      for (int j = 0; j < M; ++j) tile_nd[threadIdx.x * M + j] = F[src * M + j];
+    }
+    __syncthreads();
+    const int cnt = (int)((n - t0) < ND_T ? (n - t0) : ND_T);
+    if (!done) {
+      for (int s = 0; s < cnt; ++s) {
+        const double* sp = tile_nd + s * M;
+        if (sp[0] > v[0]) {  // sorted by objective 0: nothing further can dominate
+          done = true;
+          break;
+        }
+        bool le = true, lt = false;
+        for (int j = 0; j < M; ++j) {
+          le = le && (sp[j] <= v[j]);
+          lt = lt || (sp[j] < v[j]);
+        }
+        if (le && lt) {
+          dominated = true;
+          done = true;
+          break;
+        }
+      }
+    }
+  }
+  if (live) flag[me] = dominated ? 0 : 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) flag[n] = 0;
+}
+
 // deterministic block sum -> partial[blockIdx.x]
 __device__ __forceinline__ void block_sum_store(double v, double* partial) {
   __shared__ double ws[32];
@@ -390,13 +438,19 @@ int compact_rows(dmo_ctx* ctx, const double* dF, int64_t n, int M, DevBuf<int32_
   return DMO_OK;
 }
 
-// rank-0 subset of a device point set
+int sort_by_column(dmo_ctx* ctx, const double* dF, int64_t n, int M, int j, DevBuf<uint32_t>& sidx);
+
+// rank-0 subset of a device point set (identical vectors are mutually non-dominating and are all kept)
 int nondominated_subset(dmo_ctx* ctx, const double* dF, int64_t n, int M, DevBuf<double>& out, int64_t* count) {
-  DevBuf<int32_t> rank, flag;
-  DMO_TRY(rank.alloc(ctx, n));
+  DevBuf<int32_t> flag;
+  DevBuf<uint32_t> sidx;
   DMO_TRY(flag.alloc(ctx, n + 1));
-  DMO_TRY(rank_nd_device(ctx, dF, n, M, rank.p));
-  DMO_LAUNCH(rank0_flag_kernel, (unsigned)ceil_div(n + 1, 256), 256, 0, rank.p, n, flag.p);
+  DMO_TRY(sort_by_column(ctx, dF, n, M, 0, sidx));
+  {
+    ProfileScope ps(ctx, "nd_filter");
+    DMO_LAUNCH(nondominated_flag_kernel, (unsigned)ceil_div(n, ND_T), ND_T, (size_t)ND_T * M * sizeof(double), dF, sidx.p, n, M,
+               flag.p);
+  }
   DMO_TRY(compact_rows(ctx, dF, n, M, flag, out, count));
   return DMO_OK;
 }

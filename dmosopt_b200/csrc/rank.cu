@@ -122,11 +122,15 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
   constexpr int NV = W / 4;
   constexpr int NW = T / 32;
   constexpr int RQ = M / 4, RC = M % 4;  // uint4 / component holding the rank word
+  constexpr int DLD = T + 4;  // row stride of the path-length table in bytes: (a*33 + j/4) mod 32 -> conflict free
+  constexpr int SENT = -128;  // "no in-block path"; real path lengths are 0 .. T-1 <= 127
   __shared__ uint4 tile[T * NV];
   __shared__ __align__(16) int sh_r1[T];
+  __shared__ uint32_t sh_mask[T * NW];
+  __shared__ int8_t sD[T * DLD];
   __shared__ int sh_blk;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
 
   for (;;) {
     if (tid == 0) sh_blk = atomicAdd(ticket, 1);
@@ -167,6 +171,32 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
         m |= (dom ? 1u : 0u) << s;
       }
       mask[w] = m;
+      sh_mask[tid * NW + w] = m;
+    }
+    __syncthreads();
+
+    // ---- in-block longest-path table, computed BEFORE any rank is needed (off the critical path):
+    // D[a][i] = number of edges of the longest in-block domination chain a -> ... -> i (SENT if none, 0 for i == a).
+    // Thread a fills row a left to right; entry i only needs mask_i (shared) and earlier entries of the same row, so
+    // the 128 rows are independent and no barrier is needed.  With it, the in-block resolution collapses to one
+    // max-plus product  rank_i = max_a (best_a + D[a][i])  instead of a data-dependent number of rounds.
+    {
+      int8_t* row = sD + tid * DLD;
+      for (int i2 = 0; i2 < T; ++i2) row[i2] = (int8_t)((i2 == tid) ? 0 : SENT);
+      for (int i2 = tid + 1; i2 < T; ++i2) {
+        int val = SENT;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          uint32_t mm = sh_mask[i2 * NW + w];
+          if (w * 32 + 31 < tid) mm = 0u;  // sources before a cannot be reached from a
+          while (mm) {
+            const int s = __ffs(mm) - 1;
+            mm &= mm - 1;
+            val = max(val, (int)row[w * 32 + s] + 1);
+          }
+        }
+        row[i2] = (int8_t)(val > 0 ? val : SENT);  // unreachable sources only contribute SENT + 1 < 0
+      }
     }
     __syncthreads();
 
@@ -263,54 +293,18 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
       __syncthreads();
     }
 
-    // ---- in-block chain, warp by warp (dependencies only run from lower to higher index, so a chain crosses at most
-    // T/32 warps).  Warp w first folds in the now final ranks of warps < w, then resolves its own 32 points in
-    // mini-rounds that need only a ballot and a __syncwarp: a lane is final once all its in-warp dominators are, newly
-    // final lanes post rank + 1 to shared memory and the others fold in just those bits.  Each warp publishes its ranks
-    // at once, so the successor block can start consuming them while warps w+1.. are still working.
+    // ---- in-block resolution: one max-plus product over the possible in-block ancestors
+    sh_r1[tid] = best;
+    __syncthreads();
     int r = best;
-    for (int w = 0; w < NW; ++w) {
-      if (warp == w) {
-        uint32_t mw = 0u;
-#pragma unroll
-        for (int ww = 0; ww < NW; ++ww) {
-          if (ww == w) mw = mask[ww];
-          if (ww < w) {
-            const uint32_t mm = mask[ww];
-#pragma unroll 2
-            for (int s4 = 0; s4 < 8; ++s4) {
-              const int4 rr = *reinterpret_cast<const int4*>(&sh_r1[ww * 32 + s4 * 4]);
-              r = ((mm >> (s4 * 4 + 0)) & 1u) ? max(r, rr.x) : r;
-              r = ((mm >> (s4 * 4 + 1)) & 1u) ? max(r, rr.y) : r;
-              r = ((mm >> (s4 * 4 + 2)) & 1u) ? max(r, rr.z) : r;
-              r = ((mm >> (s4 * 4 + 3)) & 1u) ? max(r, rr.w) : r;
-            }
-          }
-        }
-        uint32_t finalm = 0u;
-        bool fin = false;
-        for (int round = 0; round < 33; ++round) {
-          const bool ready = !fin && ((mw & ~finalm) == 0u);
-          const unsigned newly = __ballot_sync(0xffffffffu, ready);
-          if (ready) {
-            sh_r1[tid] = r + 1;
-            fin = true;
-          }
-          finalm |= newly;
-          __syncwarp();
-          if (finalm == 0xFFFFFFFFu) break;
-          uint32_t mm = mw & newly;
-          while (mm) {
-            const int s = __ffs(mm) - 1;
-            mm &= mm - 1;
-            r = max(r, sh_r1[w * 32 + s]);
-          }
-        }
-        st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: the rank word doubles as the ready flag
-        rankS[i] = r;
-      }
-      __syncthreads();
+#pragma unroll 4
+    for (int a2 = 0; a2 < T; ++a2) {
+      const int dl = (int)sD[a2 * DLD + tid];
+      r = (dl >= 0) ? max(r, sh_r1[a2] + dl) : r;  // SENT = not an ancestor
     }
+    st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: the rank word doubles as the ready flag
+    rankS[i] = r;
+    __syncthreads();
   }
 }
 

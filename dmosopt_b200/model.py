@@ -119,7 +119,7 @@ class _GPRBase:
         self._gp = _lib.GPHandle(
             X_train=np.asarray(sm[0].X_train_, dtype=np.float64),
             alpha=np.stack([np.ravel(g.alpha_) for g in sm]),
-            factor=np.stack([np.asarray(g.L_, dtype=np.float64) for g in sm]),
+            factor=np.stack([np.asarray(g.L_, dtype=np.float64) for g in sm]),  # L^-1 is formed on the GPU
             constant=[g.kernel_.k1.k1.constant_value for g in sm],
             length_scale=[np.broadcast_to(np.asarray(g.kernel_.k1.k2.length_scale, dtype=np.float64), (d,)) for g in sm],
             noise=[g.kernel_.k2.noise_level for g in sm],

@@ -107,7 +107,8 @@ def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, muta
 
 class GPHandle:
     def __init__(self, X_train, alpha, factor, constant, length_scale, noise, y_mean, y_std, xlb, xub, kernel=0, factor_is_inverse=False):
-        assert not factor_is_inverse
+        if factor_is_inverse:  # the plugin uploads L^-1; the oracle works with L
+            factor = [np.linalg.inv(np.asarray(f)) for f in factor]
         self.st = gp.GPState(X_train=np.asarray(X_train, float), xlb=np.asarray(xlb, float), xub=np.asarray(xub, float))
         self.M = len(alpha)
         for m in range(self.M):
