@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "gp.cuh"
 
@@ -295,6 +296,182 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ the GEMM, version 2
+// Same contraction, 1.5x less L2 -> shared-memory traffic per MMA: a work item owns 256 candidates (two M = 128
+// sub-tiles that share every Linv tile), k is staged 32 elements at a time (64-byte rows, SWIZZLE_64B) so that three
+// 64 KiB stages fit, both TMEM accumulators (2 x 256 columns) belong to the two sub-tiles, and the Linv row blocks of a
+// candidate block are split into two halves of equal MMA count (two work items, partial sums added in a fixed order)
+// to keep the tail of the persistent schedule short.
+namespace v2 {
+constexpr int TM2 = 256, TN2 = 256, TK2 = 32, STAGES2 = 3;
+constexpr int TILE_BYTES2 = 256 * TK2 * 2;             // 16 KiB: 256 rows x 64 B
+constexpr int STAGE_BYTES2 = 4 * TILE_BYTES2;          // K* hi/lo + Linv hi/lo
+constexpr size_t GEMM_SMEM2 = (size_t)STAGES2 * STAGE_BYTES2 + 1024 + 256;
+
+// K-major SWIZZLE_64B descriptor: 8-row groups are 512 B apart, layout type 4
+__device__ __forceinline__ uint64_t make_sdesc64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
+struct GemmParams2 {
+  int M, n_pb, n_jt, j_split;  // row blocks [0, j_split) belong to half 0, [j_split, n_jt) to half 1
+  int64_t k_rows, l_rows;
+  const float* inv_scale;
+  double* vnorm;  // [2][M][vn_ld]
+  int64_t vn_ld;
+  int* abort_flag;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+    gp_var_tc2_kernel(const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl,
+                      const __grid_constant__ CUtensorMap map_lh, const __grid_constant__ CUtensorMap map_ll,
+                      const GemmParams2 prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(tiles + (size_t)STAGES2 * STAGE_BYTES2);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES2;
+  uint64_t* acc_full = bars + 2 * STAGES2;
+  uint64_t* acc_empty = bars + 2 * STAGES2 + 1;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES2 + 2);
+  volatile int* abort_flag = prm.abort_flag;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_work = prm.M * prm.n_pb * 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int z = w & 1, wp = w >> 1;
+        const int m = wp / prm.n_pb, pb = wp - m * prm.n_pb;
+        const int a_row = (int)(m * prm.k_rows + (int64_t)pb * TM2);
+        const int j0 = z ? prm.j_split : 0, j1 = z ? prm.n_jt : prm.j_split;
+        for (int jt = j0; jt < j1; ++jt) {
+          const int b_row = (int)(m * prm.l_rows + (int64_t)jt * TN2);
+          const int nkc = (jt + 1) * (TN2 / TK2);
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1u, abort_flag);
+            uint8_t* st = tiles + (size_t)stage * STAGE_BYTES2;
+            mbar_expect_tx(&full[stage], STAGE_BYTES2);
+            tma_load_2d(&map_kh, &full[stage], st, kc * TK2, a_row);
+            tma_load_2d(&map_kl, &full[stage], st + TILE_BYTES2, kc * TK2, a_row);
+            tma_load_2d(&map_lh, &full[stage], st + 2 * TILE_BYTES2, kc * TK2, b_row);
+            tma_load_2d(&map_ll, &full[stage], st + 3 * TILE_BYTES2, kc * TK2, b_row);
+            if (++stage == STAGES2) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int z = w & 1;
+        const int j0 = z ? prm.j_split : 0, j1 = z ? prm.n_jt : prm.j_split;
+        for (int jt = j0; jt < j1; ++jt) {
+          mbar_wait(acc_empty, acc_phase ^ 1u, abort_flag);
+          tc_fence_after();
+          const int nkc = (jt + 1) * (TN2 / TK2);
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&full[stage], phase, abort_flag);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t d_tmem = tmem_base + h * TN2;
+              const uint32_t a_off = h * (128 * TK2 * 2);  // second sub-tile: rows 128..255 of the K* boxes
+              const uint64_t a_hi = make_sdesc64(sa + a_off), a_lo = make_sdesc64(sa + TILE_BYTES2 + a_off);
+              const uint64_t b_hi = make_sdesc64(sa + 2 * TILE_BYTES2), b_lo = make_sdesc64(sa + 3 * TILE_BYTES2);
+#pragma unroll
+              for (int ks = 0; ks < TK2 / UK; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UK * 2) >> 4);
+                tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kc | ks) ? 1u : 0u);
+                tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+                tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1u);
+              }
+            }
+            tc_commit(&empty[stage]);
+            if (++stage == STAGES2) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          tc_commit(acc_full);
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int z = w & 1, wp = w >> 1;
+      const int m = wp / prm.n_pb, pb = wp - m * prm.n_pb;
+      const float* isc = prm.inv_scale + (int64_t)m * prm.l_rows;
+      const int j0 = z ? prm.j_split : 0, j1 = z ? prm.n_jt : prm.j_split;
+      double total0 = 0.0, total1 = 0.0;
+      for (int jt = j0; jt < j1; ++jt) {
+        mbar_wait(acc_full, acc_phase, abort_flag);
+        tc_fence_after();
+        float part0 = 0.f, part1 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN2; c0 += 32) {
+          uint32_t r0[32], r1[32];
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c0;
+          tc_ld_32x32(t_addr, r0);
+          tc_ld_32x32(t_addr + TN2, r1);
+          tc_wait_ld();
+          const float* sc = isc + jt * TN2 + c0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float s = __ldg(sc + e);
+            const float t0 = __uint_as_float(r0[e]) * s, t1 = __uint_as_float(r1[e]) * s;
+            part0 = fmaf(t0, t0, part0);
+            part1 = fmaf(t1, t1, part1);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        total0 += (double)part0;
+        total1 += (double)part1;
+        acc_phase ^= 1u;
+      }
+      double* out = prm.vnorm + ((int64_t)z * prm.M + m) * prm.vn_ld + (int64_t)pb * TM2 + quarter * 32 + lane;
+      out[0] = total0;
+      out[128] = total1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+}  // namespace v2
+
 // ------------------------------------------------------------------------------------------------ operand preparation
 // Linv row -> scaled fp16 hi / lo.  One block per (objective, row).
 __global__ void split_linv_kernel(const double* __restrict__ Linv, int64_t Npad, int M, const int* __restrict__ k_exp,
@@ -438,14 +615,16 @@ __global__ void mean_split_kernel(const uint16_t* __restrict__ Kh, const uint16_
   if (lane == 0) mean[(p_base + pl) * M + m] = ystd[m] * scalbn(s, -k_exp[m]) + ymean[m];
 }
 
-__global__ void var_finish_tc_kernel(const double* __restrict__ vnorm, int64_t Pc, int64_t ld, int M,
+__global__ void var_finish_tc_kernel(const double* __restrict__ vnorm, int nplanes, int64_t Pc, int64_t ld, int M,
                                      const double* __restrict__ constant, const double* __restrict__ noise,
                                      const double* __restrict__ ystd, int64_t p_base, double* __restrict__ var) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= Pc * M) return;
   int64_t pl = t / M;
   int m = (int)(t - pl * M);
-  double v = (constant[m] + noise[m]) - vnorm[(int64_t)m * ld + pl];
+  double vn = vnorm[(int64_t)m * ld + pl];
+  if (nplanes == 2) vn += vnorm[((int64_t)M + m) * ld + pl];  // the two halves of the Linv row blocks, fixed order
+  double v = (constant[m] + noise[m]) - vn;
   if (v < 0.0) v = 0.0;
   double sd = sqrt(v * (ystd[m] * ystd[m]));
   var[(p_base + pl) * M + m] = sd * sd;
@@ -465,15 +644,16 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // 2-D fp16 tensor [rows][cols] (cols contiguous), box = box_rows x 64 columns, 128-byte swizzle
-int make_map(dmo_ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+int make_map(dmo_ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+             uint32_t box_cols = TK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto fn = get_encode_fn();
   if (!fn) return dmo_fail(ctx, DMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TK, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return dmo_fail(ctx, DMO_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return DMO_OK;
@@ -513,25 +693,39 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   int64_t Pc_max = ((int64_t)6 << 30) / ((int64_t)M * Npad * 4);
   Pc_max = (Pc_max / TM) * TM;
   if (Pc_max < TM) Pc_max = TM;
-  const int64_t Pc_alloc = P < Pc_max ? ceil_div(P, TM) * TM : Pc_max;
+  // kernel version: 2 (default) = 256-candidate work items, SWIZZLE_64B, 3 stages; 1 = first version (DMO_GP_TC=1)
+  int version = 2;
+  if (const char* e = getenv("DMO_GP_TC")) version = atoi(e) == 1 ? 1 : 2;
+  const int64_t TMv = version == 2 ? v2::TM2 : TM;
+  Pc_max = (Pc_max / TMv) * TMv;
+  if (Pc_max < TMv) Pc_max = TMv;
+  const int64_t Pc_alloc = P < Pc_max ? ceil_div(P, TMv) * TMv : Pc_max;
   DevBuf<uint16_t> Kh, Kl;
   DevBuf<double> vnorm;
   DevBuf<int> abort_flag;
   DMO_TRY(Kh.alloc(ctx, (size_t)M * Pc_alloc * Npad));
   DMO_TRY(Kl.alloc(ctx, (size_t)M * Pc_alloc * Npad));
-  DMO_TRY(vnorm.alloc(ctx, (size_t)M * Pc_alloc));
+  DMO_TRY(vnorm.alloc(ctx, (size_t)2 * M * Pc_alloc));
   DMO_TRY(abort_flag.alloc(ctx, 1));
   DMO_CUDA(cudaMemsetAsync(abort_flag.p, 0, sizeof(int), ctx->stream));
   CUtensorMap map_kh, map_kl, map_lh, map_ll;
-  DMO_TRY(make_map(ctx, &map_kh, Kh.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, TM));
-  DMO_TRY(make_map(ctx, &map_kl, Kl.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, TM));
-  DMO_TRY(make_map(ctx, &map_lh, gp->Lhi.p, (uint64_t)M * Npad, (uint64_t)Npad, TN));
-  DMO_TRY(make_map(ctx, &map_ll, gp->Llo.p, (uint64_t)M * Npad, (uint64_t)Npad, TN));
-  DMO_CUDA(cudaFuncSetAttribute(gp_var_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  if (version == 2) {
+    DMO_TRY(make_map(ctx, &map_kh, Kh.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
+    DMO_TRY(make_map(ctx, &map_kl, Kl.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
+    DMO_TRY(make_map(ctx, &map_lh, gp->Lhi.p, (uint64_t)M * Npad, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
+    DMO_TRY(make_map(ctx, &map_ll, gp->Llo.p, (uint64_t)M * Npad, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
+    DMO_CUDA(cudaFuncSetAttribute(v2::gp_var_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::GEMM_SMEM2));
+  } else {
+    DMO_TRY(make_map(ctx, &map_kh, Kh.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, TM));
+    DMO_TRY(make_map(ctx, &map_kl, Kl.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, TM));
+    DMO_TRY(make_map(ctx, &map_lh, gp->Lhi.p, (uint64_t)M * Npad, (uint64_t)Npad, TN));
+    DMO_TRY(make_map(ctx, &map_ll, gp->Llo.p, (uint64_t)M * Npad, (uint64_t)Npad, TN));
+    DMO_CUDA(cudaFuncSetAttribute(gp_var_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  }
   const int64_t kplane = Pc_alloc * Npad;
   for (int64_t p_base = 0; p_base < P; p_base += Pc_alloc) {
     const int64_t Pc = (P - p_base) < Pc_alloc ? (P - p_base) : Pc_alloc;
-    const int64_t Pcpad = ceil_div(Pc, TM) * TM;
+    const int64_t Pcpad = ceil_div(Pc, TMv) * TMv;
     {
       ProfileScope ps(ctx, "gp_kstar");
       dim3 gk((unsigned)(Npad / (2 * KT_TN)), (unsigned)ceil_div(Pcpad, KT_TP));
@@ -557,7 +751,40 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       DMO_LAUNCH(mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane, M,
                  gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
     }
-    if (d_var) {
+    if (d_var && version == 2) {
+      v2::GemmParams2 prm;
+      prm.M = M;
+      prm.n_pb = (int)(Pcpad / v2::TM2);
+      prm.n_jt = (int)(Npad / v2::TN2);
+      // split the row blocks where the cumulative MMA count sum_{j < J} (j + 1) is closest to half of the total
+      {
+        const int64_t tot = (int64_t)prm.n_jt * (prm.n_jt + 1) / 2;
+        int best_j = prm.n_jt;
+        int64_t best_d = tot;
+        for (int J = 0; J <= prm.n_jt; ++J) {
+          const int64_t dlt = llabs(2 * ((int64_t)J * (J + 1) / 2) - tot);
+          if (dlt < best_d) {
+            best_d = dlt;
+            best_j = J;
+          }
+        }
+        prm.j_split = best_j;
+      }
+      prm.k_rows = Pc_alloc;
+      prm.l_rows = Npad;
+      prm.inv_scale = gp->Lscale.p;
+      prm.vnorm = vnorm.p;
+      prm.vn_ld = Pc_alloc;
+      prm.abort_flag = abort_flag.p;
+      const int n_work = prm.M * prm.n_pb * 2;
+      const int grid = n_work < ctx->sm_count ? n_work : ctx->sm_count;
+      {
+        ProfileScope ps(ctx, "gp_var");
+        DMO_LAUNCH(v2::gp_var_tc2_kernel, grid, NTHREADS, v2::GEMM_SMEM2, map_kh, map_kl, map_lh, map_ll, prm);
+      }
+      DMO_LAUNCH(var_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, 2, Pc, Pc_alloc, M,
+                 gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
+    } else if (d_var) {
       GemmParams prm;
       prm.M = M;
       prm.n_pb = (int)(Pcpad / TM);
@@ -574,7 +801,7 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
         ProfileScope ps(ctx, "gp_var");
         DMO_LAUNCH(gp_var_tc_kernel, grid, NTHREADS, GEMM_SMEM, map_kh, map_kl, map_lh, map_ll, prm);
       }
-      DMO_LAUNCH(var_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, Pc, Pc_alloc, M,
+      DMO_LAUNCH(var_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, 1, Pc, Pc_alloc, M,
                  gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
     }
   }

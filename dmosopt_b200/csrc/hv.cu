@@ -445,12 +445,12 @@ int nondominated_subset(dmo_ctx* ctx, const double* dF, int64_t n, int M, DevBuf
   DevBuf<int32_t> flag;
   DevBuf<uint32_t> sidx;
   DMO_TRY(flag.alloc(ctx, n + 1));
-  if (n >= 4096) {
-    // large sets: the integer chain kernel costs O(n^2 / 2) cheap id compares whatever the data looks like, while the
+  if (n >= 1024) {
+    // large sets: the integer-id scan costs O(n^2 / 2) cheap id compares whatever the data looks like, while the
     // early-exit scan below degenerates to n^2 / 2 float64 tests as soon as every block holds a non-dominated point
     DevBuf<int32_t> rank;
     DMO_TRY(rank.alloc(ctx, n));
-    DMO_TRY(rank_nd_device(ctx, dF, n, M, rank.p));
+    DMO_TRY(nondominated_flags_device(ctx, dF, n, M, rank.p));
     DMO_LAUNCH(rank0_flag_kernel, (unsigned)ceil_div(n + 1, 256), 256, 0, rank.p, n, flag.p);
     DMO_TRY(compact_rows(ctx, dF, n, M, flag, out, count));
     return DMO_OK;

@@ -308,6 +308,67 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
   }
 }
 
+// Rank-0 test only (filter for the hypervolume / EHVI routines): "is some point dominating me" has no dependency chain,
+// so it is the bulk scan alone, with a block-wide early exit once every target of the block has found a dominator.
+template <int M, int T>
+__global__ void __launch_bounds__(T) nd_flag_kernel(const uint32_t* __restrict__ rec, int nblocks, int* __restrict__ flagS) {
+  constexpr int W = 4 * ((M + 1 + 3) / 4);
+  constexpr int NV = W / 4;
+  __shared__ uint4 tile[T * NV];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int64_t i = (int64_t)b * T + tid;
+  uint32_t v[W];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(rec + i * W);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      uint4 a = src[q];
+      v[4 * q + 0] = a.x;
+      v[4 * q + 1] = a.y;
+      v[4 * q + 2] = a.z;
+      v[4 * q + 3] = a.w;
+    }
+  }
+  const uint32_t gidv = v[M - 1];
+  bool dominated = false;
+  for (int k = 0; k <= b; ++k) {
+    if (__syncthreads_and(dominated ? 1 : 0)) break;
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)k * T * W);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) tile[tid * NV + q] = src[tid * NV + q];
+    }
+    __syncthreads();
+    const int lim = (k == b) ? tid : T;  // inside the own block only earlier positions can dominate
+#pragma unroll 8
+    for (int s = 0; s < T; ++s) {
+      uint32_t sw[W];
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        uint4 a = tile[s * NV + q];
+        sw[4 * q + 0] = a.x;
+        sw[4 * q + 1] = a.y;
+        sw[4 * q + 2] = a.z;
+        sw[4 * q + 3] = a.w;
+      }
+      bool dom = (s < lim) && (sw[M - 1] != gidv);
+#pragma unroll
+      for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
+      dominated = dominated || dom;
+    }
+  }
+  flagS[i] = dominated ? 1 : 0;
+}
+
+template <int M>
+int launch_nd_flags(dmo_ctx* ctx, const uint32_t* rec, int nblocks, int* flagS) {
+  ProfileScope ps(ctx, "nd_flags");
+  DMO_LAUNCH((nd_flag_kernel<M, RANK_T>), nblocks, RANK_T, 0, rec, nblocks, flagS);
+  DMO_CHECK_LAUNCH();
+  return DMO_OK;
+}
+
 __global__ void scatter_rank_kernel(const int* __restrict__ rankS, const uint32_t* __restrict__ perm, int64_t n,
                                     int32_t* __restrict__ rank) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,7 +405,7 @@ int bits_for(int64_t n) {
 
 }  // namespace
 
-int rank_nd_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_rank) {
+int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_rank, bool flags_only) {
   if (n <= 0) return DMO_OK;
   DMO_REQUIRE(M >= 1 && M <= 8, "rank_nd: M=%d out of range [1,8]", M);
   DMO_REQUIRE(n < ((int64_t)1 << 31) - 4096, "rank_nd: n too large");
@@ -413,6 +474,20 @@ int rank_nd_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_
   DMO_LAUNCH(build_records_kernel, (unsigned)ceil_div(npad, 256), 256, 0, R.p, perm, gid.p, n, npad, M, W, rec.p);
   int* ticket = sync.p + nblocks;
   int* errflag = sync.p + nblocks + 1;
+  if (flags_only) {  // d_rank receives 0 for non-dominated points and 1 otherwise
+    switch (M) {
+      case 2: DMO_TRY(launch_nd_flags<2>(ctx, rec.p, (int)nblocks, rankS.p)); break;
+      case 3: DMO_TRY(launch_nd_flags<3>(ctx, rec.p, (int)nblocks, rankS.p)); break;
+      case 4: DMO_TRY(launch_nd_flags<4>(ctx, rec.p, (int)nblocks, rankS.p)); break;
+      case 5: DMO_TRY(launch_nd_flags<5>(ctx, rec.p, (int)nblocks, rankS.p)); break;
+      case 6: DMO_TRY(launch_nd_flags<6>(ctx, rec.p, (int)nblocks, rankS.p)); break;
+      case 7: DMO_TRY(launch_nd_flags<7>(ctx, rec.p, (int)nblocks, rankS.p)); break;
+      default: DMO_TRY(launch_nd_flags<8>(ctx, rec.p, (int)nblocks, rankS.p)); break;
+    }
+    DMO_LAUNCH(scatter_rank_kernel, g, 256, 0, rankS.p, perm, n, d_rank);
+    DMO_CHECK_LAUNCH();
+    return DMO_OK;
+  }
   switch (M) {
     case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
     case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
@@ -429,6 +504,13 @@ int rank_nd_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_
   DMO_CUDA(cudaStreamSynchronize(ctx->stream));
   if (herr) return dmo_fail(ctx, DMO_ERR_INTERNAL, "rank_nd: chain kernel watchdog tripped");
   return DMO_OK;
+}
+
+int rank_nd_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_rank) {
+  return rank_nd_device_ex(ctx, dY, n, M, d_rank, false);
+}
+int nondominated_flags_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_flag01) {
+  return rank_nd_device_ex(ctx, dY, n, M, d_flag01, true);
 }
 
 extern "C" int dmo_rank_nd(dmo_ctx* ctx, const double* Y, int64_t n, int M, int32_t* rank) {
