@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
   __shared__ __align__(16) int sh_r1[T];
   __shared__ uint32_t sh_mask[T * NW];
   __shared__ int8_t sD[T * DLD];
+  __shared__ int8_t sE[T * DLD];
+  __shared__ uint32_t sh_pmask[T * NW];
   __shared__ int sh_blk;
 
   const int tid = threadIdx.x;
@@ -209,10 +211,13 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
 #pragma unroll
         for (int q = 0; q < NV; ++q) a[q] = ld_relaxed_v4(src + q);
         unsigned spins = 0;
-        while (word_of(a[RQ], RC) == 0u) {  // not final yet (only ever true close to the diagonal)
-          __nanosleep(20);
+        // Not final yet: this block has caught up with the wavefront.  It is at least two links away from being the
+        // critical block (that one waits in the dedicated predecessor poll below), so it backs off generously and
+        // leaves the SM's issue slots to the blocks that are on the critical path.
+        while (word_of(a[RQ], RC) == 0u) {
+          __nanosleep(spins < 4 ? 300 : 1000);
           a[RQ] = ld_relaxed_v4(src + RQ);
-          if ((++spins & 0xFFFu) == 0u && (spins > (1u << 22) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
+          if ((++spins & 0xFFu) == 0u && (spins > (1u << 21) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
             atomicExch(errflag, 1);
             break;
           }
@@ -240,8 +245,24 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
       }
       __syncthreads();
     }
-    // ---- the predecessor block is the critical dependency: its dominance pattern does not depend on its ranks, so it
-    // is evaluated into a bitmask BEFORE its ranks are awaited; afterwards only a predicated max over 128 ranks remains
+    // ---- in-block resolution, part 1 (before the predecessor's ranks are needed):
+    //   Rb_i = max_a (bulk_a + D[a][i]) folds the contributions of all blocks < b-1 through the in-block paths.
+    sh_r1[tid] = best;
+    __syncthreads();
+    int r = best;
+#pragma unroll 4
+    for (int a2 = 0; a2 < T; ++a2) {
+      const int dl = (int)sD[a2 * DLD + tid];
+      r = (dl >= 0) ? max(r, sh_r1[a2] + dl) : r;
+    }
+    __syncthreads();
+
+    // ---- the predecessor block is the critical dependency.  Everything that does not depend on its ranks is done
+    // first: its dominance pattern (pmask) and, from it, the table  E[s][i] = longest in-block continuation of a chain that
+    // enters this block from predecessor point s and ends at i  (E = max_{a : s dominates a} D[a][i], SENT if none).
+    // Once the ranks r1_s = rank_s + 1 arrive the resolution is a single max-plus product
+    //     rank_i = max(Rb_i, max_s (r1_s + E[s][i])),
+    // i.e. the critical path per block is: poll -> one barrier -> 128 independent loads / adds / maxes -> publish.
     if (b > 0) {
       const int k = b - 1;
       {
@@ -250,20 +271,36 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
         for (int q = 0; q < NV; ++q) tile[tid * NV + q] = src[tid * NV + q];  // static words only (ids, group)
       }
       __syncthreads();
-      uint32_t pmask[NW];
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
         uint32_t mm = 0u;
 #pragma unroll 8
-        for (int s = 0; s < 32; ++s) {
-          const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s) * NV]);
+        for (int s2 = 0; s2 < 32; ++s2) {
+          const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s2) * NV]);
           bool dom = (sp[M - 1] != gidv);
 #pragma unroll
           for (int j = 0; j < M - 1; ++j) dom = dom && (sp[j] <= v[j]);
-          mm |= (dom ? 1u : 0u) << s;
+          mm |= (dom ? 1u : 0u) << s2;
         }
-        pmask[w] = mm;
+        sh_pmask[tid * NW + w] = mm;
       }
+      for (int s2 = 0; s2 < T; ++s2) sE[s2 * DLD + tid] = (int8_t)SENT;  // own column
+      __syncthreads();
+      for (int a2 = 0; a2 <= tid; ++a2) {  // in-block ancestors of i (a2 == tid: the point itself, D = 0)
+        const int dl = (int)sD[a2 * DLD + tid];
+        if (dl < 0) continue;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          uint32_t mm = sh_pmask[a2 * NW + w];
+          while (mm) {
+            const int s2 = __ffs(mm) - 1;
+            mm &= mm - 1;
+            int8_t* e = &sE[(w * 32 + s2) * DLD + tid];
+            if ((int)*e < dl) *e = (int8_t)dl;
+          }
+        }
+      }
+      // ---- critical section starts here
       {
         const uint32_t* rw = rec + ((int64_t)k * T + tid) * W + M;
         uint32_t r1 = ld_relaxed_u32(rw);
@@ -278,29 +315,18 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
         sh_r1[tid] = (int)r1;
       }
       __syncthreads();
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const uint32_t mm = pmask[w];
+      int r_a = r, r_b = 0, r_c = 0, r_d = 0;  // four independent max chains
 #pragma unroll 2
-        for (int s4 = 0; s4 < 8; ++s4) {
-          const int4 rr = *reinterpret_cast<const int4*>(&sh_r1[w * 32 + s4 * 4]);
-          best = ((mm >> (s4 * 4 + 0)) & 1u) ? max(best, rr.x) : best;
-          best = ((mm >> (s4 * 4 + 1)) & 1u) ? max(best, rr.y) : best;
-          best = ((mm >> (s4 * 4 + 2)) & 1u) ? max(best, rr.z) : best;
-          best = ((mm >> (s4 * 4 + 3)) & 1u) ? max(best, rr.w) : best;
-        }
+      for (int s2 = 0; s2 < T; s2 += 4) {
+        const int4 rr = *reinterpret_cast<const int4*>(&sh_r1[s2]);
+        const int e0 = (int)sE[(s2 + 0) * DLD + tid], e1 = (int)sE[(s2 + 1) * DLD + tid];
+        const int e2 = (int)sE[(s2 + 2) * DLD + tid], e3 = (int)sE[(s2 + 3) * DLD + tid];
+        r_a = (e0 >= 0) ? max(r_a, rr.x + e0) : r_a;
+        r_b = (e1 >= 0) ? max(r_b, rr.y + e1) : r_b;
+        r_c = (e2 >= 0) ? max(r_c, rr.z + e2) : r_c;
+        r_d = (e3 >= 0) ? max(r_d, rr.w + e3) : r_d;
       }
-      __syncthreads();
-    }
-
-    // ---- in-block resolution: one max-plus product over the possible in-block ancestors
-    sh_r1[tid] = best;
-    __syncthreads();
-    int r = best;
-#pragma unroll 4
-    for (int a2 = 0; a2 < T; ++a2) {
-      const int dl = (int)sD[a2 * DLD + tid];
-      r = (dl >= 0) ? max(r, sh_r1[a2] + dl) : r;  // SENT = not an ancestor
+      r = max(max(r_a, r_b), max(r_c, r_d));
     }
     st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: the rank word doubles as the ready flag
     rankS[i] = r;
