@@ -202,6 +202,47 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     }
     __syncthreads();
 
+    // ---- predecessor tables (static data only), computed up front so that they are off the critical path
+    if (b > 0) {
+      const int k = b - 1;
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)k * T * W);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) tile[tid * NV + q] = src[tid * NV + q];  // static words only (ids, group)
+      }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        uint32_t mm = 0u;
+#pragma unroll 8
+        for (int s2 = 0; s2 < 32; ++s2) {
+          const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s2) * NV]);
+          bool dom = (sp[M - 1] != gidv);
+#pragma unroll
+          for (int j = 0; j < M - 1; ++j) dom = dom && (sp[j] <= v[j]);
+          mm |= (dom ? 1u : 0u) << s2;
+        }
+        sh_pmask[tid * NW + w] = mm;
+      }
+      for (int s2 = 0; s2 < T; ++s2) sE[s2 * DLD + tid] = (int8_t)SENT;  // own column
+      __syncthreads();
+      for (int a2 = 0; a2 <= tid; ++a2) {  // in-block ancestors of i (a2 == tid: the point itself, D = 0)
+        const int dl = (int)sD[a2 * DLD + tid];
+        if (dl < 0) continue;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          uint32_t mm = sh_pmask[a2 * NW + w];
+          while (mm) {
+            const int s2 = __ffs(mm) - 1;
+            mm &= mm - 1;
+            int8_t* e = &sE[(w * 32 + s2) * DLD + tid];
+            if ((int)*e < dl) *e = (int8_t)dl;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
     // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
     int best = 0;
     for (int k = 0; k < b - 1; ++k) {
@@ -265,41 +306,6 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     // i.e. the critical path per block is: poll -> one barrier -> 128 independent loads / adds / maxes -> publish.
     if (b > 0) {
       const int k = b - 1;
-      {
-        const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)k * T * W);
-#pragma unroll
-        for (int q = 0; q < NV; ++q) tile[tid * NV + q] = src[tid * NV + q];  // static words only (ids, group)
-      }
-      __syncthreads();
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        uint32_t mm = 0u;
-#pragma unroll 8
-        for (int s2 = 0; s2 < 32; ++s2) {
-          const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s2) * NV]);
-          bool dom = (sp[M - 1] != gidv);
-#pragma unroll
-          for (int j = 0; j < M - 1; ++j) dom = dom && (sp[j] <= v[j]);
-          mm |= (dom ? 1u : 0u) << s2;
-        }
-        sh_pmask[tid * NW + w] = mm;
-      }
-      for (int s2 = 0; s2 < T; ++s2) sE[s2 * DLD + tid] = (int8_t)SENT;  // own column
-      __syncthreads();
-      for (int a2 = 0; a2 <= tid; ++a2) {  // in-block ancestors of i (a2 == tid: the point itself, D = 0)
-        const int dl = (int)sD[a2 * DLD + tid];
-        if (dl < 0) continue;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          uint32_t mm = sh_pmask[a2 * NW + w];
-          while (mm) {
-            const int s2 = __ffs(mm) - 1;
-            mm &= mm - 1;
-            int8_t* e = &sE[(w * 32 + s2) * DLD + tid];
-            if ((int)*e < dl) *e = (int8_t)dl;
-          }
-        }
-      }
       // ---- critical section starts here
       {
         const uint32_t* rw = rec + ((int64_t)k * T + tid) * W + M;
