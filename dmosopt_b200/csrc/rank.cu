@@ -224,20 +224,25 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
         }
         sh_pmask[tid * NW + w] = mm;
       }
-      for (int s2 = 0; s2 < T; ++s2) sE[s2 * DLD + tid] = (int8_t)SENT;  // own column
       __syncthreads();
-      for (int a2 = 0; a2 <= tid; ++a2) {  // in-block ancestors of i (a2 == tid: the point itself, D = 0)
-        const int dl = (int)sD[a2 * DLD + tid];
-        if (dl < 0) continue;
+      // row s of E, left to right (same recurrence as D, seeded by "s dominates i directly"); thread s owns its row,
+      // so no barrier is needed:  E[s][i] = max( s in pmask_i ? 0 : SENT,  max_{j in mask_i} E[s][j] + 1 )
+      {
+        int8_t* row = sE + tid * DLD;
+        const int ws = tid >> 5;
+        const uint32_t bs = 1u << (tid & 31);
+        for (int i2 = 0; i2 < T; ++i2) {
+          int val = (sh_pmask[i2 * NW + ws] & bs) ? 0 : SENT;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          uint32_t mm = sh_pmask[a2 * NW + w];
-          while (mm) {
-            const int s2 = __ffs(mm) - 1;
-            mm &= mm - 1;
-            int8_t* e = &sE[(w * 32 + s2) * DLD + tid];
-            if ((int)*e < dl) *e = (int8_t)dl;
+          for (int w = 0; w < NW; ++w) {
+            uint32_t mm = sh_mask[i2 * NW + w];
+            while (mm) {
+              const int s2 = __ffs(mm) - 1;
+              mm &= mm - 1;
+              val = max(val, (int)row[w * 32 + s2] + 1);
+            }
           }
+          row[i2] = (int8_t)(val >= 0 ? val : SENT);
         }
       }
     }
