@@ -85,9 +85,11 @@ class NSGA2(MOEA):
         """NSGA2.py:84-114."""
         x, y, rank, _ = sortMO(x, y, x_distance_metrics=self.x_distance_metrics, y_distance_metrics=self.y_distance_metrics)
         n = self.opt_params.popsize
-        # same values / dtypes as the reference's slices; the parameter matrix is kept in page-locked memory because it
-        # crosses the PCIe bus twice per generation (generate, update)
-        px = _lib.pinned_like(x[:n])
+        # same values / dtypes as the reference's slices.  The parameter matrix is exposed as a read-only view of a
+        # page-locked array with a device mirror: generate / update then read and write it in HBM and only the
+        # survivors cross the PCIe bus (once, device -> host).  Replacing state.population_parm with an ordinary
+        # array simply turns the mirror off.
+        px, self._pop_base = _lib.mirrored_readonly(x[:n])
         return Struct(
             bounds=bounds,
             population_parm=px,
@@ -128,9 +130,16 @@ class NSGA2(MOEA):
             # children stacked over parents (NSGA2.py:205-206) on the device; survivors land directly in the state array
             code = {None: _lib.METRIC_NONE, "crowding": _lib.METRIC_CROWDING, "euclidean": _lib.METRIC_EUCLIDEAN}[
                 None if self.y_distance_metrics is None else self.y_distance_metrics[0]]
-            out_x = st.population_parm if st.population_parm.dtype == np.float64 and st.population_parm.shape[0] == popsize else None
+            base = getattr(self, "_pop_base", None)
+            if base is not None and (st.population_parm.ctypes.data != base.ctypes.data or st.population_parm.shape != base.shape):
+                base = self._pop_base = None  # the caller replaced the state array
+            out_x = base
+            if out_x is None and st.population_parm.flags.writeable and st.population_parm.dtype == np.float64 and st.population_parm.shape[0] == popsize:
+                out_x = st.population_parm
             population_parm, population_obj, rank, perm = _lib.remove_worst_pair(
                 x_gen, y_gen, st.population_parm, st.population_obj, popsize, code, out_X=out_x)
+            if population_parm is base:
+                population_parm = st.population_parm  # survivors are already in the (mirrored) state array
         else:
             population_parm = np.vstack((x_gen, st.population_parm))
             population_obj = np.vstack((y_gen, st.population_obj))
@@ -145,11 +154,23 @@ class NSGA2(MOEA):
             self.update_population_size()
         else:
             if population_parm is not st.population_parm:
-                st.population_parm[:] = population_parm
+                self._store_population(population_parm)
             st.population_obj[:] = population_obj
             st.rank[:] = rank
         if self.opt_params.adaptive_operator_rates:
             self.update_operator_rates()
+
+    def _store_population(self, new):
+        """Write a new parameter matrix into the state, keeping the device mirror (if any) coherent."""
+        st = self.state
+        base = getattr(self, "_pop_base", None)
+        if base is not None and st.population_parm.ctypes.data == base.ctypes.data and base.shape == new.shape:
+            base[...] = new
+            _lib.mirror_upload(base)
+        elif st.population_parm.flags.writeable and st.population_parm.shape == new.shape:
+            st.population_parm[:] = new
+        else:
+            st.population_parm = np.array(new, dtype=st.population_parm.dtype)
 
     def get_population_strategy(self):
         return self.state.population_parm.copy(), self.state.population_obj.copy()

@@ -252,21 +252,106 @@ def memcpy(dst, src, nbytes):
     _check(load_library().dmo_memcpy(context(), _ptr(dst), _ptr(src), int(nbytes)), "dmo_memcpy")
 
 
+# Page-locked host buffers are pooled: cudaHostAlloc of a population-sized block costs milliseconds, and the plugins
+# hand out one offspring matrix per generation.  A block returns to the pool when the last NumPy view of it dies.
+_pin_pool = {}
+_pin_pool_bytes = 0
+_PIN_POOL_LIMIT = 1 << 30
+# Device mirrors of read-only host arrays the library itself produced (offspring matrix, population state):
+# {host address: (nbytes, DeviceArray)}.  ``_in`` substitutes the device address, so data that was born on the GPU is
+# not shipped back over PCIe when the caller hands it to the next call.  Only non-writeable arrays qualify: a
+# caller who wants to edit must copy, and the copy has no mirror.
+_mirrors = {}
+
+
+def _pin_release(ptr, nbytes):
+    global _pin_pool_bytes
+    _mirrors.pop(ptr, None)
+    lst = _pin_pool.setdefault(nbytes, [])
+    if len(lst) < 4 and _pin_pool_bytes + nbytes <= _PIN_POOL_LIMIT:
+        lst.append(ptr)
+        _pin_pool_bytes += nbytes
+    elif _lib is not None:
+        _lib.dmo_host_free(ptr)
+
+
 def pinned_empty(shape, dtype=np.float64):
-    """NumPy array backed by page-locked host memory (released when the last view is collected)."""
+    """NumPy array backed by page-locked host memory (pooled; recycled when the last view is collected)."""
+    global _pin_pool_bytes
     import weakref
 
     lib = load_library()
     context()
     dt = np.dtype(dtype)
     count = int(np.prod(shape))
-    nbytes = max(count * dt.itemsize, 1)
-    p = _vp()
-    if lib.dmo_host_alloc(ctypes.byref(p), nbytes) != 0:
-        raise DmoError("dmo_host_alloc failed")
-    buf = (ctypes.c_char * nbytes).from_address(p.value)
-    weakref.finalize(buf, lib.dmo_host_free, p.value)
+    nbytes = (max(count * dt.itemsize, 1) + 4095) & ~4095
+    lst = _pin_pool.get(nbytes)
+    if lst:
+        addr = lst.pop()
+        _pin_pool_bytes -= nbytes
+    else:
+        p = _vp()
+        if lib.dmo_host_alloc(ctypes.byref(p), nbytes) != 0:
+            raise DmoError("dmo_host_alloc failed")
+        addr = p.value
+    buf = (ctypes.c_char * nbytes).from_address(addr)
+    weakref.finalize(buf, _pin_release, addr, nbytes)
     return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+
+
+def mirror_register(host, dev):
+    """Declare ``dev`` (DeviceArray) the device copy of the pinned array ``host`` (from pinned_empty)."""
+    _mirrors[host.ctypes.data] = (host.nbytes, dev)
+
+
+def mirror_upload(host):
+    """Refresh the device mirror of ``host`` after a host-side write through its writable base."""
+    ent = _mirrors.get(host.ctypes.data)
+    if ent is not None:
+        ent[1].upload(host)
+
+
+def mirror_ptr(a, require_readonly=True):
+    """Device address mirroring the host array ``a`` (or an interior C-contiguous view of it), else None."""
+    if not _mirrors or not isinstance(a, np.ndarray) or not a.flags.c_contiguous:
+        return None
+    if require_readonly and a.flags.writeable:
+        return None
+    addr = a.ctypes.data
+    ent = _mirrors.get(addr)
+    if ent is not None:
+        return ent[1].ptr if a.nbytes <= ent[0] and ent[1].ptr else None
+    for base, (nbytes, dev) in _mirrors.items():
+        if base <= addr and addr + a.nbytes <= base + nbytes and dev.ptr:
+            return dev.ptr + (addr - base)
+    return None
+
+
+def _in(a):
+    """Pointer for an input array: the device mirror when the library holds one, else the host address."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        m = mirror_ptr(a)
+        return m if m is not None else a.ctypes.data
+    return _ptr(a)
+
+
+def mirrored_readonly(a):
+    """(read-only view, writable pinned base) of a page-locked, device-mirrored copy of ``a``.
+
+    Returns (copy of a, None) when no CUDA context can be created (host-only unit tests)."""
+    a = np.asarray(a)
+    try:
+        base = pinned_empty(a.shape, a.dtype)
+        base[...] = a
+        dev = DeviceArray(a.shape, a.dtype).upload(base)
+    except DmoError:
+        return np.array(a, copy=True), None
+    mirror_register(base, dev)
+    view = base.view()
+    view.flags.writeable = False
+    return view, base
 
 
 def pinned_like(a):
@@ -350,7 +435,8 @@ def remove_worst(X, Y, keep, metric=METRIC_NONE, extra_desc_keys=None):
 def remove_worst_pair(Xa, Ya, Xb, Yb, keep, metric=METRIC_NONE, out_X=None):
     """remove_worst(vstack(Xa, Xb), vstack(Ya, Yb), keep) without the host-side concatenation.
 
-    ``out_X`` (optional, float64 C-contiguous (keep, d)) receives the surviving rows directly; it may be ``Xb`` itself.
+    ``out_X`` (optional, float64 C-contiguous (keep, d)) receives the surviving rows directly; it may be the writable
+    base of ``Xb``.  When ``out_X`` has a device mirror the survivors are written to the mirror and copied out once.
     """
     Xa, Ya, Xb, Yb = _f64(Xa), _f64(Ya), _f64(Xb), _f64(Yb)
     na, d = Xa.shape
@@ -359,14 +445,18 @@ def remove_worst_pair(Xa, Ya, Xb, Yb, keep, metric=METRIC_NONE, out_X=None):
     keep = int(min(keep, na + nb))
     if out_X is not None and (out_X.dtype != np.float64 or not out_X.flags.c_contiguous or out_X.shape != (keep, d)):
         out_X = None
-    Xo = out_X if out_X is not None else np.empty((keep, d), dtype=np.float64)
+    Xo = out_X if out_X is not None else pinned_empty((keep, d), np.float64)
     Yo = np.empty((keep, M), dtype=np.float64)
     rank = np.empty(keep, dtype=np.int32)
     perm = np.empty(keep, dtype=np.int64)
+    xo_dev = mirror_ptr(Xo, require_readonly=False) if out_X is not None else None
     _check(
-        load_library().dmo_remove_worst_pair(context(), _ptr(Xa), _ptr(Ya), na, _ptr(Xb), _ptr(Yb), nb, d, M, metric, keep, _ptr(Xo), _ptr(Yo), _ptr(rank), _ptr(perm)),
+        load_library().dmo_remove_worst_pair(context(), _in(Xa), _in(Ya), na, _in(Xb), _in(Yb), nb, d, M, metric, keep,
+                                             xo_dev if xo_dev is not None else _ptr(Xo), _ptr(Yo), _ptr(rank), _ptr(perm)),
         "dmo_remove_worst_pair",
     )
+    if xo_dev is not None:
+        memcpy(Xo, xo_dev, Xo.nbytes)
     return Xo, Yo, rank.astype(np.intp), perm
 
 
@@ -422,7 +512,8 @@ def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, muta
     pool_idx = np.ascontiguousarray(pool_idx, dtype=np.int64)
     popsize = int(popsize)
     T = 2 * popsize + 64
-    x_gen = np.empty((popsize + 1, d), dtype=np.float64)
+    # the offspring matrix stays on the device as the mirror of the (read-only, page-locked) array handed back
+    x_dev = DeviceArray((popsize + 1, d), np.float64)
     kind = np.empty(popsize + 1, dtype=np.int32)
     nch = np.zeros(1, dtype=np.int64)
     draws = np.empty(T * (5 + 2 * d), dtype=np.float64) if return_draws else None
@@ -431,13 +522,18 @@ def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, muta
     lb, ub = _f64(xlb), _f64(xub)
     _check(
         load_library().dmo_nsga2_generate(
-            context(), _ptr(pop_x), npop, d, _ptr(pool_idx), pool_idx.shape[0], popsize, float(crossover_prob), float(mutation_prob),
+            context(), _in(pop_x), npop, d, _ptr(pool_idx), pool_idx.shape[0], popsize, float(crossover_prob), float(mutation_prob),
             float(mutation_rate), _ptr(dic), _ptr(dim), _ptr(lb), _ptr(ub), int(seed) & (2**64 - 1), int(stream_id),
-            _ptr(x_gen), _ptr(kind), _ptr(nch), _ptr(draws),
+            x_dev.ptr, _ptr(kind), _ptr(nch), _ptr(draws),
         ),
         "dmo_nsga2_generate",
     )
     P = int(nch[0])
+    x_gen = pinned_empty((popsize + 1, d), np.float64)
+    if P:
+        memcpy(x_gen, x_dev.ptr, P * d * 8)
+    mirror_register(x_gen, x_dev)
+    x_gen.flags.writeable = False
     if not return_draws:
         return x_gen[:P], kind[:P]
     dd = {
@@ -483,9 +579,9 @@ class GPHandle:
         if X.ndim == 1:
             X = X.reshape(1, -1)
         P = X.shape[0]
-        mean = np.empty((P, self.M), dtype=np.float64)
-        var = np.empty((P, self.M), dtype=np.float64) if return_var else None
-        _check(load_library().dmo_gp_predict(context(), self._h, _ptr(X), P, _ptr(mean), _ptr(var), int(precision)), "dmo_gp_predict")
+        mean = pinned_empty((P, self.M), np.float64)
+        var = pinned_empty((P, self.M), np.float64) if return_var else None
+        _check(load_library().dmo_gp_predict(context(), self._h, _in(X), P, _ptr(mean), _ptr(var), int(precision)), "dmo_gp_predict")
         return mean, var
 
     def close(self):

@@ -118,8 +118,13 @@ int dmo_device_free(dmo_ctx* ctx, void* p) {
 }
 
 int dmo_memcpy(dmo_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return DMO_ERR_ARG;
+  if (bytes == 0) return DMO_OK;
   DMO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
   DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  const bool sd = dmo_is_device_ptr(src), dd = dmo_is_device_ptr(dst);
+  if (!sd && dd) ctx->h2d_bytes += bytes;
+  if (sd && !dd) ctx->d2h_bytes += bytes;
   return DMO_OK;
 }
 
