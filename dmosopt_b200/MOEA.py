@@ -129,6 +129,10 @@ class MOEA(object):
     def generate(self, **params):
         x, state = self.generate_strategy(**params)
         lb, ub = self.bounds[:, 0], self.bounds[:, 1]
+        if isinstance(x, np.ndarray) and not x.flags.writeable and _lib.mirror_ptr(x) is not None:
+            # offspring produced by the variation kernels are already clamped to these bounds on the device
+            # (variation.cu, same [xlb, xub] as MOEA.py:155); the read-only array keeps its device mirror
+            return x, state
         if isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.writeable:
             return np.clip(x, lb, ub, out=x), state  # same values as MOEA.py:155, without a second 8*P*d byte buffer
         return np.clip(x, lb, ub), state

@@ -107,13 +107,17 @@ int dmo_host_alloc(void** out, uint64_t bytes) {
 int dmo_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? DMO_OK : DMO_ERR_CUDA; }
 
 int dmo_device_alloc(dmo_ctx* ctx, void** out, uint64_t bytes) {
+  // stream-ordered, from the context's pool (release threshold = unlimited): a per-generation buffer costs
+  // microseconds, not a cudaMalloc / cudaFree pair
+  if (!ctx || !out) return DMO_ERR_ARG;
   DMO_CUDA(cudaSetDevice(ctx->device));
-  DMO_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  DMO_CUDA(cudaMallocAsync(out, bytes ? bytes : 1, ctx->stream));
   return DMO_OK;
 }
 int dmo_device_free(dmo_ctx* ctx, void* p) {
-  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
-  DMO_CUDA(cudaFree(p));
+  if (!ctx) return DMO_ERR_ARG;
+  if (!p) return DMO_OK;
+  DMO_CUDA(cudaFreeAsync(p, ctx->stream));
   return DMO_OK;
 }
 

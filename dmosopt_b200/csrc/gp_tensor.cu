@@ -504,17 +504,22 @@ __global__ void split_linv_kernel(const double* __restrict__ Linv, int64_t Npad,
 
 constexpr int KT_TN = 128, KT_TP = 32;
 
+// c * k(r): hardware approximations (sqrt.approx / ex2.approx, relative error ~2^-22 each) are inside the 2^-22 budget
+// the hi + lo fp16 split of K_* has anyway
 __device__ __forceinline__ float stationary_f(float s2, int kind) {
   if (kind == DMO_KERNEL_MATERN52) {
-    const float K = sqrtf(s2) * 2.2360679774997896f;
-    return (1.0f + K + K * K * (1.0f / 3.0f)) * expf(-K);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s2));
+    const float K = r * 2.2360679774997896f;
+    return fmaf(K, fmaf(K, 1.0f / 3.0f, 1.0f), 1.0f) * __expf(-K);
   }
-  return expf(-0.5f * s2);
+  return __expf(-0.5f * s2);
 }
 
 // K_* in fp32 -> scaled fp16 hi / lo.  Each thread owns two adjacent training points (their coordinates live in
 // registers, results leave as packed half2), a block covers 256 training points x KT_TP candidates; the candidate
-// tile is read from shared memory as broadcasts.
+// tile is read from shared memory as 16-byte broadcasts (rows padded with zeros to DMAX coordinates, so the
+// distance loops need no bounds tests and the LSU pipe carries a quarter of the instructions of scalar loads).
 template <bool ISO, int DMAX>
 __global__ void __launch_bounds__(KT_TN)
     kstar_tensor_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, int64_t Pcpad,
@@ -522,16 +527,20 @@ __global__ void __launch_bounds__(KT_TN)
                         const double* __restrict__ inv_ls, const double* __restrict__ constant,
                         const int* __restrict__ k_exp, int64_t ldk, int64_t plane, uint16_t* __restrict__ Kh,
                         uint16_t* __restrict__ Kl) {
-  extern __shared__ float sxf[];  // [KT_TP][d] candidate tile, then [4][d] 1/l, [4] c * 2^kexp
-  float* s_il = sxf + KT_TP * d;
-  float* s_c = s_il + 4 * d;
+  extern __shared__ __align__(16) float sxf[];  // [KT_TP][DMAX] candidate tile, then [4][DMAX] 1/l, [4] c * 2^kexp
+  float* s_il = sxf + KT_TP * DMAX;
+  float* s_c = s_il + 4 * DMAX;
   const int64_t n0 = ((int64_t)blockIdx.x * KT_TN + threadIdx.x) * 2;
   const int64_t pt0 = (int64_t)blockIdx.y * KT_TP;
-  for (int t = threadIdx.x; t < KT_TP * d; t += KT_TN) {
-    int64_t p = p_base + pt0 + t / d;
-    sxf[t] = (p < P) ? (float)Xn[p * d + (t % d)] : 0.f;
+  for (int t = threadIdx.x; t < KT_TP * DMAX; t += KT_TN) {
+    const int64_t p = p_base + pt0 + t / DMAX;
+    const int j = t % DMAX;
+    sxf[t] = (p < P && j < d) ? (float)Xn[p * d + j] : 0.f;
   }
-  for (int t = threadIdx.x; t < M * d; t += KT_TN) s_il[t] = (float)inv_ls[t];
+  for (int t = threadIdx.x; t < M * DMAX; t += KT_TN) {
+    const int m = t / DMAX, j = t % DMAX;
+    s_il[t] = j < d ? (float)inv_ls[m * d + j] : 0.f;
+  }
   if (threadIdx.x < M) s_c[threadIdx.x] = scalbnf((float)constant[threadIdx.x], k_exp[threadIdx.x]);
   float xa[DMAX], xb[DMAX];
 #pragma unroll
@@ -547,34 +556,54 @@ __global__ void __launch_bounds__(KT_TN)
   for (int q = 0; q < KT_TP; ++q) {
     const int64_t pl = pt0 + q;
     if (pl >= Pcpad) break;
-    const float* xc = sxf + q * d;
+    const float4* xc = reinterpret_cast<const float4*>(sxf + q * DMAX);
     float sa = 0.f, sb = 0.f;
     if (ISO) {
+      float sa1 = 0.f, sb1 = 0.f;  // two accumulators per point: shorter dependent chains
 #pragma unroll
-      for (int j = 0; j < DMAX; ++j)
-        if (j < d) {
-          const float c = xc[j];
-          const float da = c - xa[j], db = c - xb[j];
-          sa = fmaf(da, da, sa);
-          sb = fmaf(db, db, sb);
-        }
+      for (int j = 0; j < DMAX / 4; ++j) {
+        const float4 c = xc[j];
+        float da = c.x - xa[4 * j], db = c.x - xb[4 * j];
+        sa = fmaf(da, da, sa);
+        sb = fmaf(db, db, sb);
+        da = c.y - xa[4 * j + 1], db = c.y - xb[4 * j + 1];
+        sa1 = fmaf(da, da, sa1);
+        sb1 = fmaf(db, db, sb1);
+        da = c.z - xa[4 * j + 2], db = c.z - xb[4 * j + 2];
+        sa = fmaf(da, da, sa);
+        sb = fmaf(db, db, sb);
+        da = c.w - xa[4 * j + 3], db = c.w - xb[4 * j + 3];
+        sa1 = fmaf(da, da, sa1);
+        sb1 = fmaf(db, db, sb1);
+      }
+      sa += sa1;
+      sb += sb1;
     }
     for (int m = 0; m < M; ++m) {
       float ra, rb;
       if (ISO) {
-        const float il = s_il[m * d];
+        const float il = s_il[m * DMAX];
         ra = sa * il * il;
         rb = sb * il * il;
       } else {
         ra = rb = 0.f;
+        const float4* il4 = reinterpret_cast<const float4*>(s_il + m * DMAX);
 #pragma unroll
-        for (int j = 0; j < DMAX; ++j)
-          if (j < d) {
-            const float c = xc[j], il = s_il[m * d + j];
-            const float da = (c - xa[j]) * il, db = (c - xb[j]) * il;
-            ra = fmaf(da, da, ra);
-            rb = fmaf(db, db, rb);
-          }
+        for (int j = 0; j < DMAX / 4; ++j) {
+          const float4 c = xc[j], il = il4[j];
+          float da = (c.x - xa[4 * j]) * il.x, db = (c.x - xb[4 * j]) * il.x;
+          ra = fmaf(da, da, ra);
+          rb = fmaf(db, db, rb);
+          da = (c.y - xa[4 * j + 1]) * il.y, db = (c.y - xb[4 * j + 1]) * il.y;
+          ra = fmaf(da, da, ra);
+          rb = fmaf(db, db, rb);
+          da = (c.z - xa[4 * j + 2]) * il.z, db = (c.z - xb[4 * j + 2]) * il.z;
+          ra = fmaf(da, da, ra);
+          rb = fmaf(db, db, rb);
+          da = (c.w - xa[4 * j + 3]) * il.w, db = (c.w - xb[4 * j + 3]) * il.w;
+          ra = fmaf(da, da, ra);
+          rb = fmaf(db, db, rb);
+        }
       }
       const float ka = live_a ? s_c[m] * stationary_f(ra, kind) : 0.f;  // c * k(r), scaled by 2^kexp (exact)
       const float kb = live_b ? s_c[m] * stationary_f(rb, kind) : 0.f;
@@ -687,6 +716,7 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   const int64_t N = gp->N, Npad = gp->Npad;
   const int M = gp->M, d = gp->d;
   DMO_REQUIRE(M <= 4, "gp_predict(tensor): at most 4 objectives per model (got %d)", M);
+  DMO_REQUIRE(d <= 64, "gp_predict(tensor): at most 64 input dimensions (got %d); use DMO_GP_FP64", d);
   DMO_REQUIRE(Npad % TN == 0, "gp_predict(tensor): internal padding error");
   DMO_TRY(prepare_tensor_state(ctx, gp));
   // candidate chunk: K_* hi/lo (2 x M x Pc x Npad fp16) within ~6 GiB
@@ -729,7 +759,8 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
     {
       ProfileScope ps(ctx, "gp_kstar");
       dim3 gk((unsigned)(Npad / (2 * KT_TN)), (unsigned)ceil_div(Pcpad, KT_TP));
-      size_t smem = (size_t)(KT_TP * d + 4 * d + 4) * sizeof(float);
+      const int dmax = d <= 32 ? 32 : 64;
+      size_t smem = (size_t)(KT_TP * dmax + 4 * dmax + 4) * sizeof(float);
 #define KSTAR_LAUNCH(ISO_, DM_)                                                                                      \
   DMO_LAUNCH((kstar_tensor_kernel<ISO_, DM_>), gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel, \
              gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p)

@@ -21,6 +21,9 @@
 // see DESIGN.md).
 #include <stdlib.h>
 
+#include <cstdio>
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -115,21 +118,89 @@ __device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c ==
 
 // The rank word of a record (rank + 1, 0 = not yet final) is its own ready flag: a 4-byte store is atomic and carries
 // no other data, so publication needs neither fences nor a separate flag, and consumers simply poll the word.
+// Breadth-first walk by path length from the node set `f` (level `level`): table[i * DLD + col] = last level at which
+// i is reached = longest path.  Each thread walks its own source; the frontier is a 128-bit set in registers.
+template <int T, int DLD>
+__device__ __forceinline__ void frontier_fill(int8_t* table, const uint4* succ, uint4 f, int col, int level) {
+  static_assert(T == 128, "frontier sets are 128 bits wide");
+  while ((f.x | f.y | f.z | f.w) != 0u) {
+    uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+#define DMO_WALK(word, base)                           \
+  for (uint32_t mm = (word); mm != 0u; mm &= mm - 1u) { \
+    const int i = (base) + __ffs(mm) - 1;               \
+    table[i * DLD + col] = (int8_t)level;               \
+    const uint4 sc = succ[i];                           \
+    nx.x |= sc.x;                                       \
+    nx.y |= sc.y;                                       \
+    nx.z |= sc.z;                                       \
+    nx.w |= sc.w;                                       \
+  }
+    DMO_WALK(f.x, 0)
+    DMO_WALK(f.y, 32)
+    DMO_WALK(f.z, 64)
+    DMO_WALK(f.w, 96)
+#undef DMO_WALK
+    f = nx;
+    ++level;
+  }
+}
+
+// max(init, max_a (vals16[a] + row[a])) over one table row of T int8 path lengths (SENT = -128 = "no path"), two
+// 16-bit lanes per instruction: PRMT + AND expand a byte pair to int16 (SENT becomes -32768, so SENT + value < 0 never
+// wins against init >= 0), VIADDMNMX.S16x2 does the add and the max.  Requires 0 <= vals16, init <= 32127.
+template <int T>
+__device__ __forceinline__ int maxplus_packed(const int8_t* row, const int16_t* vals16, int init) {
+  const uint4* dr = reinterpret_cast<const uint4*>(row);
+  const uint4* vr = reinterpret_cast<const uint4*>(vals16);
+  unsigned acc0 = ((unsigned)init & 0xFFFFu) * 0x00010001u, acc1 = acc0;
+#define DMO_EXP_LO(w) (__byte_perm((w), 0u, 0x1100) & 0x807F807Fu)
+#define DMO_EXP_HI(w) (__byte_perm((w), 0u, 0x3322) & 0x807F807Fu)
+#pragma unroll
+  for (int c = 0; c < T / 16; ++c) {
+    const uint4 dv = dr[c];
+    const uint4 v0 = vr[2 * c], v1 = vr[2 * c + 1];
+    acc0 = __viaddmax_s16x2(DMO_EXP_LO(dv.x), v0.x, acc0);
+    acc1 = __viaddmax_s16x2(DMO_EXP_HI(dv.x), v0.y, acc1);
+    acc0 = __viaddmax_s16x2(DMO_EXP_LO(dv.y), v0.z, acc0);
+    acc1 = __viaddmax_s16x2(DMO_EXP_HI(dv.y), v0.w, acc1);
+    acc0 = __viaddmax_s16x2(DMO_EXP_LO(dv.z), v1.x, acc0);
+    acc1 = __viaddmax_s16x2(DMO_EXP_HI(dv.z), v1.y, acc1);
+    acc0 = __viaddmax_s16x2(DMO_EXP_LO(dv.w), v1.z, acc0);
+    acc1 = __viaddmax_s16x2(DMO_EXP_HI(dv.w), v1.w, acc1);
+  }
+#undef DMO_EXP_LO
+#undef DMO_EXP_HI
+  const unsigned m = __vmaxs2(acc0, acc1);
+  return max((int)(int16_t)(m & 0xFFFFu), (int)(int16_t)(m >> 16));
+}
+
 template <int M, int T>
 __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
-                                                       int* errflag) {
+                                                       int* errflag, long long* trace) {
+  // optional per-block time stamps (DMO_RANK_TRACE=<file>): 8 x globaltimer ns, then 8 x clock64, see scripts/rank_trace.py
+#define RANK_TRACE(slot)                                                         \
+  if (trace != nullptr && tid == 0) {                                            \
+    long long gt_;                                                               \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                     \
+    trace[(int64_t)b * 16 + (slot)] = gt_;                                       \
+    trace[(int64_t)b * 16 + 8 + (slot)] = clock64();                             \
+  }
   constexpr int W = 4 * ((M + 1 + 3) / 4);
   constexpr int NV = W / 4;
   constexpr int NW = T / 32;
   constexpr int RQ = M / 4, RC = M % 4;  // uint4 / component holding the rank word
-  constexpr int DLD = T + 4;  // row stride of the path-length table in bytes: (a*33 + j/4) mod 32 -> conflict free
+  // Path-length tables are stored TRANSPOSED, [destination i][source], row stride T + 16 bytes: the thread that owns
+  // destination i reads its whole row with 16-byte loads (stride 36 words -> the 8 threads of a quarter warp hit 8
+  // distinct 4-word groups, conflict free), while the threads that fill the tables walk columns (consecutive bytes).
+  constexpr int DLD = T + 16;
   constexpr int SENT = -128;  // "no in-block path"; real path lengths are 0 .. T-1 <= 127
+  constexpr int PACK_LIMIT = 32000;  // ranks up to here take the packed 16-bit max-plus path
   __shared__ uint4 tile[T * NV];
   __shared__ __align__(16) int sh_r1[T];
-  __shared__ uint32_t sh_mask[T * NW];
-  __shared__ int8_t sD[T * DLD];
-  __shared__ int8_t sE[T * DLD];
-  __shared__ uint32_t sh_pmask[T * NW];
+  __shared__ __align__(16) int16_t sh_h16[T];
+  __shared__ uint4 sh_succ[T];
+  __shared__ __align__(16) int8_t sD[T * DLD];
+  __shared__ __align__(16) int8_t sE[T * DLD];
   __shared__ int sh_blk;
 
   const int tid = threadIdx.x;
@@ -141,6 +212,12 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     __syncthreads();
     if (b >= nblocks) return;
     const int64_t i = (int64_t)b * T + tid;
+    RANK_TRACE(0);
+    if (trace != nullptr && tid == 0) {
+      unsigned smid_;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+      trace[(int64_t)b * 16 + 7] = smid_;
+    }
 
     // ---- own record -> registers and shared tile
     uint32_t v[W];
@@ -159,98 +236,80 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     const uint32_t gidv = v[M - 1];
     __syncthreads();
 
-    // ---- in-block dominator bitmask (sources earlier in the block); independent of any rank
-    uint32_t mask[NW];
+    // ---- in-block successor bitmasks: succ[j] = { i > j in this block : j dominates i }; independent of any rank
+    {
+      uint32_t sm[NW];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      uint32_t m = 0u;
+      for (int w = 0; w < NW; ++w) {
+        uint32_t m = 0u;
 #pragma unroll 8
-      for (int s = 0; s < 32; ++s) {
-        const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s) * NV]);
-        bool dom = (w * 32 + s < tid) && (sp[M - 1] != gidv);
+        for (int s = 0; s < 32; ++s) {
+          const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s) * NV]);
+          bool dom = (w * 32 + s > tid) && (sp[M - 1] != gidv);
 #pragma unroll
-        for (int j = 0; j < M - 1; ++j) dom = dom && (sp[j] <= v[j]);
-        m |= (dom ? 1u : 0u) << s;
+          for (int j = 0; j < M - 1; ++j) dom = dom && (v[j] <= sp[j]);
+          m |= (dom ? 1u : 0u) << s;
+        }
+        sm[w] = m;
       }
-      mask[w] = m;
-      sh_mask[tid * NW + w] = m;
+      static_assert(NW == 4, "successor masks are stored as one uint4 per node");
+      sh_succ[tid] = make_uint4(sm[0], sm[1], sm[2], sm[3]);
+      // both path-length tables start as "no path"
+      const uint4 fill = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+      for (int t = tid; t < T * DLD / 16; t += T) {
+        reinterpret_cast<uint4*>(sD)[t] = fill;
+        reinterpret_cast<uint4*>(sE)[t] = fill;
+      }
     }
     __syncthreads();
 
     // ---- in-block longest-path table, computed BEFORE any rank is needed (off the critical path):
     // D[a][i] = number of edges of the longest in-block domination chain a -> ... -> i (SENT if none, 0 for i == a).
-    // Thread a fills row a left to right; entry i only needs mask_i (shared) and earlier entries of the same row, so
-    // the 128 rows are independent and no barrier is needed.  With it, the in-block resolution collapses to one
-    // max-plus product  rank_i = max_a (best_a + D[a][i])  instead of a data-dependent number of rounds.
-    {
-      int8_t* row = sD + tid * DLD;
-      for (int i2 = 0; i2 < T; ++i2) row[i2] = (int8_t)((i2 == tid) ? 0 : SENT);
-      for (int i2 = tid + 1; i2 < T; ++i2) {
-        int val = SENT;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          uint32_t mm = sh_mask[i2 * NW + w];
-          if (w * 32 + 31 < tid) mm = 0u;  // sources before a cannot be reached from a
-          while (mm) {
-            const int s = __ffs(mm) - 1;
-            mm &= mm - 1;
-            val = max(val, (int)row[w * 32 + s] + 1);
-          }
-        }
-        row[i2] = (int8_t)(val > 0 ? val : SENT);  // unreachable sources only contribute SENT + 1 < 0
-      }
-    }
-    __syncthreads();
+    // Thread a walks the DAG breadth first by path length: F_l = nodes reached from a by a path of exactly l edges,
+    // F_{l+1} = union of succ[i] over i in F_l; the last level that contains i is the longest path (later writes win).
+    // With it the in-block resolution is one max-plus product  rank_i = max_a (best_a + D[a][i]).
+    frontier_fill<T, DLD>(sD, sh_succ, sh_succ[tid], tid, 1);
+    sD[tid * DLD + tid] = 0;
 
-    // ---- predecessor tables (static data only), computed up front so that they are off the critical path
+    // ---- predecessor table: E[s][i] = longest in-block continuation of a chain that enters this block from point s of
+    // block b-1 (0 if s dominates i directly).  Same walk, seeded with the block nodes s dominates, level 0.
     if (b > 0) {
-      const int k = b - 1;
+      const int64_t ps = (int64_t)(b - 1) * T + tid;
+      uint32_t pv[W];
       {
-        const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)k * T * W);
+        const uint4* src = reinterpret_cast<const uint4*>(rec + ps * W);
 #pragma unroll
-        for (int q = 0; q < NV; ++q) tile[tid * NV + q] = src[tid * NV + q];  // static words only (ids, group)
+        for (int q = 0; q < NV; ++q) {
+          uint4 a4 = src[q];  // static words only (ids, group); the rank word is read later with ld.relaxed
+          pv[4 * q + 0] = a4.x;
+          pv[4 * q + 1] = a4.y;
+          pv[4 * q + 2] = a4.z;
+          pv[4 * q + 3] = a4.w;
+        }
       }
-      __syncthreads();
+      uint32_t pm[NW];
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
-        uint32_t mm = 0u;
+        uint32_t m = 0u;
 #pragma unroll 8
         for (int s2 = 0; s2 < 32; ++s2) {
           const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile[(w * 32 + s2) * NV]);
-          bool dom = (sp[M - 1] != gidv);
+          bool dom = (sp[M - 1] != pv[M - 1]);
 #pragma unroll
-          for (int j = 0; j < M - 1; ++j) dom = dom && (sp[j] <= v[j]);
-          mm |= (dom ? 1u : 0u) << s2;
+          for (int j = 0; j < M - 1; ++j) dom = dom && (pv[j] <= sp[j]);
+          m |= (dom ? 1u : 0u) << s2;
         }
-        sh_pmask[tid * NW + w] = mm;
+        pm[w] = m;
       }
-      __syncthreads();
-      // row s of E, left to right (same recurrence as D, seeded by "s dominates i directly"); thread s owns its row,
-      // so no barrier is needed:  E[s][i] = max( s in pmask_i ? 0 : SENT,  max_{j in mask_i} E[s][j] + 1 )
-      {
-        int8_t* row = sE + tid * DLD;
-        const int ws = tid >> 5;
-        const uint32_t bs = 1u << (tid & 31);
-        for (int i2 = 0; i2 < T; ++i2) {
-          int val = (sh_pmask[i2 * NW + ws] & bs) ? 0 : SENT;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) {
-            uint32_t mm = sh_mask[i2 * NW + w];
-            while (mm) {
-              const int s2 = __ffs(mm) - 1;
-              mm &= mm - 1;
-              val = max(val, (int)row[w * 32 + s2] + 1);
-            }
-          }
-          row[i2] = (int8_t)(val >= 0 ? val : SENT);
-        }
-      }
+      frontier_fill<T, DLD>(sE, sh_succ, make_uint4(pm[0], pm[1], pm[2], pm[3]), tid, 0);
     }
     __syncthreads();
 
     // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
+    RANK_TRACE(1);
     int best = 0;
     for (int k = 0; k < b - 1; ++k) {
+      if (k == b - 2) RANK_TRACE(2);
       {
         const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
         uint4 a[NV];
@@ -272,6 +331,7 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
         for (int q = 0; q < NV; ++q) tile[tid * NV + q] = a[q];
       }
       __syncthreads();
+      if (k == b - 2) RANK_TRACE(3);
 #pragma unroll 8
       for (int s = 0; s < T; ++s) {
         uint32_t sw[W];
@@ -293,13 +353,18 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     }
     // ---- in-block resolution, part 1 (before the predecessor's ranks are needed):
     //   Rb_i = max_a (bulk_a + D[a][i]) folds the contributions of all blocks < b-1 through the in-block paths.
-    sh_r1[tid] = best;
-    __syncthreads();
     int r = best;
-#pragma unroll 4
-    for (int a2 = 0; a2 < T; ++a2) {
-      const int dl = (int)sD[a2 * DLD + tid];
-      r = (dl >= 0) ? max(r, sh_r1[a2] + dl) : r;
+    if (!__syncthreads_or(best > PACK_LIMIT)) {
+      sh_h16[tid] = (int16_t)best;
+      __syncthreads();
+      r = maxplus_packed<T>(sD + tid * DLD, sh_h16, best);
+    } else {  // more than 32000 fronts: plain 32-bit max-plus over the same table
+      sh_r1[tid] = best;
+      __syncthreads();
+      for (int a2 = 0; a2 < T; ++a2) {
+        const int dl = (int)sD[tid * DLD + a2];
+        r = (dl >= 0) ? max(r, sh_r1[a2] + dl) : r;
+      }
     }
     __syncthreads();
 
@@ -312,6 +377,8 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     if (b > 0) {
       const int k = b - 1;
       // ---- critical section starts here
+      RANK_TRACE(4);
+      bool big;
       {
         const uint32_t* rw = rec + ((int64_t)k * T + tid) * W + M;
         uint32_t r1 = ld_relaxed_u32(rw);
@@ -324,25 +391,26 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
           }
         }
         sh_r1[tid] = (int)r1;
+        sh_h16[tid] = (int16_t)r1;
+        big = (int)r1 > PACK_LIMIT || r > PACK_LIMIT;
       }
-      __syncthreads();
-      int r_a = r, r_b = 0, r_c = 0, r_d = 0;  // four independent max chains
-#pragma unroll 2
-      for (int s2 = 0; s2 < T; s2 += 4) {
-        const int4 rr = *reinterpret_cast<const int4*>(&sh_r1[s2]);
-        const int e0 = (int)sE[(s2 + 0) * DLD + tid], e1 = (int)sE[(s2 + 1) * DLD + tid];
-        const int e2 = (int)sE[(s2 + 2) * DLD + tid], e3 = (int)sE[(s2 + 3) * DLD + tid];
-        r_a = (e0 >= 0) ? max(r_a, rr.x + e0) : r_a;
-        r_b = (e1 >= 0) ? max(r_b, rr.y + e1) : r_b;
-        r_c = (e2 >= 0) ? max(r_c, rr.z + e2) : r_c;
-        r_d = (e3 >= 0) ? max(r_d, rr.w + e3) : r_d;
+      const int any_big = __syncthreads_or(big ? 1 : 0);
+      RANK_TRACE(5);
+      if (!any_big) {
+        r = maxplus_packed<T>(sE + tid * DLD, sh_h16, r);
+      } else {
+        for (int s2 = 0; s2 < T; ++s2) {
+          const int e = (int)sE[tid * DLD + s2];
+          r = (e >= 0) ? max(r, sh_r1[s2] + e) : r;
+        }
       }
-      r = max(max(r_a, r_b), max(r_c, r_d));
     }
     st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: the rank word doubles as the ready flag
     rankS[i] = r;
+    RANK_TRACE(6);
     __syncthreads();
   }
+#undef RANK_TRACE
 }
 
 // Rank-0 test only (filter for the hypervolume / EHVI routines): "is some point dominating me" has no dependency chain,
@@ -419,6 +487,13 @@ __global__ void copy_u32_to_i32_kernel(const uint32_t* __restrict__ a, int64_t n
 
 template <int M>
 int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* ticket, int* errflag) {
+  // debugging aid: DMO_RANK_TRACE=<file> dumps 16 int64 time stamps per block of the chain kernel
+  DevBuf<long long> trace;
+  const char* trace_path = getenv("DMO_RANK_TRACE");
+  if (trace_path && *trace_path) {
+    DMO_TRY(trace.alloc(ctx, (size_t)nblocks * 16));
+    DMO_CUDA(cudaMemsetAsync(trace.p, 0, (size_t)nblocks * 16 * sizeof(long long), ctx->stream));
+  }
   int occ = 0;
   DMO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_chain_kernel<M, RANK_T>, RANK_T, 0));
   if (occ < 1) occ = 1;
@@ -428,9 +503,20 @@ int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* tick
   if (const char* e = getenv("DMO_RANK_OCC")) cap = atoi(e);
   if (cap >= 1 && occ > cap) occ = cap;
   int grid = nblocks < occ * ctx->sm_count ? nblocks : occ * ctx->sm_count;
-  ProfileScope ps(ctx, "rank_chain");
-  DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), grid, RANK_T, 0, rec, nblocks, rankS, ticket, errflag);
-  DMO_CHECK_LAUNCH();
+  {
+    ProfileScope ps(ctx, "rank_chain");
+    DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), grid, RANK_T, 0, rec, nblocks, rankS, ticket, errflag, trace.p);
+    DMO_CHECK_LAUNCH();
+  }
+  if (trace.p) {
+    std::vector<long long> h((size_t)nblocks * 16);
+    DMO_CUDA(cudaMemcpyAsync(h.data(), trace.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (FILE* f = fopen(trace_path, "wb")) {
+      fwrite(h.data(), sizeof(long long), h.size(), f);
+      fclose(f);
+    }
+  }
   return DMO_OK;
 }
 

@@ -56,6 +56,18 @@ def test_rank_edge_cases(L):
     perm = rng.permutation(n)
     Y = np.column_stack((base, base * 2.0, base + 0.5))[perm]
     assert np.array_equal(L.rank_nd(Y), perm)
+    # more than 32000 fronts: ranks leave the packed 16-bit max-plus path of the chain kernel (32-bit fallback), and a
+    # mixed case where only the later blocks do
+    n = 40000
+    base = np.arange(n, dtype=np.float64)
+    perm = rng.permutation(n)
+    assert np.array_equal(L.rank_nd(np.column_stack((base, base))[perm]), perm)
+    n = 33000
+    base = np.arange(n, dtype=np.float64)
+    Y = np.vstack((np.column_stack((base, base)), rng.random((1500, 2)) * n))
+    rk = L.rank_nd(Y)
+    assert np.array_equal(rk[:n], np.arange(n))
+    assert np.array_equal(rk, dda.rank_chain_dp(Y))
     # heavy ties (integer grid) and negative / signed-zero values
     Y = rng.integers(-2, 3, size=(800, 3)).astype(np.float64)
     Y[Y == 0] = -0.0
