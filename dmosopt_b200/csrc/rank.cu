@@ -118,6 +118,120 @@ __device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c ==
 
 // The rank word of a record (rank + 1, 0 = not yet final) is its own ready flag: a 4-byte store is atomic and carries
 // no other data, so publication needs neither fences nor a separate flag, and consumers simply poll the word.
+// ------------------------------------------------------------------------------------------------ cell index (M <= 3)
+// For two and three objectives the records carry one or two compare words (the first objective is implied by the
+// lexicographic order).  A RANK_G x RANK_G grid over those words turns most of the "all earlier blocks" scan into one
+// table lookup: every finalised point in a cell strictly below a target's cell in both words dominates it, so the
+// maximum rank over those cells (a 2-D prefix maximum of the per-cell maxima) is a valid contribution; only the
+// points in the target's own cell row / column need the exact pair test.  (M == 2 uses the diagonal cells (a, a).)
+constexpr int RANK_G = 512;
+constexpr int RANK_GBITS = 9;
+constexpr int RANK_BLD = RANK_G + 1;  // row stride of the (1-based) Fenwick tree
+
+struct RankGrid {
+  // two cell-ordered copies of the records (static words + rank word): A is row-major over (word 0 cell, word 1 cell),
+  // B is column-major, so that a target's cell row and its cell column are each ONE contiguous range of slots
+  uint4* crecA = nullptr;
+  uint4* crecB = nullptr;
+  const uint32_t* slotA = nullptr;   // [npad] slot of lexicographic position p in crecA
+  const uint32_t* slotB = nullptr;
+  const uint32_t* cstartA = nullptr; // [G*G + 1] first slot of every cell (lower bounds, empty cells included)
+  const uint32_t* cstartB = nullptr;
+  int* bit = nullptr;                // [(G+1)*(G+1)] 2-D Fenwick tree of max (rank + 1) over the finalised points' cells
+  int* done = nullptr;               // [nblocks] 1 once blocks 0..k have folded their ranks into cmax
+  int lag = 0;                       // blocks b-lag .. b-1 are streamed tile by tile, older ones come from the grid
+  int cshift = 0;                    // id >> cshift = cell coordinate
+  int64_t n = 0;
+};
+
+template <int M>
+__device__ __forceinline__ void rank_cell_coords(const uint32_t* w, int cshift, int& a, int& b) {
+  a = (int)min(w[0] >> cshift, (uint32_t)(RANK_G - 1));
+  b = (M == 3) ? (int)min(w[1] >> cshift, (uint32_t)(RANK_G - 1)) : a;
+}
+
+// Fenwick tree over cells, 1-based, max instead of sum.  Both walks are written level by level (one candidate node per
+// bit level) so that the loops have fixed trip counts and the loads of one row are independent and in flight together;
+// the pointer-chasing form (x -= x & -x) serialises one L2 round trip per node.
+__device__ __forceinline__ int fenwick_prefix_max(const int* bit, int ca, int cb) {  // cells [0, ca) x [0, cb)
+  int best = 0;
+#pragma unroll
+  for (int lx = 0; lx < RANK_GBITS; ++lx) {
+    if (((ca >> lx) & 1) == 0) continue;
+    const int x = ca & ~((1 << lx) - 1);
+    int vals[RANK_GBITS];
+#pragma unroll
+    for (int ly = 0; ly < RANK_GBITS; ++ly) {
+      const int y = cb & ~((1 << ly) - 1);
+      vals[ly] = ((cb >> ly) & 1) ? (int)ld_relaxed_u32((const uint32_t*)bit + x * RANK_BLD + y) : 0;
+    }
+#pragma unroll
+    for (int ly = 0; ly < RANK_GBITS; ++ly) best = max(best, vals[ly]);
+  }
+  return best;
+}
+
+__device__ __forceinline__ void fenwick_update_max(int* bit, int ca, int cb, int val) {  // cell (ca, cb), 0-based
+  const int ix = ca + 1, iy = cb + 1;
+#pragma unroll
+  for (int lx = 0; lx <= RANK_GBITS; ++lx) {
+    const int x = ((ix + (1 << lx) - 1) >> lx) << lx;
+    if (x > RANK_G || ((x >> lx) & 1) == 0) continue;
+    int cur[RANK_GBITS + 1];
+#pragma unroll
+    for (int ly = 0; ly <= RANK_GBITS; ++ly) {
+      const int y = ((iy + (1 << ly) - 1) >> ly) << ly;
+      const bool ok = y <= RANK_G && ((y >> ly) & 1) == 1;
+      // the values only grow: a stale read can only cause a redundant atomic, never a missed one
+      cur[ly] = ok ? (int)ld_relaxed_u32((const uint32_t*)bit + x * RANK_BLD + y) : 0x7FFFFFFF;
+    }
+#pragma unroll
+    for (int ly = 0; ly <= RANK_GBITS; ++ly) {
+      const int y = ((iy + (1 << ly) - 1) >> ly) << ly;
+      if (val > cur[ly]) atomicMax(bit + x * RANK_BLD + y, val);
+    }
+  }
+}
+
+__global__ void cell_key_kernel(const uint32_t* __restrict__ rec, int64_t npad, int W, int M, int cshift,
+                                uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB, uint32_t* __restrict__ pos) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npad) return;
+  const uint32_t* w = rec + p * W;
+  int a, b;
+  if (M == 3)
+    rank_cell_coords<3>(w, cshift, a, b);
+  else
+    rank_cell_coords<2>(w, cshift, a, b);
+  keyA[p] = (uint32_t)(a * RANK_G + b);
+  keyB[p] = (uint32_t)(b * RANK_G + a);
+  pos[p] = (uint32_t)p;
+}
+
+// cell-ordered copy of the static record words (rank word cleared) and the position -> slot map
+__global__ void cell_gather_kernel(const uint32_t* __restrict__ rec, const uint32_t* __restrict__ order, int64_t npad,
+                                   uint4* __restrict__ crec, uint32_t* __restrict__ slot, int M) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npad) return;
+  const uint32_t p = order[t];
+  uint4 r = *reinterpret_cast<const uint4*>(rec + (int64_t)p * 4);  // W == 4 for M <= 3
+  if (M == 3) r.w = 0u; else { r.z = 0u; r.w = 0u; }
+  crec[t] = r;
+  slot[p] = (uint32_t)t;
+}
+
+// cstart[c] = first slot whose key is >= c, c = 0 .. ncell (lower bounds over the sorted keys)
+__global__ void cell_start_kernel(const uint32_t* __restrict__ skey, int64_t npad, int ncell, uint32_t* __restrict__ cstart) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncell) return;
+  int64_t lo = 0, hi = npad;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (skey[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
+  }
+  cstart[c] = (uint32_t)lo;
+}
+
 // Breadth-first walk by path length from the node set `f` (level `level`): table[i * DLD + col] = last level at which
 // i is reached = longest path.  Each thread walks its own source; the frontier is a 128-bit set in registers.
 template <int T, int DLD>
@@ -175,15 +289,15 @@ __device__ __forceinline__ int maxplus_packed(const int8_t* row, const int16_t* 
 }
 
 template <int M, int T>
-__global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
-                                                       int* errflag, long long* trace) {
-  // optional per-block time stamps (DMO_RANK_TRACE=<file>): 8 x globaltimer ns, then 8 x clock64, see scripts/rank_trace.py
+__global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
+                                                       int* errflag, long long* trace, RankGrid grid) {
+  // optional per-block time stamps (DMO_RANK_TRACE=<file>): 16 x globaltimer ns, then 16 x clock64, see scripts/rank_trace.py
 #define RANK_TRACE(slot)                                                         \
   if (trace != nullptr && tid == 0) {                                            \
     long long gt_;                                                               \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                     \
-    trace[(int64_t)b * 16 + (slot)] = gt_;                                       \
-    trace[(int64_t)b * 16 + 8 + (slot)] = clock64();                             \
+    trace[(int64_t)b * 32 + (slot)] = gt_;                                       \
+    trace[(int64_t)b * 32 + 16 + (slot)] = clock64();                             \
   }
   constexpr int W = 4 * ((M + 1 + 3) / 4);
   constexpr int NV = W / 4;
@@ -195,7 +309,9 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
   constexpr int DLD = T + 16;
   constexpr int SENT = -128;  // "no in-block path"; real path lengths are 0 .. T-1 <= 127
   constexpr int PACK_LIMIT = 32000;  // ranks up to here take the packed 16-bit max-plus path
-  __shared__ uint4 tile[T * NV];
+  __shared__ uint4 tile[T * NV];   // own block's records during table construction, then stream buffer 0
+  constexpr bool DBUF = NV <= 2;  // M == 8 (three uint4 per record) would exceed 48 KB of static shared memory
+  __shared__ uint4 tile2[DBUF ? T * NV : 1];  // stream buffer 1
   __shared__ __align__(16) int sh_r1[T];
   __shared__ __align__(16) int16_t sh_h16[T];
   __shared__ uint4 sh_succ[T];
@@ -216,7 +332,7 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     if (trace != nullptr && tid == 0) {
       unsigned smid_;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
-      trace[(int64_t)b * 16 + 7] = smid_;
+      trace[(int64_t)b * 32 + 7] = smid_;
     }
 
     // ---- own record -> registers and shared tile
@@ -254,12 +370,9 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
       }
       static_assert(NW == 4, "successor masks are stored as one uint4 per node");
       sh_succ[tid] = make_uint4(sm[0], sm[1], sm[2], sm[3]);
-      // both path-length tables start as "no path"
+      // the path-length table starts as "no path"
       const uint4 fill = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
-      for (int t = tid; t < T * DLD / 16; t += T) {
-        reinterpret_cast<uint4*>(sD)[t] = fill;
-        reinterpret_cast<uint4*>(sE)[t] = fill;
-      }
+      for (int t = tid; t < T * DLD / 16; t += T) reinterpret_cast<uint4*>(sD)[t] = fill;
     }
     __syncthreads();
 
@@ -273,6 +386,11 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
 
     // ---- predecessor table: E[s][i] = longest in-block continuation of a chain that enters this block from point s of
     // block b-1 (0 if s dominates i directly).  Same walk, seeded with the block nodes s dominates, level 0.
+    {
+      const uint4 fill = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+      for (int t = tid; t < T * DLD / 16; t += T) reinterpret_cast<uint4*>(sE)[t] = fill;
+    }
+    __syncthreads();
     if (b > 0) {
       const int64_t ps = (int64_t)(b - 1) * T + tid;
       uint32_t pv[W];
@@ -305,51 +423,124 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     }
     __syncthreads();
 
-    // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
-    RANK_TRACE(1);
+    // ---- blocks older than b - lag: one grid lookup plus exact tests against the target's cell row / column
     int best = 0;
-    for (int k = 0; k < b - 1; ++k) {
-      if (k == b - 2) RANK_TRACE(2);
-      {
-        const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
-        uint4 a[NV];
-#pragma unroll
-        for (int q = 0; q < NV; ++q) a[q] = ld_relaxed_v4(src + q);
+    int k0 = 0;
+    if (M <= 3 && grid.crecA != nullptr && b > grid.lag + 1) {
+      constexpr int G = RANK_G;
+      k0 = b - grid.lag;
+      if (tid == 0) {  // the tree must contain every block < k0
         unsigned spins = 0;
-        // Not final yet: this block has caught up with the wavefront.  It is at least two links away from being the
-        // critical block (that one waits in the dedicated predecessor poll below), so it backs off generously and
-        // leaves the SM's issue slots to the blocks that are on the critical path.
-        while (word_of(a[RQ], RC) == 0u) {
-          __nanosleep(spins < 4 ? 300 : 1000);
-          a[RQ] = ld_relaxed_v4(src + RQ);
-          if ((++spins & 0xFFu) == 0u && (spins > (1u << 21) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
+        while (ld_acquire_gpu(grid.done + (k0 - 1)) == 0) {
+          __nanosleep(200);
+          if ((++spins & 0xFFu) == 0u && (spins > (1u << 22) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
             atomicExch(errflag, 1);
             break;
           }
         }
-#pragma unroll
-        for (int q = 0; q < NV; ++q) tile[tid * NV + q] = a[q];
       }
       __syncthreads();
-      if (k == b - 2) RANK_TRACE(3);
-#pragma unroll 8
-      for (int s = 0; s < T; ++s) {
-        uint32_t sw[W];
+      RANK_TRACE(8);
+      int ca, cb;
+      rank_cell_coords<(M <= 3 ? M : 3)>(v, grid.cshift, ca, cb);
+      // every finalised point in a cell strictly below (ca, cb) in both words dominates this target: prefix maximum
+      // over cells [0, ca) x [0, cb) from the Fenwick tree (<= 81 independent loads)
+      best = fenwick_prefix_max(grid.bit, ca, cb);
+      // own cell row (ca, 0..cb) in the row-major copy, own cell column (0..ca-1, cb) in the column-major copy: two
+      // contiguous streams of 16-byte records.  A point that is not final yet has rank word 0 and contributes nothing;
+      // a final one that passes the test is a genuine dominator (points after this block are never final here).
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          uint4 a = tile[s * NV + q];
-          sw[4 * q + 0] = a.x;
-          sw[4 * q + 1] = a.y;
-          sw[4 * q + 2] = a.z;
-          sw[4 * q + 3] = a.w;
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint4* cr = pass == 0 ? grid.crecA : grid.crecB;
+        const uint32_t t0 = pass == 0 ? __ldg(grid.cstartA + ca * G) : __ldg(grid.cstartB + cb * G);
+        const uint32_t t1 = pass == 0 ? __ldg(grid.cstartA + ca * G + cb + 1) : __ldg(grid.cstartB + cb * G + ca);
+        uint32_t t = t0;
+#define DMO_GRID_TEST(rj)                                         \
+  {                                                               \
+    const uint32_t wj[4] = {(rj).x, (rj).y, (rj).z, (rj).w};     \
+    bool dom = (wj[M - 1] != gidv);                               \
+    _Pragma("unroll") for (int jj = 0; jj < M - 1; ++jj) dom = dom && (wj[jj] <= v[jj]); \
+    best = dom ? max(best, (int)wj[M]) : best;                    \
+  }
+        for (; t + 8 <= t1; t += 8) {
+          const uint4 r0 = ld_relaxed_v4(cr + t), r1 = ld_relaxed_v4(cr + t + 1);
+          const uint4 r2 = ld_relaxed_v4(cr + t + 2), r3 = ld_relaxed_v4(cr + t + 3);
+          const uint4 r4 = ld_relaxed_v4(cr + t + 4), r5 = ld_relaxed_v4(cr + t + 5);
+          const uint4 r6 = ld_relaxed_v4(cr + t + 6), r7 = ld_relaxed_v4(cr + t + 7);
+          DMO_GRID_TEST(r0)
+          DMO_GRID_TEST(r1)
+          DMO_GRID_TEST(r2)
+          DMO_GRID_TEST(r3)
+          DMO_GRID_TEST(r4)
+          DMO_GRID_TEST(r5)
+          DMO_GRID_TEST(r6)
+          DMO_GRID_TEST(r7)
         }
-        bool dom = (sw[M - 1] != gidv);
-#pragma unroll
-        for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
-        const int r1 = (int)sw[M];
-        best = dom ? max(best, r1) : best;
+        for (; t < t1; ++t) {
+          const uint4 r0 = ld_relaxed_v4(cr + t);
+          DMO_GRID_TEST(r0)
+        }
+#undef DMO_GRID_TEST
       }
-      __syncthreads();
+      RANK_TRACE(9);
+    }
+
+    // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
+    RANK_TRACE(1);
+    // Software pipelined: the record of tile k+1 (static words and, speculatively, its rank word) is requested before
+    // the pair tests of tile k, and the shared tile is double buffered, so a block that is behind the wavefront pays
+    // one barrier and the pair tests per tile, not an L2 round trip on top; a block at the wavefront only waits for
+    // the rank word.
+    {
+      uint4 cur[NV];
+      if (k0 < b - 1) {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k0 * T + tid) * W);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
+      }
+      for (int k = k0; k < b - 1; ++k) {
+        if (k == b - 2) RANK_TRACE(2);
+        {
+          const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
+          unsigned spins = 0;
+          while (word_of(cur[RQ], RC) == 0u) {  // not final yet: this block has caught up with the wavefront
+            __nanosleep(spins < 8 ? 100 : 400);
+            cur[RQ] = ld_relaxed_v4(src + RQ);
+            if ((++spins & 0xFFu) == 0u && (spins > (1u << 21) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
+              atomicExch(errflag, 1);
+              break;
+            }
+          }
+        }
+        uint4* tb = (DBUF && (k & 1)) ? tile2 : tile;
+        if (!DBUF) __syncthreads();  // single buffer: everyone must be done with the previous tile
+#pragma unroll
+        for (int q = 0; q < NV; ++q) tb[tid * NV + q] = cur[q];
+        if (k + 1 < b - 1) {  // request the next record now; it is consumed after this tile's pair tests
+          const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)(k + 1) * T + tid) * W);
+#pragma unroll
+          for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
+        }
+        __syncthreads();  // one barrier per tile: buffer (k & 1) is rewritten two iterations later, after barrier k+1
+        if (k == b - 2) RANK_TRACE(3);
+#pragma unroll 8
+        for (int s = 0; s < T; ++s) {
+          uint32_t sw[W];
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            uint4 a4 = tb[s * NV + q];
+            sw[4 * q + 0] = a4.x;
+            sw[4 * q + 1] = a4.y;
+            sw[4 * q + 2] = a4.z;
+            sw[4 * q + 3] = a4.w;
+          }
+          bool dom = (sw[M - 1] != gidv);
+#pragma unroll
+          for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
+          const int r1 = (int)sw[M];
+          best = dom ? max(best, r1) : best;
+        }
+      }
     }
     // ---- in-block resolution, part 1 (before the predecessor's ranks are needed):
     //   Rb_i = max_a (bulk_a + D[a][i]) folds the contributions of all blocks < b-1 through the in-block paths.
@@ -408,6 +599,33 @@ __global__ void __launch_bounds__(T, 8) rank_chain_kernel(uint32_t* rec, int nbl
     st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: the rank word doubles as the ready flag
     rankS[i] = r;
     RANK_TRACE(6);
+    if (M <= 3 && grid.crecA != nullptr) {
+      // fold this block's ranks into the Fenwick tree, then extend the "done" prefix (in block order)
+      {
+        uint32_t* wa = reinterpret_cast<uint32_t*>(grid.crecA + grid.slotA[i]) + M;
+        uint32_t* wb = reinterpret_cast<uint32_t*>(grid.crecB + grid.slotB[i]) + M;
+        st_relaxed_u32(wa, (uint32_t)(r + 1));
+        st_relaxed_u32(wb, (uint32_t)(r + 1));
+        int ca, cb;
+        rank_cell_coords<(M <= 3 ? M : 3)>(v, grid.cshift, ca, cb);
+        if (i < grid.n) fenwick_update_max(grid.bit, ca, cb, r + 1);
+      }
+      __threadfence();
+      __syncthreads();
+      RANK_TRACE(10);
+      if (tid == 0) {
+        unsigned spins = 0;
+        while (b > 0 && ld_acquire_gpu(grid.done + (b - 1)) == 0) {
+          __nanosleep(100);
+          if ((++spins & 0xFFu) == 0u && (spins > (1u << 22) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
+            atomicExch(errflag, 1);
+            break;
+          }
+        }
+        st_release_gpu(grid.done + b, 1);
+      }
+      RANK_TRACE(11);
+    }
     __syncthreads();
   }
 #undef RANK_TRACE
@@ -486,13 +704,13 @@ __global__ void copy_u32_to_i32_kernel(const uint32_t* __restrict__ a, int64_t n
 }
 
 template <int M>
-int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* ticket, int* errflag) {
-  // debugging aid: DMO_RANK_TRACE=<file> dumps 16 int64 time stamps per block of the chain kernel
+int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* ticket, int* errflag, const RankGrid& grid) {
+  // debugging aid: DMO_RANK_TRACE=<file> dumps 32 int64 time stamps per block of the chain kernel
   DevBuf<long long> trace;
   const char* trace_path = getenv("DMO_RANK_TRACE");
   if (trace_path && *trace_path) {
-    DMO_TRY(trace.alloc(ctx, (size_t)nblocks * 16));
-    DMO_CUDA(cudaMemsetAsync(trace.p, 0, (size_t)nblocks * 16 * sizeof(long long), ctx->stream));
+    DMO_TRY(trace.alloc(ctx, (size_t)nblocks * 32));
+    DMO_CUDA(cudaMemsetAsync(trace.p, 0, (size_t)nblocks * 32 * sizeof(long long), ctx->stream));
   }
   int occ = 0;
   DMO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_chain_kernel<M, RANK_T>, RANK_T, 0));
@@ -502,14 +720,14 @@ int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* tick
   int cap = 6;
   if (const char* e = getenv("DMO_RANK_OCC")) cap = atoi(e);
   if (cap >= 1 && occ > cap) occ = cap;
-  int grid = nblocks < occ * ctx->sm_count ? nblocks : occ * ctx->sm_count;
+  int nctas = nblocks < occ * ctx->sm_count ? nblocks : occ * ctx->sm_count;
   {
     ProfileScope ps(ctx, "rank_chain");
-    DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), grid, RANK_T, 0, rec, nblocks, rankS, ticket, errflag, trace.p);
+    DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), nctas, RANK_T, 0, rec, nblocks, rankS, ticket, errflag, trace.p, grid);
     DMO_CHECK_LAUNCH();
   }
   if (trace.p) {
-    std::vector<long long> h((size_t)nblocks * 16);
+    std::vector<long long> h((size_t)nblocks * 32);
     DMO_CUDA(cudaMemcpyAsync(h.data(), trace.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     DMO_CUDA(cudaStreamSynchronize(ctx->stream));
     if (FILE* f = fopen(trace_path, "wb")) {
@@ -611,14 +829,60 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
     DMO_CHECK_LAUNCH();
     return DMO_OK;
   }
+  // cell index for the grid-accelerated scan (two and three objectives, enough blocks to be worth it)
+  RankGrid grid;
+  DevBuf<uint32_t> ckeyA, ckeyB, ckeyS, cpos, cord, slotA, slotB, cstartA, cstartB;
+  DevBuf<uint4> crecA, crecB;
+  DevBuf<int> cstate;
+  int lag = 32;
+  if (const char* e = getenv("DMO_RANK_LAG")) lag = atoi(e);
+  if (M <= 3 && lag >= 2 && nblocks > 2 * (int64_t)lag && bits_for(n) > RANK_GBITS) {
+    const int GG = RANK_G * RANK_G;
+    const int cshift = bits_for(n) - RANK_GBITS;  // dense ids are < n <= 2^bits
+    DMO_TRY(ckeyA.alloc(ctx, npad));
+    DMO_TRY(ckeyB.alloc(ctx, npad));
+    DMO_TRY(ckeyS.alloc(ctx, npad));
+    DMO_TRY(cpos.alloc(ctx, npad));
+    DMO_TRY(cord.alloc(ctx, npad));
+    DMO_TRY(slotA.alloc(ctx, npad));
+    DMO_TRY(slotB.alloc(ctx, npad));
+    DMO_TRY(cstartA.alloc(ctx, GG + 1));
+    DMO_TRY(cstartB.alloc(ctx, GG + 1));
+    DMO_TRY(crecA.alloc(ctx, npad));
+    DMO_TRY(crecB.alloc(ctx, npad));
+    const size_t nbit = (size_t)RANK_BLD * RANK_BLD;
+    DMO_TRY(cstate.alloc(ctx, nbit + nblocks));
+    DMO_CUDA(cudaMemsetAsync(cstate.p, 0, (nbit + nblocks) * sizeof(int), ctx->stream));
+    const unsigned gp = (unsigned)ceil_div(npad, 256);
+    DMO_LAUNCH(cell_key_kernel, gp, 256, 0, rec.p, npad, W, M, cshift, ckeyA.p, ckeyB.p, cpos.p);
+    for (int pass = 0; pass < 2; ++pass) {  // stable sorts: lexicographic position stays ascending inside a cell
+      DMO_TRY(prim_sort_pairs_u32(ctx, pass == 0 ? ckeyA.p : ckeyB.p, ckeyS.p, cpos.p, cord.p, npad, 0, 2 * RANK_GBITS));
+      DMO_LAUNCH(cell_gather_kernel, gp, 256, 0, rec.p, cord.p, npad, pass == 0 ? crecA.p : crecB.p,
+                 pass == 0 ? slotA.p : slotB.p, M);
+      DMO_LAUNCH(cell_start_kernel, (unsigned)ceil_div(GG + 1, 256), 256, 0, ckeyS.p, npad, GG,
+                 pass == 0 ? cstartA.p : cstartB.p);
+    }
+    DMO_CHECK_LAUNCH();
+    grid.crecA = crecA.p;
+    grid.crecB = crecB.p;
+    grid.slotA = slotA.p;
+    grid.slotB = slotB.p;
+    grid.cstartA = cstartA.p;
+    grid.cstartB = cstartB.p;
+    grid.bit = cstate.p;
+    grid.done = cstate.p + nbit;
+    grid.lag = lag;
+    grid.cshift = cshift;
+    grid.n = n;
+  }
   switch (M) {
-    case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 4: DMO_TRY(launch_chain<4>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 5: DMO_TRY(launch_chain<5>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 6: DMO_TRY(launch_chain<6>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 7: DMO_TRY(launch_chain<7>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    default: DMO_TRY(launch_chain<8>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
+    case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
+    case 4: DMO_TRY(launch_chain<4>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
+    case 5: DMO_TRY(launch_chain<5>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
+    case 6: DMO_TRY(launch_chain<6>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
+    case 7: DMO_TRY(launch_chain<7>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
+    default: DMO_TRY(launch_chain<8>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
   }
   DMO_LAUNCH(scatter_rank_kernel, g, 256, 0, rankS.p, perm, n, d_rank);
   DMO_CHECK_LAUNCH();

@@ -99,6 +99,31 @@ def test_rank_full_size_property(L):
     assert len(np.unique(r)) == r.max() + 1
 
 
+@pytest.mark.parametrize("n,M,kind", [(65536, 2, "uniform"), (50000, 3, "sphere"), (40000, 3, "ties"), (130995, 3, "uniform"), (30000, 2, "ties")])
+def test_rank_grid_path_property(L, n, M, kind):
+    """Sizes that take the grid-accelerated scan of the chain kernel (M <= 3, more than 64 blocks): the chain identity
+    rank_i = 1 + max rank of the dominators of i is checked exactly on a sample, including tied and duplicated values."""
+    rng = np.random.default_rng(n + M)
+    if kind == "uniform":
+        Y = rng.random((n, M))
+    elif kind == "sphere":
+        x = rng.random((n, M))
+        Y = x / np.linalg.norm(x, axis=1, keepdims=True) * (1 + 1e-3 * rng.random((n, 1)))
+    else:
+        Y = rng.integers(0, 60, size=(n, M)).astype(np.float64)
+    r = L.rank_nd(Y)
+    assert r.min() == 0 and len(np.unique(r)) == r.max() + 1
+    for i in rng.choice(n, size=200, replace=False):
+        dom = np.all(Y <= Y[i], axis=1) & np.any(Y < Y[i], axis=1)
+        assert r[i] == ((r[dom].max() + 1) if dom.any() else 0)
+    if kind == "ties":  # identical vectors share a rank
+        _, inv = np.unique(Y, axis=0, return_inverse=True)
+        inv = np.ravel(inv)
+        first = np.zeros(inv.max() + 1, dtype=np.int64)
+        first[inv] = r
+        assert np.array_equal(first[inv], r)
+
+
 # ------------------------------------------------------------------------------------------ A3/A4
 def test_distance_metrics_golden_bit_exact(L):
     g = load_golden("distance")
