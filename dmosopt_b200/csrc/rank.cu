@@ -118,120 +118,6 @@ __device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c ==
 
 // The rank word of a record (rank + 1, 0 = not yet final) is its own ready flag: a 4-byte store is atomic and carries
 // no other data, so publication needs neither fences nor a separate flag, and consumers simply poll the word.
-// ------------------------------------------------------------------------------------------------ cell index (M <= 3)
-// For two and three objectives the records carry one or two compare words (the first objective is implied by the
-// lexicographic order).  A RANK_G x RANK_G grid over those words turns most of the "all earlier blocks" scan into one
-// table lookup: every finalised point in a cell strictly below a target's cell in both words dominates it, so the
-// maximum rank over those cells (a 2-D prefix maximum of the per-cell maxima) is a valid contribution; only the
-// points in the target's own cell row / column need the exact pair test.  (M == 2 uses the diagonal cells (a, a).)
-constexpr int RANK_G = 512;
-constexpr int RANK_GBITS = 9;
-constexpr int RANK_BLD = RANK_G + 1;  // row stride of the (1-based) Fenwick tree
-
-struct RankGrid {
-  // two cell-ordered copies of the records (static words + rank word): A is row-major over (word 0 cell, word 1 cell),
-  // B is column-major, so that a target's cell row and its cell column are each ONE contiguous range of slots
-  uint4* crecA = nullptr;
-  uint4* crecB = nullptr;
-  const uint32_t* slotA = nullptr;   // [npad] slot of lexicographic position p in crecA
-  const uint32_t* slotB = nullptr;
-  const uint32_t* cstartA = nullptr; // [G*G + 1] first slot of every cell (lower bounds, empty cells included)
-  const uint32_t* cstartB = nullptr;
-  int* bit = nullptr;                // [(G+1)*(G+1)] 2-D Fenwick tree of max (rank + 1) over the finalised points' cells
-  int* done = nullptr;               // [nblocks] 1 once blocks 0..k have folded their ranks into cmax
-  int lag = 0;                       // blocks b-lag .. b-1 are streamed tile by tile, older ones come from the grid
-  int cshift = 0;                    // id >> cshift = cell coordinate
-  int64_t n = 0;
-};
-
-template <int M>
-__device__ __forceinline__ void rank_cell_coords(const uint32_t* w, int cshift, int& a, int& b) {
-  a = (int)min(w[0] >> cshift, (uint32_t)(RANK_G - 1));
-  b = (M == 3) ? (int)min(w[1] >> cshift, (uint32_t)(RANK_G - 1)) : a;
-}
-
-// Fenwick tree over cells, 1-based, max instead of sum.  Both walks are written level by level (one candidate node per
-// bit level) so that the loops have fixed trip counts and the loads of one row are independent and in flight together;
-// the pointer-chasing form (x -= x & -x) serialises one L2 round trip per node.
-__device__ __forceinline__ int fenwick_prefix_max(const int* bit, int ca, int cb) {  // cells [0, ca) x [0, cb)
-  int best = 0;
-#pragma unroll
-  for (int lx = 0; lx < RANK_GBITS; ++lx) {
-    if (((ca >> lx) & 1) == 0) continue;
-    const int x = ca & ~((1 << lx) - 1);
-    int vals[RANK_GBITS];
-#pragma unroll
-    for (int ly = 0; ly < RANK_GBITS; ++ly) {
-      const int y = cb & ~((1 << ly) - 1);
-      vals[ly] = ((cb >> ly) & 1) ? (int)ld_relaxed_u32((const uint32_t*)bit + x * RANK_BLD + y) : 0;
-    }
-#pragma unroll
-    for (int ly = 0; ly < RANK_GBITS; ++ly) best = max(best, vals[ly]);
-  }
-  return best;
-}
-
-__device__ __forceinline__ void fenwick_update_max(int* bit, int ca, int cb, int val) {  // cell (ca, cb), 0-based
-  const int ix = ca + 1, iy = cb + 1;
-#pragma unroll
-  for (int lx = 0; lx <= RANK_GBITS; ++lx) {
-    const int x = ((ix + (1 << lx) - 1) >> lx) << lx;
-    if (x > RANK_G || ((x >> lx) & 1) == 0) continue;
-    int cur[RANK_GBITS + 1];
-#pragma unroll
-    for (int ly = 0; ly <= RANK_GBITS; ++ly) {
-      const int y = ((iy + (1 << ly) - 1) >> ly) << ly;
-      const bool ok = y <= RANK_G && ((y >> ly) & 1) == 1;
-      // the values only grow: a stale read can only cause a redundant atomic, never a missed one
-      cur[ly] = ok ? (int)ld_relaxed_u32((const uint32_t*)bit + x * RANK_BLD + y) : 0x7FFFFFFF;
-    }
-#pragma unroll
-    for (int ly = 0; ly <= RANK_GBITS; ++ly) {
-      const int y = ((iy + (1 << ly) - 1) >> ly) << ly;
-      if (val > cur[ly]) atomicMax(bit + x * RANK_BLD + y, val);
-    }
-  }
-}
-
-__global__ void cell_key_kernel(const uint32_t* __restrict__ rec, int64_t npad, int W, int M, int cshift,
-                                uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB, uint32_t* __restrict__ pos) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npad) return;
-  const uint32_t* w = rec + p * W;
-  int a, b;
-  if (M == 3)
-    rank_cell_coords<3>(w, cshift, a, b);
-  else
-    rank_cell_coords<2>(w, cshift, a, b);
-  keyA[p] = (uint32_t)(a * RANK_G + b);
-  keyB[p] = (uint32_t)(b * RANK_G + a);
-  pos[p] = (uint32_t)p;
-}
-
-// cell-ordered copy of the static record words (rank word cleared) and the position -> slot map
-__global__ void cell_gather_kernel(const uint32_t* __restrict__ rec, const uint32_t* __restrict__ order, int64_t npad,
-                                   uint4* __restrict__ crec, uint32_t* __restrict__ slot, int M) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= npad) return;
-  const uint32_t p = order[t];
-  uint4 r = *reinterpret_cast<const uint4*>(rec + (int64_t)p * 4);  // W == 4 for M <= 3
-  if (M == 3) r.w = 0u; else { r.z = 0u; r.w = 0u; }
-  crec[t] = r;
-  slot[p] = (uint32_t)t;
-}
-
-// cstart[c] = first slot whose key is >= c, c = 0 .. ncell (lower bounds over the sorted keys)
-__global__ void cell_start_kernel(const uint32_t* __restrict__ skey, int64_t npad, int ncell, uint32_t* __restrict__ cstart) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > ncell) return;
-  int64_t lo = 0, hi = npad;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (skey[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
-  }
-  cstart[c] = (uint32_t)lo;
-}
-
 // Breadth-first walk by path length from the node set `f` (level `level`): table[i * DLD + col] = last level at which
 // i is reached = longest path.  Each thread walks its own source; the frontier is a 128-bit set in registers.
 template <int T, int DLD>
@@ -290,7 +176,7 @@ __device__ __forceinline__ int maxplus_packed(const int8_t* row, const int16_t* 
 
 template <int M, int T>
 __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
-                                                       int* errflag, long long* trace, RankGrid grid) {
+                                                       int* errflag, long long* trace) {
   // optional per-block time stamps (DMO_RANK_TRACE=<file>): 16 x globaltimer ns, then 16 x clock64, see scripts/rank_trace.py
 #define RANK_TRACE(slot)                                                         \
   if (trace != nullptr && tid == 0) {                                            \
@@ -423,68 +309,7 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
     }
     __syncthreads();
 
-    // ---- blocks older than b - lag: one grid lookup plus exact tests against the target's cell row / column
     int best = 0;
-    int k0 = 0;
-    if (M <= 3 && grid.crecA != nullptr && b > grid.lag + 1) {
-      constexpr int G = RANK_G;
-      k0 = b - grid.lag;
-      if (tid == 0) {  // the tree must contain every block < k0
-        unsigned spins = 0;
-        while (ld_acquire_gpu(grid.done + (k0 - 1)) == 0) {
-          __nanosleep(200);
-          if ((++spins & 0xFFu) == 0u && (spins > (1u << 22) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
-            atomicExch(errflag, 1);
-            break;
-          }
-        }
-      }
-      __syncthreads();
-      RANK_TRACE(8);
-      int ca, cb;
-      rank_cell_coords<(M <= 3 ? M : 3)>(v, grid.cshift, ca, cb);
-      // every finalised point in a cell strictly below (ca, cb) in both words dominates this target: prefix maximum
-      // over cells [0, ca) x [0, cb) from the Fenwick tree (<= 81 independent loads)
-      best = fenwick_prefix_max(grid.bit, ca, cb);
-      // own cell row (ca, 0..cb) in the row-major copy, own cell column (0..ca-1, cb) in the column-major copy: two
-      // contiguous streams of 16-byte records.  A point that is not final yet has rank word 0 and contributes nothing;
-      // a final one that passes the test is a genuine dominator (points after this block are never final here).
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const uint4* cr = pass == 0 ? grid.crecA : grid.crecB;
-        const uint32_t t0 = pass == 0 ? __ldg(grid.cstartA + ca * G) : __ldg(grid.cstartB + cb * G);
-        const uint32_t t1 = pass == 0 ? __ldg(grid.cstartA + ca * G + cb + 1) : __ldg(grid.cstartB + cb * G + ca);
-        uint32_t t = t0;
-#define DMO_GRID_TEST(rj)                                         \
-  {                                                               \
-    const uint32_t wj[4] = {(rj).x, (rj).y, (rj).z, (rj).w};     \
-    bool dom = (wj[M - 1] != gidv);                               \
-    _Pragma("unroll") for (int jj = 0; jj < M - 1; ++jj) dom = dom && (wj[jj] <= v[jj]); \
-    best = dom ? max(best, (int)wj[M]) : best;                    \
-  }
-        for (; t + 8 <= t1; t += 8) {
-          const uint4 r0 = ld_relaxed_v4(cr + t), r1 = ld_relaxed_v4(cr + t + 1);
-          const uint4 r2 = ld_relaxed_v4(cr + t + 2), r3 = ld_relaxed_v4(cr + t + 3);
-          const uint4 r4 = ld_relaxed_v4(cr + t + 4), r5 = ld_relaxed_v4(cr + t + 5);
-          const uint4 r6 = ld_relaxed_v4(cr + t + 6), r7 = ld_relaxed_v4(cr + t + 7);
-          DMO_GRID_TEST(r0)
-          DMO_GRID_TEST(r1)
-          DMO_GRID_TEST(r2)
-          DMO_GRID_TEST(r3)
-          DMO_GRID_TEST(r4)
-          DMO_GRID_TEST(r5)
-          DMO_GRID_TEST(r6)
-          DMO_GRID_TEST(r7)
-        }
-        for (; t < t1; ++t) {
-          const uint4 r0 = ld_relaxed_v4(cr + t);
-          DMO_GRID_TEST(r0)
-        }
-#undef DMO_GRID_TEST
-      }
-      RANK_TRACE(9);
-    }
-
     // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
     RANK_TRACE(1);
     // Software pipelined: the record of tile k+1 (static words and, speculatively, its rank word) is requested before
@@ -493,12 +318,12 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
     // the rank word.
     {
       uint4 cur[NV];
-      if (k0 < b - 1) {
-        const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k0 * T + tid) * W);
+      if (b > 1) {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)tid * W);
 #pragma unroll
         for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
       }
-      for (int k = k0; k < b - 1; ++k) {
+      for (int k = 0; k < b - 1; ++k) {
         if (k == b - 2) RANK_TRACE(2);
         {
           const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
@@ -599,33 +424,6 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
     st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: the rank word doubles as the ready flag
     rankS[i] = r;
     RANK_TRACE(6);
-    if (M <= 3 && grid.crecA != nullptr) {
-      // fold this block's ranks into the Fenwick tree, then extend the "done" prefix (in block order)
-      {
-        uint32_t* wa = reinterpret_cast<uint32_t*>(grid.crecA + grid.slotA[i]) + M;
-        uint32_t* wb = reinterpret_cast<uint32_t*>(grid.crecB + grid.slotB[i]) + M;
-        st_relaxed_u32(wa, (uint32_t)(r + 1));
-        st_relaxed_u32(wb, (uint32_t)(r + 1));
-        int ca, cb;
-        rank_cell_coords<(M <= 3 ? M : 3)>(v, grid.cshift, ca, cb);
-        if (i < grid.n) fenwick_update_max(grid.bit, ca, cb, r + 1);
-      }
-      __threadfence();
-      __syncthreads();
-      RANK_TRACE(10);
-      if (tid == 0) {
-        unsigned spins = 0;
-        while (b > 0 && ld_acquire_gpu(grid.done + (b - 1)) == 0) {
-          __nanosleep(100);
-          if ((++spins & 0xFFu) == 0u && (spins > (1u << 22) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
-            atomicExch(errflag, 1);
-            break;
-          }
-        }
-        st_release_gpu(grid.done + b, 1);
-      }
-      RANK_TRACE(11);
-    }
     __syncthreads();
   }
 #undef RANK_TRACE
@@ -684,6 +482,146 @@ __global__ void __launch_bounds__(T) nd_flag_kernel(const uint32_t* __restrict__
   flagS[i] = dominated ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------ rank-0 test on a cell grid
+// For two and three objectives the records carry one or two compare words (the first objective is implied by the
+// lexicographic order).  A G x G grid over those words answers most rank-0 queries with one table lookup: a point in a
+// cell strictly below the target's cell in both words, and earlier in lexicographic order, dominates it, so the target
+// is dominated iff the minimum position over those cells (an exclusive 2-D prefix minimum of the per-cell minima) is
+// smaller than its own.  Only the points in the target's own cell row and cell column need the exact test; two
+// cell-ordered copies of the records (row-major and column-major) make both of them contiguous streams.
+// (M == 2 duplicates its single compare word, i.e. only the diagonal cells are populated.)
+__global__ void ndg_key_kernel(const uint32_t* __restrict__ rec, int64_t npad, int M, int cshift, int gbits,
+                               uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB, uint32_t* __restrict__ pos) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npad) return;
+  const uint32_t G1 = (1u << gbits) - 1u;
+  const uint32_t* w = rec + p * 4;  // W == 4 for M <= 3
+  const uint32_t a = min(w[0] >> cshift, G1);
+  const uint32_t b = (M == 3) ? min(w[1] >> cshift, G1) : a;
+  keyA[p] = (a << gbits) | b;
+  keyB[p] = (b << gbits) | a;
+  pos[p] = (uint32_t)p;
+}
+
+// cell-ordered copy: (word 0, word 1 (word 0 again for M == 2), group id, lexicographic position)
+__global__ void ndg_gather_kernel(const uint32_t* __restrict__ rec, const uint32_t* __restrict__ order, int64_t npad,
+                                  int M, uint4* __restrict__ crec) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npad) return;
+  const uint32_t p = order[t];
+  const uint4 r = *reinterpret_cast<const uint4*>(rec + (int64_t)p * 4);
+  crec[t] = (M == 3) ? make_uint4(r.x, r.y, r.z, p) : make_uint4(r.x, r.x, r.y, p);
+}
+
+// cstart[c] = first slot whose key is >= c, c = 0 .. ncell (lower bounds over the sorted keys)
+__global__ void ndg_start_kernel(const uint32_t* __restrict__ skey, int64_t npad, int ncell, uint32_t* __restrict__ cstart) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncell) return;
+  int64_t lo = 0, hi = npad;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (skey[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
+  }
+  cstart[c] = (uint32_t)lo;
+}
+
+// inclusive prefix minimum of the per-cell minimum positions: pass 0 along each row, pass 1 along each column
+__global__ void ndg_prefix_min_kernel(const uint32_t* __restrict__ cstartA, const uint4* __restrict__ crecA, int gbits,
+                                      int pass, uint32_t* __restrict__ pm) {
+  extern __shared__ uint32_t sh_scan[];
+  const int G = 1 << gbits;
+  const int line = blockIdx.x, t = threadIdx.x;  // pass 0: line = row a, t = column b; pass 1: line = column b, t = row a
+  const int cell = pass == 0 ? line * G + t : t * G + line;
+  uint32_t v;
+  if (pass == 0) {
+    const uint32_t s0 = cstartA[cell], s1 = cstartA[cell + 1];
+    v = s0 < s1 ? crecA[s0].w : 0xFFFFFFFFu;  // stable sort: the first record of a cell has its smallest position
+  } else {
+    v = pm[cell];
+  }
+  sh_scan[t] = v;
+  __syncthreads();
+  for (int off = 1; off < G; off <<= 1) {
+    const uint32_t o = t >= off ? sh_scan[t - off] : 0xFFFFFFFFu;
+    __syncthreads();
+    v = min(v, o);
+    sh_scan[t] = v;
+    __syncthreads();
+  }
+  pm[cell] = v;
+}
+
+__global__ void ndg_flag_kernel(const uint32_t* __restrict__ rec, int64_t n, int M, int cshift, int gbits,
+                                const uint32_t* __restrict__ pm, const uint32_t* __restrict__ cstartA,
+                                const uint32_t* __restrict__ cstartB, const uint4* __restrict__ crecA,
+                                const uint4* __restrict__ crecB, int* __restrict__ flagS) {
+  const int64_t p64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p64 >= n) return;
+  const uint32_t p = (uint32_t)p64;
+  const int G = 1 << gbits;
+  const uint4 r = *reinterpret_cast<const uint4*>(rec + p64 * 4);
+  const uint32_t c0 = r.x, c1 = (M == 3) ? r.y : r.x, gid = (M == 3) ? r.z : r.y;
+  const int a = (int)min(c0 >> cshift, (uint32_t)(G - 1)), b = (int)min(c1 >> cshift, (uint32_t)(G - 1));
+  bool dom = a > 0 && b > 0 && __ldg(pm + (a - 1) * G + (b - 1)) < p;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if (dom) break;
+    const uint4* cr = pass == 0 ? crecA : crecB;
+    uint32_t t = pass == 0 ? __ldg(cstartA + a * G) : __ldg(cstartB + b * G);
+    const uint32_t t1 = pass == 0 ? __ldg(cstartA + a * G + b + 1) : __ldg(cstartB + b * G + a);
+#define DMO_NDG_TEST(q) ((q).w < p && (q).x <= c0 && (q).y <= c1 && (q).z != gid)
+    for (; t + 4 <= t1 && !dom; t += 4) {
+      const uint4 q0 = __ldg(cr + t), q1 = __ldg(cr + t + 1), q2 = __ldg(cr + t + 2), q3 = __ldg(cr + t + 3);
+      dom = DMO_NDG_TEST(q0) || DMO_NDG_TEST(q1) || DMO_NDG_TEST(q2) || DMO_NDG_TEST(q3);
+    }
+    for (; t < t1 && !dom; ++t) {
+      const uint4 q0 = __ldg(cr + t);
+      dom = DMO_NDG_TEST(q0);
+    }
+#undef DMO_NDG_TEST
+  }
+  flagS[p64] = dom ? 1 : 0;
+}
+
+int bits_for(int64_t n);
+
+// flagS[p] = 1 iff the record at lexicographic position p is dominated (M <= 3, W == 4)
+int nd_flags_grid(dmo_ctx* ctx, const uint32_t* rec, int64_t n, int64_t npad, int M, int* flagS) {
+  const int bits = bits_for(n);
+  int gbits = bits / 2;
+  if (gbits < 4) gbits = 4;
+  if (gbits > 9) gbits = 9;
+  const int G = 1 << gbits, GG = G * G;
+  const int cshift = bits > gbits ? bits - gbits : 0;  // dense ids are < n <= 2^bits
+  DevBuf<uint32_t> keyA, keyB, keyS, pos, ord, cstartA, cstartB, pm;
+  DevBuf<uint4> crecA, crecB;
+  DMO_TRY(keyA.alloc(ctx, npad));
+  DMO_TRY(keyB.alloc(ctx, npad));
+  DMO_TRY(keyS.alloc(ctx, npad));
+  DMO_TRY(pos.alloc(ctx, npad));
+  DMO_TRY(ord.alloc(ctx, npad));
+  DMO_TRY(cstartA.alloc(ctx, GG + 1));
+  DMO_TRY(cstartB.alloc(ctx, GG + 1));
+  DMO_TRY(pm.alloc(ctx, GG));
+  DMO_TRY(crecA.alloc(ctx, npad));
+  DMO_TRY(crecB.alloc(ctx, npad));
+  const unsigned gp = (unsigned)ceil_div(npad, 256);
+  ProfileScope ps(ctx, "nd_flags");
+  DMO_LAUNCH(ndg_key_kernel, gp, 256, 0, rec, npad, M, cshift, gbits, keyA.p, keyB.p, pos.p);
+  for (int pass = 0; pass < 2; ++pass) {  // stable sorts: positions stay ascending inside a cell
+    DMO_TRY(prim_sort_pairs_u32(ctx, pass == 0 ? keyA.p : keyB.p, keyS.p, pos.p, ord.p, npad, 0, 2 * gbits));
+    DMO_LAUNCH(ndg_gather_kernel, gp, 256, 0, rec, ord.p, npad, M, pass == 0 ? crecA.p : crecB.p);
+    DMO_LAUNCH(ndg_start_kernel, (unsigned)ceil_div(GG + 1, 256), 256, 0, keyS.p, npad, GG,
+               pass == 0 ? cstartA.p : cstartB.p);
+  }
+  DMO_LAUNCH(ndg_prefix_min_kernel, G, G, G * sizeof(uint32_t), cstartA.p, crecA.p, gbits, 0, pm.p);
+  DMO_LAUNCH(ndg_prefix_min_kernel, G, G, G * sizeof(uint32_t), cstartA.p, crecA.p, gbits, 1, pm.p);
+  DMO_LAUNCH(ndg_flag_kernel, (unsigned)ceil_div(n, 128), 128, 0, rec, n, M, cshift, gbits, pm.p, cstartA.p, cstartB.p,
+             crecA.p, crecB.p, flagS);
+  DMO_CHECK_LAUNCH();
+  return DMO_OK;
+}
+
 template <int M>
 int launch_nd_flags(dmo_ctx* ctx, const uint32_t* rec, int nblocks, int* flagS) {
   ProfileScope ps(ctx, "nd_flags");
@@ -704,7 +642,7 @@ __global__ void copy_u32_to_i32_kernel(const uint32_t* __restrict__ a, int64_t n
 }
 
 template <int M>
-int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* ticket, int* errflag, const RankGrid& grid) {
+int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* ticket, int* errflag) {
   // debugging aid: DMO_RANK_TRACE=<file> dumps 32 int64 time stamps per block of the chain kernel
   DevBuf<long long> trace;
   const char* trace_path = getenv("DMO_RANK_TRACE");
@@ -723,7 +661,7 @@ int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* tick
   int nctas = nblocks < occ * ctx->sm_count ? nblocks : occ * ctx->sm_count;
   {
     ProfileScope ps(ctx, "rank_chain");
-    DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), nctas, RANK_T, 0, rec, nblocks, rankS, ticket, errflag, trace.p, grid);
+    DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), nctas, RANK_T, 0, rec, nblocks, rankS, ticket, errflag, trace.p);
     DMO_CHECK_LAUNCH();
   }
   if (trace.p) {
@@ -815,6 +753,12 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
   DMO_LAUNCH(build_records_kernel, (unsigned)ceil_div(npad, 256), 256, 0, R.p, perm, gid.p, n, npad, M, W, rec.p);
   int* ticket = sync.p + nblocks;
   int* errflag = sync.p + nblocks + 1;
+  if (flags_only && M <= 3 && n >= 8192 && getenv("DMO_ND_BRUTE") == nullptr) {
+    DMO_TRY(nd_flags_grid(ctx, rec.p, n, npad, M, rankS.p));
+    DMO_LAUNCH(scatter_rank_kernel, g, 256, 0, rankS.p, perm, n, d_rank);
+    DMO_CHECK_LAUNCH();
+    return DMO_OK;
+  }
   if (flags_only) {  // d_rank receives 0 for non-dominated points and 1 otherwise
     switch (M) {
       case 2: DMO_TRY(launch_nd_flags<2>(ctx, rec.p, (int)nblocks, rankS.p)); break;
@@ -829,60 +773,14 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
     DMO_CHECK_LAUNCH();
     return DMO_OK;
   }
-  // cell index for the grid-accelerated scan (two and three objectives, enough blocks to be worth it)
-  RankGrid grid;
-  DevBuf<uint32_t> ckeyA, ckeyB, ckeyS, cpos, cord, slotA, slotB, cstartA, cstartB;
-  DevBuf<uint4> crecA, crecB;
-  DevBuf<int> cstate;
-  int lag = 32;
-  if (const char* e = getenv("DMO_RANK_LAG")) lag = atoi(e);
-  if (M <= 3 && lag >= 2 && nblocks > 2 * (int64_t)lag && bits_for(n) > RANK_GBITS) {
-    const int GG = RANK_G * RANK_G;
-    const int cshift = bits_for(n) - RANK_GBITS;  // dense ids are < n <= 2^bits
-    DMO_TRY(ckeyA.alloc(ctx, npad));
-    DMO_TRY(ckeyB.alloc(ctx, npad));
-    DMO_TRY(ckeyS.alloc(ctx, npad));
-    DMO_TRY(cpos.alloc(ctx, npad));
-    DMO_TRY(cord.alloc(ctx, npad));
-    DMO_TRY(slotA.alloc(ctx, npad));
-    DMO_TRY(slotB.alloc(ctx, npad));
-    DMO_TRY(cstartA.alloc(ctx, GG + 1));
-    DMO_TRY(cstartB.alloc(ctx, GG + 1));
-    DMO_TRY(crecA.alloc(ctx, npad));
-    DMO_TRY(crecB.alloc(ctx, npad));
-    const size_t nbit = (size_t)RANK_BLD * RANK_BLD;
-    DMO_TRY(cstate.alloc(ctx, nbit + nblocks));
-    DMO_CUDA(cudaMemsetAsync(cstate.p, 0, (nbit + nblocks) * sizeof(int), ctx->stream));
-    const unsigned gp = (unsigned)ceil_div(npad, 256);
-    DMO_LAUNCH(cell_key_kernel, gp, 256, 0, rec.p, npad, W, M, cshift, ckeyA.p, ckeyB.p, cpos.p);
-    for (int pass = 0; pass < 2; ++pass) {  // stable sorts: lexicographic position stays ascending inside a cell
-      DMO_TRY(prim_sort_pairs_u32(ctx, pass == 0 ? ckeyA.p : ckeyB.p, ckeyS.p, cpos.p, cord.p, npad, 0, 2 * RANK_GBITS));
-      DMO_LAUNCH(cell_gather_kernel, gp, 256, 0, rec.p, cord.p, npad, pass == 0 ? crecA.p : crecB.p,
-                 pass == 0 ? slotA.p : slotB.p, M);
-      DMO_LAUNCH(cell_start_kernel, (unsigned)ceil_div(GG + 1, 256), 256, 0, ckeyS.p, npad, GG,
-                 pass == 0 ? cstartA.p : cstartB.p);
-    }
-    DMO_CHECK_LAUNCH();
-    grid.crecA = crecA.p;
-    grid.crecB = crecB.p;
-    grid.slotA = slotA.p;
-    grid.slotB = slotB.p;
-    grid.cstartA = cstartA.p;
-    grid.cstartB = cstartB.p;
-    grid.bit = cstate.p;
-    grid.done = cstate.p + nbit;
-    grid.lag = lag;
-    grid.cshift = cshift;
-    grid.n = n;
-  }
   switch (M) {
-    case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
-    case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
-    case 4: DMO_TRY(launch_chain<4>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
-    case 5: DMO_TRY(launch_chain<5>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
-    case 6: DMO_TRY(launch_chain<6>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
-    case 7: DMO_TRY(launch_chain<7>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
-    default: DMO_TRY(launch_chain<8>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, grid)); break;
+    case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 4: DMO_TRY(launch_chain<4>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 5: DMO_TRY(launch_chain<5>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 6: DMO_TRY(launch_chain<6>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    case 7: DMO_TRY(launch_chain<7>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+    default: DMO_TRY(launch_chain<8>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
   }
   DMO_LAUNCH(scatter_rank_kernel, g, 256, 0, rankS.p, perm, n, d_rank);
   DMO_CHECK_LAUNCH();

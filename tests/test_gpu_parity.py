@@ -387,6 +387,40 @@ def test_hv_edge_cases_and_properties(L):
     assert exact * 0.98 < v < exact
 
 
+@pytest.mark.parametrize("n,M,kind", [(20000, 3, "uniform"), (30000, 2, "uniform"), (12000, 3, "ties"), (9000, 2, "ties"), (10000, 3, "sphere"), (65536, 3, "mixed")])
+def test_hv_large_sets_grid_filter(L, n, M, kind):
+    """n >= 8192, M <= 3: the rank-0 filter in front of the hypervolume runs on the cell grid.  Same value as with the
+    plain block scan (DMO_ND_BRUTE), and as the CPU oracle applied to the exact non-dominated subset."""
+    import os
+
+    rng = np.random.default_rng(n * 7 + M)
+    if kind == "uniform":
+        F = rng.random((n, M))
+    elif kind == "ties":
+        F = rng.integers(0, 40, size=(n, M)).astype(np.float64) / 40.0
+    elif kind == "sphere":
+        x = rng.random((n, M))
+        F = x / np.linalg.norm(x, axis=1, keepdims=True)
+    else:  # a large front plus a dominated cloud and duplicated rows
+        x = rng.random((n // 2, M))
+        front = x / np.linalg.norm(x, axis=1, keepdims=True)
+        F = np.vstack((front[: n // 4], front[: n // 4], front[n // 4 :], front[n // 4 :] * (1 + rng.random((n // 4, 1)))))
+    ref = F.max(axis=0) + 0.1
+    v = L.hypervolume(F, ref)
+    os.environ["DMO_ND_BRUTE"] = "1"
+    try:
+        v_brute = L.hypervolume(F, ref)
+    finally:
+        del os.environ["DMO_ND_BRUTE"]
+    assert v == v_brute
+    if kind in ("uniform", "ties"):  # small fronts: exact subset on the CPU, oracle hypervolume
+        nd = L.rank_nd(F) == 0
+        sub = np.unique(F[nd], axis=0)
+        assert len(sub) < 3000
+        exp = hv.hypervolume(sub, ref)
+        assert abs(v - exp) <= 1e-10 * exp
+
+
 # ------------------------------------------------------------------------------------------ A17 EHVI
 def test_ehvi_golden(L):
     g = load_golden("ehvi")
