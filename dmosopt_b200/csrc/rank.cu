@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
     }
     const uint32_t gidv = v[M - 1];
     __syncthreads();
+    const uint32_t first_gid = reinterpret_cast<const uint32_t*>(&tile[0])[M - 1];  // group of the block's first record
 
     // ---- in-block successor bitmasks: succ[j] = { i > j in this block : j dominates i }; independent of any rank
     {
@@ -348,22 +349,46 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
         }
         __syncthreads();  // one barrier per tile: buffer (k & 1) is rewritten two iterations later, after barrier k+1
         if (k == b - 2) RANK_TRACE(3);
+        // Group ids grow along the lexicographic order, so a tile whose last record is in an earlier group than this
+        // block's first record holds no copy of any of this block's vectors: the "not identical" test can be dropped
+        // (one compare per pair less).  Block-uniform choice, both loops are otherwise the same.
+        const bool may_share_group = reinterpret_cast<const uint32_t*>(&tb[(T - 1) * NV])[M - 1] >= first_gid;
+        if (!may_share_group) {
 #pragma unroll 8
-        for (int s = 0; s < T; ++s) {
-          uint32_t sw[W];
+          for (int s = 0; s < T; ++s) {
+            uint32_t sw[W];
 #pragma unroll
-          for (int q = 0; q < NV; ++q) {
-            uint4 a4 = tb[s * NV + q];
-            sw[4 * q + 0] = a4.x;
-            sw[4 * q + 1] = a4.y;
-            sw[4 * q + 2] = a4.z;
-            sw[4 * q + 3] = a4.w;
+            for (int q = 0; q < NV; ++q) {
+              uint4 a4 = tb[s * NV + q];
+              sw[4 * q + 0] = a4.x;
+              sw[4 * q + 1] = a4.y;
+              sw[4 * q + 2] = a4.z;
+              sw[4 * q + 3] = a4.w;
+            }
+            bool dom = true;
+#pragma unroll
+            for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
+            const int r1 = (int)sw[M];
+            best = dom ? max(best, r1) : best;
           }
-          bool dom = (sw[M - 1] != gidv);
+        } else {
+#pragma unroll 8
+          for (int s = 0; s < T; ++s) {
+            uint32_t sw[W];
 #pragma unroll
-          for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
-          const int r1 = (int)sw[M];
-          best = dom ? max(best, r1) : best;
+            for (int q = 0; q < NV; ++q) {
+              uint4 a4 = tb[s * NV + q];
+              sw[4 * q + 0] = a4.x;
+              sw[4 * q + 1] = a4.y;
+              sw[4 * q + 2] = a4.z;
+              sw[4 * q + 3] = a4.w;
+            }
+            bool dom = (sw[M - 1] != gidv);
+#pragma unroll
+            for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
+            const int r1 = (int)sw[M];
+            best = dom ? max(best, r1) : best;
+          }
         }
       }
     }
