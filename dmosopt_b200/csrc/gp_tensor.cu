@@ -527,9 +527,9 @@ __global__ void __launch_bounds__(KT_TN)
                         const double* __restrict__ inv_ls, const double* __restrict__ constant,
                         const int* __restrict__ k_exp, int64_t ldk, int64_t plane, uint16_t* __restrict__ Kh,
                         uint16_t* __restrict__ Kl) {
-  extern __shared__ __align__(16) float sxf[];  // [KT_TP][DMAX] candidate tile, then [4][DMAX] 1/l, [4] c * 2^kexp
+  extern __shared__ __align__(16) float sxf[];  // [KT_TP][DMAX] candidate tile, then [M][DMAX] 1/l, [M] c * 2^kexp
   float* s_il = sxf + KT_TP * DMAX;
-  float* s_c = s_il + 4 * DMAX;
+  float* s_c = s_il + M * DMAX;
   const int64_t n0 = ((int64_t)blockIdx.x * KT_TN + threadIdx.x) * 2;
   const int64_t pt0 = (int64_t)blockIdx.y * KT_TP;
   for (int t = threadIdx.x; t < KT_TP * DMAX; t += KT_TN) {
@@ -715,7 +715,7 @@ int prepare_tensor_state(dmo_ctx* ctx, dmo_gp* gp) {
 int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var) {
   const int64_t N = gp->N, Npad = gp->Npad;
   const int M = gp->M, d = gp->d;
-  DMO_REQUIRE(M <= 4, "gp_predict(tensor): at most 4 objectives per model (got %d)", M);
+  DMO_REQUIRE(M <= 16, "gp_predict(tensor): at most 16 objectives per model (got %d)", M);
   DMO_REQUIRE(d <= 64, "gp_predict(tensor): at most 64 input dimensions (got %d); use DMO_GP_FP64", d);
   DMO_REQUIRE(Npad % TN == 0, "gp_predict(tensor): internal padding error");
   DMO_TRY(prepare_tensor_state(ctx, gp));
@@ -760,7 +760,7 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       ProfileScope ps(ctx, "gp_kstar");
       dim3 gk((unsigned)(Npad / (2 * KT_TN)), (unsigned)ceil_div(Pcpad, KT_TP));
       const int dmax = d <= 32 ? 32 : 64;
-      size_t smem = (size_t)(KT_TP * dmax + 4 * dmax + 4) * sizeof(float);
+      size_t smem = (size_t)(KT_TP * dmax + M * dmax + M) * sizeof(float);
 #define KSTAR_LAUNCH(ISO_, DM_)                                                                                      \
   DMO_LAUNCH((kstar_tensor_kernel<ISO_, DM_>), gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel, \
              gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p)

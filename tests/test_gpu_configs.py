@@ -1,0 +1,71 @@
+"""BASELINE.json configurations other than the bench line, run at (or near) their stated sizes through the plugin API.
+
+These are size-independent property checks (the CPU oracle cannot reach these sizes in test time): one warm-up and two
+timed generations per configuration, then the invariants of the reference contract -- population size, bounds,
+finiteness, stored ranks = canonical ranks of the stored objectives, survivors drawn from (offspring + parents).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from dmosopt_b200 import _lib
+
+    _lib.context()
+    return _lib
+
+
+def test_c2_agemoea_pop8192(L):
+    """ZDT3 d=30 M=2 pop=8192 AGEMOEA + GP N_train=2048 (BASELINE configs[1]), full size."""
+    import config_sweep as cs
+    import dmosopt_b200 as b2
+
+    opt, px, py = cs.run("C2 AGEMOEA", b2.AGEMOEA, 30, 2, 8192, 2048, "zdt3")
+    assert px.shape == (8192, 30) and py.shape == (8192, 2)
+    r = L.rank_nd(py.astype(np.float64))
+    assert np.array_equal(np.asarray(opt.state.rank), r)
+    assert np.all(np.diff(r) >= 0)  # sortMO order: rank ascending
+
+
+def test_c3_nsga2_pop65536_d12(L):
+    """DTLZ2 d=12 M=3 pop=65536 NSGA2 + GP N_train=4096 (BASELINE configs[2]), full size."""
+    import config_sweep as cs
+    import dmosopt_b200 as b2
+
+    opt, px, py = cs.run("C3 NSGA2", b2.NSGA2, 12, 3, 65536, 4096, "dtlz2", distance_metric=None)
+    assert px.shape == (65536, 12)
+    r = L.rank_nd(py.astype(np.float64))
+    assert np.array_equal(np.asarray(opt.state.rank), r)
+    assert np.all(np.diff(r) >= 0)
+
+
+def test_c4_smpso_m5_with_hv_contribution_select(L):
+    """DTLZ7 d=22 M=5 SMPSO + HV-contribution selection (BASELINE configs[3]); pop 8192 per swarm (x5 swarms)."""
+    import config_sweep as cs
+    import dmosopt_b200 as b2
+
+    opt, px, py = cs.run("C4 SMPSO", b2.SMPSO, 22, 5, 8192, 2048, "dtlz7")
+    assert px.shape[0] <= 5 * 8192 and px.shape[0] >= 5 * 8192 - 64  # de-duplicated population (SMPSO.py:248)
+    front = py[L.rank_nd(py.astype(np.float64)) == 0].astype(np.float64)[:128]
+    mu, var = opt.model.objective.predict(px[:2048])
+    ref = py.max(axis=0).astype(np.float64) + 1.0
+    sel, score = L.ehvi_select(front, mu, var, ref, 256, return_scores=True)
+    assert len(np.unique(sel)) == 256 and np.all(np.isfinite(score)) and np.all(score >= 0)
+    assert np.all(score[sel].min() >= np.delete(score, sel).max() - 1e-12)  # top-k by score
+
+
+def test_c5_cmaes_m4(L):
+    """WFG4-shaped d=24 M=4 CMAES + dda + GP (BASELINE configs[4]); pop 16384 (the 131072 run is scripts/config_sweep.py)."""
+    import config_sweep as cs
+    import dmosopt_b200 as b2
+
+    opt, px, py = cs.run("C5 CMAES", b2.CMAES, 24, 4, 16384, 2048, "dtlz2")
+    assert px.shape == (16384, 24) and py.shape == (16384, 4)
