@@ -64,6 +64,7 @@ _SIGNATURES = {
     ),
     "dmo_gp_create": (_c_int, [_vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "dmo_gp_destroy": (_c_int, [_vp, _vp]),
+    "dmo_gp_set_linear_mean": (_c_int, [_vp, _vp, _vp, _vp]),
     "dmo_gp_predict": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _c_int]),
     "dmo_hypervolume": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp, ctypes.POINTER(_c_dbl)]),
     "dmo_ehvi_select": (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp, _c_int, _c_i64, _vp, _vp]),
@@ -573,6 +574,15 @@ class GPHandle:
             "dmo_gp_create",
         )
         self._h = h
+
+    def set_linear_mean(self, weight, bias):
+        """Prior mean w_m . x_n + b_m per objective (gpytorch LinearMean, A19); ``None, None`` removes it."""
+        if weight is None and bias is None:
+            _check(load_library().dmo_gp_set_linear_mean(context(), self._h, None, None), "dmo_gp_set_linear_mean")
+            return
+        w = _f64(np.asarray(weight, dtype=np.float64).reshape(self.M, self.d))
+        b = _f64(np.asarray(bias, dtype=np.float64).reshape(self.M))
+        _check(load_library().dmo_gp_set_linear_mean(context(), self._h, _ptr(w), _ptr(b)), "dmo_gp_set_linear_mean")
 
     def predict(self, X, return_var=True, precision=GP_FP64):
         X = _f64(X)

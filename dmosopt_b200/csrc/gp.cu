@@ -500,6 +500,40 @@ int dmo_gp_destroy(dmo_ctx* ctx, dmo_gp* gp) {
   return DMO_OK;
 }
 
+// mean[p][m] += y_std[m] * (w_m . xn_p + b_m): the prior mean of a gpytorch ExactGP with LinearMean
+__global__ void linear_mean_add_kernel(const double* __restrict__ Xn, int64_t P, int d, int M,
+                                       const double* __restrict__ w, const double* __restrict__ b,
+                                       const double* __restrict__ ystd, double* __restrict__ mean) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P * M) return;
+  const int64_t p = t / M;
+  const int m = (int)(t - p * M);
+  double s = b[m];
+  for (int j = 0; j < d; ++j) s = fma(w[m * d + j], Xn[p * d + j], s);
+  mean[t] += ystd[m] * s;
+}
+
+int dmo_gp_set_linear_mean(dmo_ctx* ctx, dmo_gp* gp, const double* weight, const double* bias) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(gp, "gp_set_linear_mean: null model");
+  if (!weight && !bias) {
+    gp->has_linear_mean = false;
+    return DMO_OK;
+  }
+  DMO_REQUIRE(weight && bias, "gp_set_linear_mean: weight and bias must both be given (or both NULL)");
+  In<double> w, b;
+  DMO_TRY(w.init(ctx, weight, (size_t)gp->M * gp->d));
+  DMO_TRY(b.init(ctx, bias, (size_t)gp->M));
+  DMO_TRY(gp->lin_w.alloc(ctx, (size_t)gp->M * gp->d));
+  DMO_TRY(gp->lin_b.alloc(ctx, (size_t)gp->M));
+  DMO_CUDA(cudaMemcpyAsync(gp->lin_w.p, w.d, (size_t)gp->M * gp->d * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  DMO_CUDA(cudaMemcpyAsync(gp->lin_b.p, b.d, (size_t)gp->M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  gp->has_linear_mean = true;
+  return DMO_OK;
+}
+
 int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double* mean, double* var, int precision) {
   if (!ctx) return DMO_ERR_ARG;
   DMO_CUDA(cudaSetDevice(ctx->device));
@@ -520,6 +554,11 @@ int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double*
     DMO_TRY(gp_predict_tensor(ctx, gp, xn.p, P, om.d, ov.d));
   } else {
     return dmo_fail(ctx, DMO_ERR_ARG, "gp_predict: unknown precision %d", precision);
+  }
+  if (gp->has_linear_mean) {
+    DMO_LAUNCH(linear_mean_add_kernel, (unsigned)ceil_div(P * gp->M, 256), 256, 0, xn.p, P, gp->d, gp->M, gp->lin_w.p,
+               gp->lin_b.p, gp->ystd.p, om.d);
+    DMO_CHECK_LAUNCH();
   }
   DMO_TRY(om.finish(ctx));
   DMO_TRY(ov.finish(ctx));

@@ -15,6 +15,9 @@ struct dmo_gp {
   DevBuf<double> constant, noise, ymean, ystd;  // (M,)
   DevBuf<double> xlb, xrg;  // (d,)
   std::vector<double> h_constant, h_noise, h_ystd;
+  // optional linear prior mean m(x) = w . x_n + b in the normalised-output space (gpytorch LinearMean, A19)
+  bool has_linear_mean = false;
+  DevBuf<double> lin_w, lin_b;  // (M, d), (M,)
   // tensor path (built lazily on first DMO_GP_TENSOR predict)
   bool tensor_ready = false;
   DevBuf<uint16_t> Lhi, Llo;  // (M, Npad, Npad) fp16 split of the row-scaled L^-1

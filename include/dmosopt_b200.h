@@ -172,6 +172,12 @@ int dmo_gp_create(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const doubl
                   const double* y_mean, const double* y_std, const double* xlb, const double* xub,
                   dmo_gp** out);
 int dmo_gp_destroy(dmo_ctx* ctx, dmo_gp* gp);
+/* A19: prior mean of the gpytorch exact GPs (model_gpytorch.EGP_Matern.predict,
+ * dmosopt/model_gpytorch.py:2188-2228; GPyTorchExactGPModelMatern with LinearMean, :455-508):
+ * after this call dmo_gp_predict returns y_std * (K_* alpha + weight_m . x_n + bias_m) + y_mean,
+ * x_n the normalised input; alpha must then be (K + noise I)^-1 (y_n - X_n weight - bias).
+ * weight (M,d), bias (M,); both NULL removes the term.  The variance is unaffected. */
+int dmo_gp_set_linear_mean(dmo_ctx* ctx, dmo_gp* gp, const double* weight, const double* bias);
 int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double* mean,
                    double* var, int precision);
 

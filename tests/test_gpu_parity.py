@@ -343,6 +343,35 @@ def test_gp_predict_tensor_path(L, N, d, M, P):
     h.close()
 
 
+# ------------------------------------------------------------------------------------------ A19 (parity unpinned)
+@pytest.mark.parametrize("precision", ["fp64", "tensor"])
+def test_egp_linear_mean_vs_oracle(L, precision):
+    """EGP_Matern posterior (ARD Matern-5/2 + LinearMean + Gaussian noise) through dmo_gp_set_linear_mean, against
+    oracle/egp.py.  gpytorch is absent, so the hyper-parameters are given, not trained."""
+    from dmosopt_b200.model_gpytorch import EGP_Matern
+    from oracle import egp
+
+    rng = np.random.default_rng(11)
+    N, d, M, P = 700, 12, 3, 900
+    xlb, xub = -np.ones(d), 2.0 * np.ones(d)
+    X = xlb + rng.random((N, d)) * (xub - xlb)
+    Y = np.column_stack([np.sin(X[:, :3].sum(1)) + 0.3 * X[:, 3], X[:, 0] * X[:, 1] - X[:, 4], np.cos(X[:, 5]) + 0.5 * X[:, 6:].sum(1)])
+    hp = dict(lengthscale=0.4 + rng.random((M, d)), outputscale=[0.8, 1.7, 1.1], noise=[1e-3, 5e-4, 2e-3],
+              weight=0.3 * rng.standard_normal((M, d)), bias=[0.1, -0.2, 0.05])
+    sm = EGP_Matern(X, Y, d, M, xlb, xub, hyperparameters=hp, precision=precision)
+    st = egp.fit_fixed(X, Y, xlb, xub, hp["lengthscale"], hp["outputscale"], hp["noise"], hp["weight"], hp["bias"])
+    Xs = xlb + rng.random((P, d)) * (xub - xlb)
+    mean, var = sm.predict(Xs)
+    em, ev = egp.predict(st, Xs)
+    assert mean.dtype == np.float32 and var.dtype == np.float32
+    prior = np.array([(o.outputscale + o.noise) * o.y_std**2 for o in st.objectives])
+    scale = np.abs(em).max(axis=0)
+    tol = 2e-6 if precision == "fp64" else 1e-5  # float32 outputs bound the fp64 path
+    assert np.all(np.abs(mean - em).max(axis=0) <= tol * scale)
+    assert np.all(np.abs(var - ev).max(axis=0) <= tol * prior)
+    assert np.array_equal(sm.evaluate(Xs), mean)
+
+
 # ------------------------------------------------------------------------------------------ A16 HV
 def test_hv_known_answers_and_golden(L):
     g = load_golden("hv")
