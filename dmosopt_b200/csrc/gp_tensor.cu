@@ -516,6 +516,27 @@ __device__ __forceinline__ float stationary_f(float s2, int kind) {
   return __expf(-0.5f * s2);
 }
 
+// the same for a pair of squared distances, on the packed fp32 pipe (FMUL2 / FFMA2); the two MUFU ops per value stay scalar
+__device__ __forceinline__ float2 stationary2_f(float2 s2, int kind) {
+  float2 e;
+  if (kind == DMO_KERNEL_MATERN52) {
+    float2 r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(s2.x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(s2.y));
+    const float2 K = __fmul2_rn(r, make_float2(2.2360679774997896f, 2.2360679774997896f));
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 p = __ffma2_rn(K, __ffma2_rn(K, make_float2(1.0f / 3.0f, 1.0f / 3.0f), one), one);
+    const float2 t = __fmul2_rn(K, make_float2(-1.4426950408889634f, -1.4426950408889634f));  // exp(-K) = 2^(-K log2 e)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+    return __fmul2_rn(p, e);
+  }
+  const float2 t = __fmul2_rn(s2, make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+  return e;
+}
+
 // K_* in fp32 -> scaled fp16 hi / lo.  Each thread owns two adjacent training points (their coordinates live in
 // registers, results leave as packed half2), a block covers 256 training points x KT_TP candidates; the candidate
 // tile is read from shared memory as 16-byte broadcasts (rows padded with zeros to DMAX coordinates, so the
@@ -542,11 +563,15 @@ __global__ void __launch_bounds__(KT_TN)
     s_il[t] = j < d ? (float)inv_ls[m * d + j] : 0.f;
   }
   if (threadIdx.x < M) s_c[threadIdx.x] = scalbnf((float)constant[threadIdx.x], k_exp[threadIdx.x]);
-  float xa[DMAX], xb[DMAX];
+  // training coordinates as packed pairs (two coordinates per 64-bit register pair): the distance loop runs on the
+  // packed fp32 pipe, FADD2 + FFMA2 per two coordinates and point instead of 2 FADD + 2 FFMA
+  float2 xa[DMAX / 2], xb[DMAX / 2];
 #pragma unroll
-  for (int j = 0; j < DMAX; ++j) {
-    xa[j] = (j < d && n0 < N) ? (float)Xt[n0 * d + j] : 0.f;
-    xb[j] = (j < d && n0 + 1 < N) ? (float)Xt[(n0 + 1) * d + j] : 0.f;
+  for (int j = 0; j < DMAX / 2; ++j) {
+    const int j0 = 2 * j, j1 = 2 * j + 1;
+    xa[j] = make_float2((j0 < d && n0 < N) ? (float)Xt[n0 * d + j0] : 0.f, (j1 < d && n0 < N) ? (float)Xt[n0 * d + j1] : 0.f);
+    xb[j] = make_float2((j0 < d && n0 + 1 < N) ? (float)Xt[(n0 + 1) * d + j0] : 0.f,
+                        (j1 < d && n0 + 1 < N) ? (float)Xt[(n0 + 1) * d + j1] : 0.f);
   }
   __syncthreads();
   if (n0 >= ldk) return;
@@ -559,54 +584,52 @@ __global__ void __launch_bounds__(KT_TN)
     const float4* xc = reinterpret_cast<const float4*>(sxf + q * DMAX);
     float sa = 0.f, sb = 0.f;
     if (ISO) {
-      float sa1 = 0.f, sb1 = 0.f;  // two accumulators per point: shorter dependent chains
+      float2 acc_a0 = make_float2(0.f, 0.f), acc_a1 = acc_a0, acc_b0 = acc_a0, acc_b1 = acc_a0;  // independent chains
 #pragma unroll
       for (int j = 0; j < DMAX / 4; ++j) {
         const float4 c = xc[j];
-        float da = c.x - xa[4 * j], db = c.x - xb[4 * j];
-        sa = fmaf(da, da, sa);
-        sb = fmaf(db, db, sb);
-        da = c.y - xa[4 * j + 1], db = c.y - xb[4 * j + 1];
-        sa1 = fmaf(da, da, sa1);
-        sb1 = fmaf(db, db, sb1);
-        da = c.z - xa[4 * j + 2], db = c.z - xb[4 * j + 2];
-        sa = fmaf(da, da, sa);
-        sb = fmaf(db, db, sb);
-        da = c.w - xa[4 * j + 3], db = c.w - xb[4 * j + 3];
-        sa1 = fmaf(da, da, sa1);
-        sb1 = fmaf(db, db, sb1);
+        const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
+        const float2 da0 = __fadd2_rn(c01, make_float2(-xa[2 * j].x, -xa[2 * j].y));
+        const float2 db0 = __fadd2_rn(c01, make_float2(-xb[2 * j].x, -xb[2 * j].y));
+        const float2 da1 = __fadd2_rn(c23, make_float2(-xa[2 * j + 1].x, -xa[2 * j + 1].y));
+        const float2 db1 = __fadd2_rn(c23, make_float2(-xb[2 * j + 1].x, -xb[2 * j + 1].y));
+        acc_a0 = __ffma2_rn(da0, da0, acc_a0);
+        acc_b0 = __ffma2_rn(db0, db0, acc_b0);
+        acc_a1 = __ffma2_rn(da1, da1, acc_a1);
+        acc_b1 = __ffma2_rn(db1, db1, acc_b1);
       }
-      sa += sa1;
-      sb += sb1;
+      sa = (acc_a0.x + acc_a0.y) + (acc_a1.x + acc_a1.y);
+      sb = (acc_b0.x + acc_b0.y) + (acc_b1.x + acc_b1.y);
     }
     for (int m = 0; m < M; ++m) {
-      float ra, rb;
+      float2 rr;
       if (ISO) {
         const float il = s_il[m * DMAX];
-        ra = sa * il * il;
-        rb = sb * il * il;
+        const float il2 = il * il;
+        rr = __fmul2_rn(make_float2(sa, sb), make_float2(il2, il2));
       } else {
-        ra = rb = 0.f;
         const float4* il4 = reinterpret_cast<const float4*>(s_il + m * DMAX);
+        float2 acc_a = make_float2(0.f, 0.f), acc_b = acc_a;
 #pragma unroll
         for (int j = 0; j < DMAX / 4; ++j) {
           const float4 c = xc[j], il = il4[j];
-          float da = (c.x - xa[4 * j]) * il.x, db = (c.x - xb[4 * j]) * il.x;
-          ra = fmaf(da, da, ra);
-          rb = fmaf(db, db, rb);
-          da = (c.y - xa[4 * j + 1]) * il.y, db = (c.y - xb[4 * j + 1]) * il.y;
-          ra = fmaf(da, da, ra);
-          rb = fmaf(db, db, rb);
-          da = (c.z - xa[4 * j + 2]) * il.z, db = (c.z - xb[4 * j + 2]) * il.z;
-          ra = fmaf(da, da, ra);
-          rb = fmaf(db, db, rb);
-          da = (c.w - xa[4 * j + 3]) * il.w, db = (c.w - xb[4 * j + 3]) * il.w;
-          ra = fmaf(da, da, ra);
-          rb = fmaf(db, db, rb);
+          const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
+          const float2 i01 = make_float2(il.x, il.y), i23 = make_float2(il.z, il.w);
+          const float2 da0 = __fmul2_rn(__fadd2_rn(c01, make_float2(-xa[2 * j].x, -xa[2 * j].y)), i01);
+          const float2 db0 = __fmul2_rn(__fadd2_rn(c01, make_float2(-xb[2 * j].x, -xb[2 * j].y)), i01);
+          const float2 da1 = __fmul2_rn(__fadd2_rn(c23, make_float2(-xa[2 * j + 1].x, -xa[2 * j + 1].y)), i23);
+          const float2 db1 = __fmul2_rn(__fadd2_rn(c23, make_float2(-xb[2 * j + 1].x, -xb[2 * j + 1].y)), i23);
+          acc_a = __ffma2_rn(da0, da0, acc_a);
+          acc_b = __ffma2_rn(db0, db0, acc_b);
+          acc_a = __ffma2_rn(da1, da1, acc_a);
+          acc_b = __ffma2_rn(db1, db1, acc_b);
         }
+        rr = make_float2(acc_a.x + acc_a.y, acc_b.x + acc_b.y);
       }
-      const float ka = live_a ? s_c[m] * stationary_f(ra, kind) : 0.f;  // c * k(r), scaled by 2^kexp (exact)
-      const float kb = live_b ? s_c[m] * stationary_f(rb, kind) : 0.f;
+      const float sc = s_c[m];
+      const float2 kk = __fmul2_rn(stationary2_f(rr, kind), make_float2(sc, sc));  // c * k(r), scaled by 2^kexp (exact)
+      const float ka = live_a ? kk.x : 0.f;
+      const float kb = live_b ? kk.y : 0.f;
       const __half2 h = __floats2half2_rn(ka, kb);
       const float2 hf = __half22float2(h);
       const __half2 l = __floats2half2_rn(ka - hf.x, kb - hf.y);
