@@ -655,6 +655,7 @@ __global__ void mean_split_kernel(const uint16_t* __restrict__ Kh, const uint16_
   const uint32_t* rl = reinterpret_cast<const uint32_t*>(Kl + m * plane + pl * ldk);
   const double* a = alpha + (int64_t)m * N;
   double s = 0.0;
+#pragma unroll 8
   for (int64_t n2 = lane; 2 * n2 < N; n2 += 32) {  // two fp16 values per 32-bit load
     const uint32_t h = rh[n2], l = rl[n2];
     const float k0 = __half2float(__ushort_as_half((uint16_t)(h & 0xFFFFu))) + __half2float(__ushort_as_half((uint16_t)(l & 0xFFFFu)));

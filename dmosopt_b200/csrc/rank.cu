@@ -342,17 +342,18 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
         if (!DBUF) __syncthreads();  // single buffer: everyone must be done with the previous tile
 #pragma unroll
         for (int q = 0; q < NV; ++q) tb[tid * NV + q] = cur[q];
+        // Group ids grow along the lexicographic order, so a tile whose last record is in an earlier group than this
+        // block's first record holds no copy of any of this block's vectors: the "not identical" test can be dropped
+        // (one compare per pair less).  The owner of the tile's last record votes through the tile barrier.
+        const bool last_shares = (tid == T - 1) && (word_of(cur[(M - 1) / 4], (M - 1) % 4) >= first_gid);
         if (k + 1 < b - 1) {  // request the next record now; it is consumed after this tile's pair tests
           const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)(k + 1) * T + tid) * W);
 #pragma unroll
           for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
         }
-        __syncthreads();  // one barrier per tile: buffer (k & 1) is rewritten two iterations later, after barrier k+1
+        // one barrier per tile: buffer (k & 1) is rewritten two iterations later, after barrier k+1
+        const bool may_share_group = __syncthreads_or(last_shares ? 1 : 0) != 0;
         if (k == b - 2) RANK_TRACE(3);
-        // Group ids grow along the lexicographic order, so a tile whose last record is in an earlier group than this
-        // block's first record holds no copy of any of this block's vectors: the "not identical" test can be dropped
-        // (one compare per pair less).  Block-uniform choice, both loops are otherwise the same.
-        const bool may_share_group = reinterpret_cast<const uint32_t*>(&tb[(T - 1) * NV])[M - 1] >= first_gid;
         if (!may_share_group) {
 #pragma unroll 8
           for (int s = 0; s < T; ++s) {
