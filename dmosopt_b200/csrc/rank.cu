@@ -118,6 +118,93 @@ __device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c ==
 
 // The rank word of a record (rank + 1, 0 = not yet final) is its own ready flag: a 4-byte store is atomic and carries
 // no other data, so publication needs neither fences nor a separate flag, and consumers simply poll the word.
+// ------------------------------------------------------------------------------------------------ segmented order (M <= 3)
+// Any linear extension of the dominance order works for the chain recurrence.  Instead of the plain lexicographic
+// order the points are ordered by (segment of objective 1, objective 2, ..., objective M, objective 1), a segment
+// being 1/32 of the dense id range of objective 1.  Sources in an earlier segment have a smaller objective-1 id than
+// every target, and inside a segment the tiles are sorted by the first compare word, so for a target block with the
+// band [blo, bhi] of that word a whole earlier tile is
+//   * skipped        if its smallest word is > bhi (nothing in it can dominate anything in the block),
+//   * "fast"         if its largest word is < blo (the first compare is known to pass and is dropped),
+//   * tested in full otherwise (about one tile per segment) and, with the extra objective-1 compare, for the tiles that
+//     may share a segment with the block.
+// Bands are compared on 8-bit floor-quantised words (conservative in both directions) held in shared memory.
+struct RankSeg {
+  const uint32_t* c1rec = nullptr;      // [npad] objective-1 id per position (0xFFFFFFFF for the padding)
+  const uint32_t* seg_start = nullptr;  // [nseg + 1] first position whose segment is >= s
+  const uint16_t* tile_q = nullptr;     // [nblocks] low byte = min, high byte = max of the quantised first compare word
+  int sshift = 0;                       // id1 >> sshift = segment
+  int qshift = 0;                       // word >> qshift = 8-bit band coordinate (clamped to 255)
+};
+constexpr int RANK_SEG_MAXT = 1024;  // tiles whose bands fit the shared-memory cache (n <= 131072)
+
+__global__ void seg_key_kernel(const uint32_t* __restrict__ R0, const uint32_t* __restrict__ perm, int64_t n, int sshift,
+                               uint32_t* __restrict__ key) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) key[p] = R0[perm[p]] >> sshift;
+}
+
+__global__ void seg_c1_kernel(const uint32_t* __restrict__ R0, const uint32_t* __restrict__ perm, int64_t n, int64_t npad,
+                              uint32_t* __restrict__ c1rec) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < npad) c1rec[p] = p < n ? R0[perm[p]] : 0xFFFFFFFFu;
+}
+
+__global__ void seg_start_kernel(const uint32_t* __restrict__ c1rec, int64_t n, int sshift, int nseg,
+                                 uint32_t* __restrict__ seg_start) {
+  int sgi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sgi > nseg) return;
+  int64_t lo = 0, hi = n;  // positions are sorted by segment
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((c1rec[mid] >> sshift) < (uint32_t)sgi) lo = mid + 1; else hi = mid;
+  }
+  seg_start[sgi] = (uint32_t)lo;
+}
+
+// one warp per tile: quantised min / max of the first compare word
+__global__ void seg_tile_band_kernel(const uint32_t* __restrict__ rec, int nblocks, int T, int qshift,
+                                     uint16_t* __restrict__ tile_q) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= nblocks) return;
+  uint32_t lo = 255u, hi = 0u;
+  for (int t = lane; t < T; t += 32) {
+    const uint32_t q = min(rec[((int64_t)k * T + t) * 4] >> qshift, 255u);
+    lo = min(lo, q);
+    hi = max(hi, q);
+  }
+  lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+  hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+  if (lane == 0) tile_q[k] = (uint16_t)(lo | (hi << 8));
+}
+
+// 128 pair tests of one streamed tile against this thread's record.  SKIP0: the first compare word is known to pass;
+// GID: the "not identical" test is needed; C1: objective 1 must be compared too (source may share the target's segment)
+template <int M, int W, int NV, int T, bool SKIP0, bool GID, bool C1>
+__device__ __forceinline__ int rank_pair_tests(const uint4* tb, const uint32_t* c1tb, const uint32_t* v, uint32_t gidv,
+                                               uint32_t c1v, int best) {
+#pragma unroll 8
+  for (int s = 0; s < T; ++s) {
+    uint32_t sw[W];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const uint4 a4 = tb[s * NV + q];
+      sw[4 * q + 0] = a4.x;
+      sw[4 * q + 1] = a4.y;
+      sw[4 * q + 2] = a4.z;
+      sw[4 * q + 3] = a4.w;
+    }
+    bool dom = GID ? (sw[M - 1] != gidv) : true;
+#pragma unroll
+    for (int j = SKIP0 ? 1 : 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
+    if (C1) dom = dom && (c1tb[s] <= c1v);
+    const int r1 = (int)sw[M];
+    best = dom ? max(best, r1) : best;
+  }
+  return best;
+}
+
 // Breadth-first walk by path length from the node set `f` (level `level`): table[i * DLD + col] = last level at which
 // i is reached = longest path.  Each thread walks its own source; the frontier is a 128-bit set in registers.
 template <int T, int DLD>
@@ -174,9 +261,9 @@ __device__ __forceinline__ int maxplus_packed(const int8_t* row, const int16_t* 
   return max((int)(int16_t)(m & 0xFFFFu), (int)(int16_t)(m >> 16));
 }
 
-template <int M, int T>
-__global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
-                                                       int* errflag, long long* trace) {
+template <int M, int T, bool SEG>
+__global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* rec, int nblocks, int* __restrict__ rankS, int* ticket,
+                                                                 int* errflag, long long* trace, RankSeg sg) {
   // optional per-block time stamps (DMO_RANK_TRACE=<file>): 16 x globaltimer ns, then 16 x clock64, see scripts/rank_trace.py
 #define RANK_TRACE(slot)                                                         \
   if (trace != nullptr && tid == 0) {                                            \
@@ -204,6 +291,11 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
   __shared__ __align__(16) int8_t sD[T * DLD];
   __shared__ __align__(16) int8_t sE[T * DLD];
   __shared__ int sh_blk;
+  // segmented order only: objective-1 ids of the own block and of the streamed tiles, cached tile bands
+  __shared__ uint32_t c1own[SEG ? T : 1];
+  __shared__ uint32_t c1t[SEG ? 2 * T : 1];
+  __shared__ uint16_t sq16[SEG ? RANK_SEG_MAXT : 1];
+  __shared__ uint32_t sh_band[SEG ? 2 * NW : 1];
 
   const int tid = threadIdx.x;
 
@@ -236,8 +328,27 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
       }
     }
     const uint32_t gidv = v[M - 1];
+    uint32_t c1v = 0u;
+    if (SEG) {
+      c1v = sg.c1rec[i];
+      c1own[tid] = c1v;
+      const uint32_t q = min(v[0] >> sg.qshift, 255u);
+      const uint32_t qlo = __reduce_min_sync(0xFFFFFFFFu, q), qhi = __reduce_max_sync(0xFFFFFFFFu, q);
+      if ((tid & 31) == 0) {
+        sh_band[tid >> 5] = qlo;
+        sh_band[NW + (tid >> 5)] = qhi;
+      }
+      for (int t = tid; t < b - 1; t += T) sq16[t] = sg.tile_q[t];  // bands of every tile this block may stream
+    }
     __syncthreads();
     const uint32_t first_gid = reinterpret_cast<const uint32_t*>(&tile[0])[M - 1];  // group of the block's first record
+    uint32_t bq_lo = 0u, bq_hi = 255u;
+    int kc = 0;  // tiles >= kc may hold sources of the block's own segment(s): full test incl. objective 1, never skipped
+    if (SEG) {
+      bq_lo = min(min(sh_band[0], sh_band[1]), min(sh_band[2], sh_band[3]));
+      bq_hi = max(max(sh_band[NW], sh_band[NW + 1]), max(sh_band[NW + 2], sh_band[NW + 3]));
+      kc = (int)(sg.seg_start[c1own[0] >> sg.sshift] / (uint32_t)T);
+    }
 
     // ---- in-block successor bitmasks: succ[j] = { i > j in this block : j dominates i }; independent of any rank
     {
@@ -251,6 +362,7 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
           bool dom = (w * 32 + s > tid) && (sp[M - 1] != gidv);
 #pragma unroll
           for (int j = 0; j < M - 1; ++j) dom = dom && (v[j] <= sp[j]);
+          if (SEG) dom = dom && (c1v <= c1own[w * 32 + s]);  // objective 1 is not implied by the order inside a segment
           m |= (dom ? 1u : 0u) << s;
         }
         sm[w] = m;
@@ -292,6 +404,7 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
           pv[4 * q + 3] = a4.w;
         }
       }
+      const uint32_t pc1 = SEG ? sg.c1rec[ps] : 0u;
       uint32_t pm[NW];
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
@@ -302,6 +415,7 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
           bool dom = (sp[M - 1] != pv[M - 1]);
 #pragma unroll
           for (int j = 0; j < M - 1; ++j) dom = dom && (pv[j] <= sp[j]);
+          if (SEG) dom = dom && (pc1 <= c1own[w * 32 + s2]);
           m |= (dom ? 1u : 0u) << s2;
         }
         pm[w] = m;
@@ -313,18 +427,29 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
     int best = 0;
     // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
     RANK_TRACE(1);
-    // Software pipelined: the record of tile k+1 (static words and, speculatively, its rank word) is requested before
-    // the pair tests of tile k, and the shared tile is double buffered, so a block that is behind the wavefront pays
-    // one barrier and the pair tests per tile, not an L2 round trip on top; a block at the wavefront only waits for
-    // the rank word.
+    // Software pipelined: the record of the next tile (static words and, speculatively, its rank word) is requested
+    // before the pair tests of the current one, and the shared tile is double buffered, so a block that is behind the
+    // wavefront pays one barrier and the pair tests per tile, not an L2 round trip on top; a block at the wavefront
+    // only waits for the rank word.  In the segmented order whole tiles are skipped (see RankSeg).
     {
+      auto next_tile = [&](int k) {
+        if (SEG) {
+          const int lim = min(kc, b - 1);
+          while (k < lim && (uint32_t)(sq16[k] & 0xFFu) > bq_hi) ++k;  // every source word above the block's band
+        }
+        return k;
+      };
       uint4 cur[NV];
-      if (b > 1) {
-        const uint4* src = reinterpret_cast<const uint4*>(rec + (int64_t)tid * W);
+      uint32_t cur_c1 = 0u;
+      int k = next_tile(0);
+      if (k < b - 1) {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
 #pragma unroll
         for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
+        if (SEG && k >= kc) cur_c1 = sg.c1rec[(int64_t)k * T + tid];
       }
-      for (int k = 0; k < b - 1; ++k) {
+      int pb = 0;  // stream buffer parity
+      while (k < b - 1) {
         if (k == b - 2) RANK_TRACE(2);
         {
           const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
@@ -338,59 +463,38 @@ __global__ void __launch_bounds__(T, 5) rank_chain_kernel(uint32_t* rec, int nbl
             }
           }
         }
-        uint4* tb = (DBUF && (k & 1)) ? tile2 : tile;
+        uint4* tb = (DBUF && pb) ? tile2 : tile;
         if (!DBUF) __syncthreads();  // single buffer: everyone must be done with the previous tile
 #pragma unroll
         for (int q = 0; q < NV; ++q) tb[tid * NV + q] = cur[q];
-        // Group ids grow along the lexicographic order, so a tile whose last record is in an earlier group than this
-        // block's first record holds no copy of any of this block's vectors: the "not identical" test can be dropped
-        // (one compare per pair less).  The owner of the tile's last record votes through the tile barrier.
+        const bool c1need = SEG && k >= kc;
+        if (c1need) c1t[pb * T + tid] = cur_c1;
+        // Group ids grow along the order, so a tile whose last record is in an earlier group than this block's first
+        // record holds no copy of any of this block's vectors: the "not identical" test can be dropped (one compare
+        // per pair less).  The owner of the tile's last record votes through the tile barrier.
         const bool last_shares = (tid == T - 1) && (word_of(cur[(M - 1) / 4], (M - 1) % 4) >= first_gid);
-        if (k + 1 < b - 1) {  // request the next record now; it is consumed after this tile's pair tests
-          const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)(k + 1) * T + tid) * W);
+        const int kn = next_tile(k + 1);
+        if (kn < b - 1) {  // request the next record now; it is consumed after this tile's pair tests
+          const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)kn * T + tid) * W);
 #pragma unroll
           for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
+          if (SEG && kn >= kc) cur_c1 = sg.c1rec[(int64_t)kn * T + tid];
         }
-        // one barrier per tile: buffer (k & 1) is rewritten two iterations later, after barrier k+1
+        // one barrier per tile: a stream buffer is rewritten two tiles later, after the next tile's barrier
         const bool may_share_group = __syncthreads_or(last_shares ? 1 : 0) != 0;
         if (k == b - 2) RANK_TRACE(3);
-        if (!may_share_group) {
-#pragma unroll 8
-          for (int s = 0; s < T; ++s) {
-            uint32_t sw[W];
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-              uint4 a4 = tb[s * NV + q];
-              sw[4 * q + 0] = a4.x;
-              sw[4 * q + 1] = a4.y;
-              sw[4 * q + 2] = a4.z;
-              sw[4 * q + 3] = a4.w;
-            }
-            bool dom = true;
-#pragma unroll
-            for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
-            const int r1 = (int)sw[M];
-            best = dom ? max(best, r1) : best;
-          }
+        const uint32_t* c1tb = c1t + (SEG ? pb * T : 0);
+        if (c1need) {
+          best = rank_pair_tests<M, W, NV, T, false, true, true>(tb, c1tb, v, gidv, c1v, best);
+        } else if (SEG && (uint32_t)(sq16[k] >> 8) < bq_lo) {  // every source word below the block's band
+          best = may_share_group ? rank_pair_tests<M, W, NV, T, true, true, false>(tb, c1tb, v, gidv, c1v, best)
+                                 : rank_pair_tests<M, W, NV, T, true, false, false>(tb, c1tb, v, gidv, c1v, best);
         } else {
-#pragma unroll 8
-          for (int s = 0; s < T; ++s) {
-            uint32_t sw[W];
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-              uint4 a4 = tb[s * NV + q];
-              sw[4 * q + 0] = a4.x;
-              sw[4 * q + 1] = a4.y;
-              sw[4 * q + 2] = a4.z;
-              sw[4 * q + 3] = a4.w;
-            }
-            bool dom = (sw[M - 1] != gidv);
-#pragma unroll
-            for (int j = 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
-            const int r1 = (int)sw[M];
-            best = dom ? max(best, r1) : best;
-          }
+          best = may_share_group ? rank_pair_tests<M, W, NV, T, false, true, false>(tb, c1tb, v, gidv, c1v, best)
+                                 : rank_pair_tests<M, W, NV, T, false, false, false>(tb, c1tb, v, gidv, c1v, best);
         }
+        k = kn;
+        pb ^= 1;
       }
     }
     // ---- in-block resolution, part 1 (before the predecessor's ranks are needed):
@@ -667,8 +771,8 @@ __global__ void copy_u32_to_i32_kernel(const uint32_t* __restrict__ a, int64_t n
   if (p < n) out[p] = (int32_t)a[p];
 }
 
-template <int M>
-int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* ticket, int* errflag) {
+template <int M, bool SEG>
+int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* ticket, int* errflag, const RankSeg& sg) {
   // debugging aid: DMO_RANK_TRACE=<file> dumps 32 int64 time stamps per block of the chain kernel
   DevBuf<long long> trace;
   const char* trace_path = getenv("DMO_RANK_TRACE");
@@ -677,7 +781,7 @@ int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* tick
     DMO_CUDA(cudaMemsetAsync(trace.p, 0, (size_t)nblocks * 32 * sizeof(long long), ctx->stream));
   }
   int occ = 0;
-  DMO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_chain_kernel<M, RANK_T>, RANK_T, 0));
+  DMO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_chain_kernel<M, RANK_T, SEG>, RANK_T, 0));
   if (occ < 1) occ = 1;
   // fewer co-resident CTAs per SM shorten the serial chain (the block on the critical path shares its SM's issue
   // slots with the others); DMO_RANK_OCC overrides for tuning
@@ -687,7 +791,7 @@ int launch_chain(dmo_ctx* ctx, uint32_t* rec, int nblocks, int* rankS, int* tick
   int nctas = nblocks < occ * ctx->sm_count ? nblocks : occ * ctx->sm_count;
   {
     ProfileScope ps(ctx, "rank_chain");
-    DMO_LAUNCH((rank_chain_kernel<M, RANK_T>), nctas, RANK_T, 0, rec, nblocks, rankS, ticket, errflag, trace.p);
+    DMO_LAUNCH((rank_chain_kernel<M, RANK_T, SEG>), nctas, RANK_T, 0, rec, nblocks, rankS, ticket, errflag, trace.p, sg);
     DMO_CHECK_LAUNCH();
   }
   if (trace.p) {
@@ -752,12 +856,33 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
   DMO_TRY(prim_iota_u32(ctx, permA.p, n));
   uint32_t* pin = permA.p;
   uint32_t* pout = permB.p;
-  for (int j = M - 1; j >= 0; --j) {
-    DMO_LAUNCH(gather_u32_kernel, g, 256, 0, R.p + (size_t)j * n, pin, n, keyA.p);
-    DMO_TRY(prim_sort_pairs_u32(ctx, keyA.p, keyB.p, pin, pout, n, 0, bits));
+  // The chain kernel for two and three objectives takes the segmented order (RankSeg): key = (segment of objective 1,
+  // objective 2, ..., objective M, objective 1).  Everything else keeps the plain lexicographic order.
+  const int64_t nblocks_est = ceil_div(n, RANK_T);
+  int segbits = 5;  // 32 segments over the dense id range of objective 1
+  if (const char* e = getenv("DMO_RANK_SEGBITS")) segbits = atoi(e);
+  if (segbits < 1) segbits = 1;
+  const bool use_seg = !flags_only && M <= 3 && nblocks_est >= 16 && nblocks_est <= RANK_SEG_MAXT && bits > segbits + 7 &&
+                       getenv("DMO_RANK_NOSEG") == nullptr;
+  const int sshift = bits - segbits;
+  auto sort_pass = [&](const uint32_t* col, int shift, int nbits) -> int {
+    if (shift == 0) {
+      DMO_LAUNCH(gather_u32_kernel, g, 256, 0, col, pin, n, keyA.p);
+    } else {
+      DMO_LAUNCH(seg_key_kernel, g, 256, 0, col, pin, n, shift, keyA.p);
+    }
+    DMO_TRY(prim_sort_pairs_u32(ctx, keyA.p, keyB.p, pin, pout, n, 0, nbits));
     uint32_t* t = pin;
     pin = pout;
     pout = t;
+    return DMO_OK;
+  };
+  if (use_seg) {
+    DMO_TRY(sort_pass(R.p, 0, bits));  // least significant: objective 1 itself
+    for (int j = M - 1; j >= 1; --j) DMO_TRY(sort_pass(R.p + (size_t)j * n, 0, bits));
+    DMO_TRY(sort_pass(R.p, sshift, bits - sshift));  // most significant: the segment
+  } else {
+    for (int j = M - 1; j >= 0; --j) DMO_TRY(sort_pass(R.p + (size_t)j * n, 0, bits));
   }
   const uint32_t* perm = pin;
 
@@ -799,14 +924,40 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
     DMO_CHECK_LAUNCH();
     return DMO_OK;
   }
-  switch (M) {
-    case 2: DMO_TRY(launch_chain<2>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 3: DMO_TRY(launch_chain<3>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 4: DMO_TRY(launch_chain<4>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 5: DMO_TRY(launch_chain<5>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 6: DMO_TRY(launch_chain<6>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    case 7: DMO_TRY(launch_chain<7>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
-    default: DMO_TRY(launch_chain<8>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag)); break;
+  RankSeg sg;
+  DevBuf<uint32_t> c1rec, seg_start;
+  DevBuf<uint16_t> tile_q;
+  if (use_seg) {
+    const int nseg = (int)(((uint32_t)(n - 1)) >> sshift) + 1;
+    int qshift = bits - 8;
+    if (qshift < 0) qshift = 0;
+    DMO_TRY(c1rec.alloc(ctx, npad));
+    DMO_TRY(seg_start.alloc(ctx, nseg + 1));
+    DMO_TRY(tile_q.alloc(ctx, nblocks));
+    DMO_LAUNCH(seg_c1_kernel, (unsigned)ceil_div(npad, 256), 256, 0, R.p, perm, n, npad, c1rec.p);
+    DMO_LAUNCH(seg_start_kernel, (unsigned)ceil_div(nseg + 1, 128), 128, 0, c1rec.p, n, sshift, nseg, seg_start.p);
+    DMO_LAUNCH(seg_tile_band_kernel, (unsigned)ceil_div(nblocks * 32, 256), 256, 0, rec.p, (int)nblocks, RANK_T, qshift, tile_q.p);
+    DMO_CHECK_LAUNCH();
+    sg.c1rec = c1rec.p;
+    sg.seg_start = seg_start.p;
+    sg.tile_q = tile_q.p;
+    sg.sshift = sshift;
+    sg.qshift = qshift;
+    if (M == 2) {
+      DMO_TRY((launch_chain<2, true>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg)));
+    } else {
+      DMO_TRY((launch_chain<3, true>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg)));
+    }
+  } else {
+    switch (M) {
+      case 2: DMO_TRY((launch_chain<2, false>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg))); break;
+      case 3: DMO_TRY((launch_chain<3, false>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg))); break;
+      case 4: DMO_TRY((launch_chain<4, false>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg))); break;
+      case 5: DMO_TRY((launch_chain<5, false>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg))); break;
+      case 6: DMO_TRY((launch_chain<6, false>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg))); break;
+      case 7: DMO_TRY((launch_chain<7, false>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg))); break;
+      default: DMO_TRY((launch_chain<8, false>(ctx, rec.p, (int)nblocks, rankS.p, ticket, errflag, sg))); break;
+    }
   }
   DMO_LAUNCH(scatter_rank_kernel, g, 256, 0, rankS.p, perm, n, d_rank);
   DMO_CHECK_LAUNCH();
