@@ -121,7 +121,7 @@ __device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c ==
 // ------------------------------------------------------------------------------------------------ segmented order (M <= 3)
 // Any linear extension of the dominance order works for the chain recurrence.  Instead of the plain lexicographic
 // order the points are ordered by (segment of objective 1, objective 2, ..., objective M, objective 1), a segment
-// being 1/32 of the dense id range of objective 1.  Sources in an earlier segment have a smaller objective-1 id than
+// being a run of 1024 dense ids of objective 1 (at most 128 segments).  Sources in an earlier segment have a smaller objective-1 id than
 // every target, and inside a segment the tiles are sorted by the first compare word, so for a target block with the
 // band [blo, bhi] of that word a whole earlier tile is
 //   * skipped        if its smallest word is > bhi (nothing in it can dominate anything in the block),
@@ -859,7 +859,8 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
   // The chain kernel for two and three objectives takes the segmented order (RankSeg): key = (segment of objective 1,
   // objective 2, ..., objective M, objective 1).  Everything else keeps the plain lexicographic order.
   const int64_t nblocks_est = ceil_div(n, RANK_T);
-  int segbits = 5;  // 32 segments over the dense id range of objective 1
+  int segbits = bits - 10;  // segments of 1024 dense ids of objective 1 (8 blocks), at most 128 segments
+  if (segbits > 7) segbits = 7;
   if (const char* e = getenv("DMO_RANK_SEGBITS")) segbits = atoi(e);
   if (segbits < 1) segbits = 1;
   const bool use_seg = !flags_only && M <= 3 && nblocks_est >= 16 && nblocks_est <= RANK_SEG_MAXT && bits > segbits + 7 &&
