@@ -184,7 +184,8 @@ __global__ void seg_tile_band_kernel(const uint32_t* __restrict__ rec, int nbloc
 template <int M, int W, int NV, int T, bool SKIP0, bool GID, bool C1>
 __device__ __forceinline__ int rank_pair_tests(const uint4* tb, const uint32_t* c1tb, const uint32_t* v, uint32_t gidv,
                                                uint32_t c1v, int best) {
-#pragma unroll 8
+  int acc[4] = {best, 0, 0, 0};  // four independent max chains (the predicated max is the only loop-carried dependency)
+#pragma unroll 16
   for (int s = 0; s < T; ++s) {
     uint32_t sw[W];
 #pragma unroll
@@ -200,9 +201,9 @@ __device__ __forceinline__ int rank_pair_tests(const uint4* tb, const uint32_t* 
     for (int j = SKIP0 ? 1 : 0; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
     if (C1) dom = dom && (c1tb[s] <= c1v);
     const int r1 = (int)sw[M];
-    best = dom ? max(best, r1) : best;
+    acc[s & 3] = dom ? max(acc[s & 3], r1) : acc[s & 3];
   }
-  return best;
+  return max(max(acc[0], acc[1]), max(acc[2], acc[3]));
 }
 
 // Breadth-first walk by path length from the node set `f` (level `level`): table[i * DLD + col] = last level at which

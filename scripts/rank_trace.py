@@ -40,7 +40,10 @@ def main():
     names = [("tables (0->1)", 0, 1), ("bulk up to tile b-3 (1->2)", 1, 2), ("wait+load tile b-2 (2->3)", 2, 3), ("tile b-2 pairs + fold (3->4)", 3, 4),
              ("wait predecessor (4->5)", 4, 5), ("resolve + publish (5->6)", 5, 6)]
     for nm, a, b in names:
-        d = clk(a, b)
+        ok = (t[sel, a] > 0) & (t[sel, b] > 0)  # a skipped tile leaves its stamps empty
+        d = clk(a, b)[ok]
+        if d.size == 0:
+            continue
         print(f"  {nm:32s} SM cycles: mean {d.mean():9.0f}  median {np.median(d):9.0f}  p90 {np.percentile(d, 90):9.0f}")
     # how long after the predecessor's publish does this block see it, and publish itself (global ns)
     see = g[1:, 5] - pub[:-1]
@@ -49,8 +52,10 @@ def main():
     print(f"  predecessor publish -> seen here: mean {see[sel].mean():.0f} ns (median {np.median(see[sel]):.0f});  seen -> own publish: mean {own[sel].mean():.0f} ns")
     print(f"  fraction of blocks already waiting when the predecessor published: {ready_before:.2f}")
     # tile b-2: publish of b-2 -> this block has it in shared memory
-    lag2 = g[2:, 3] - pub[:-2]
-    print(f"  publish(b-2) -> tile b-2 loaded here: mean {lag2[sel].mean():.0f} ns (median {np.median(lag2[sel]):.0f})")
+    ok3 = t[2:, 3] > 0
+    lag2 = (g[2:, 3] - pub[:-2])[ok3]
+    if lag2.size:
+        print(f"  publish(b-2) -> tile b-2 loaded here: mean {lag2.mean():.0f} ns (median {np.median(lag2):.0f})")
     print("  blocks per SM:", np.bincount(t[:, 7].astype(int)).max())
     dump_gaps(g, pub)
     if t[:, 8].any():  # grid phase stamps (M <= 3): 8 query start, 9 query end, 10 tree update fenced, 11 done flag set
