@@ -385,9 +385,9 @@ def run_ours(args):
         ach = flops_per_launch / avg_s / 1e12
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         # DRAM traffic of one gp_var launch from the committed ncu --set full capture of this shape
-        # (profiles/r1_gp_var_tc2_kernel_details.txt: dram__bytes_read.sum 22.094 GB + dram__bytes_write.sum 7.5 MB);
+        # (profiles/r1_gp_var_tc2_kernel_details.txt: dram__bytes_read.sum 22.554 GB + dram__bytes_write.sum 7.6 MB);
         # null for any other shape / precision / shard size.
-        traffic = 22.093851e9 + 7.519744e6 if (prec == L.GP_TENSOR and world == 1 and (pop, d, M, N) == (65536, 30, 3, 4096)) else None
+        traffic = 22.553779e9 + 7.566592e6 if (prec == L.GP_TENSOR and world == 1 and (pop, d, M, N) == (65536, 30, 3, 4096)) else None
         roof = {"bound": "tensor", "kernel": "gp_var (V = L^-1 K_*^T, column sums of V^2)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "peak_kind": f"bf16 dense, sustained, {peak_kind}", "avg_launch_ms": avg_s * 1e3,
                 "flops_per_launch": flops_per_launch, "arithmetic": "float64 CUDA cores" if prec == L.GP_FP64 else "tcgen05 split-fp16"}
