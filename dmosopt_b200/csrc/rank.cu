@@ -114,6 +114,14 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
 __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c == 0 ? a.x : c == 1 ? a.y : c == 2 ? a.z : a.w; }
 
 // The rank word of a record (rank + 1, 0 = not yet final) is its own ready flag: a 4-byte store is atomic and carries
@@ -128,11 +136,16 @@ __device__ __forceinline__ uint32_t word_of(const uint4& a, int c) { return c ==
 //   * "fast"         if its largest word is < blo (the first compare is known to pass and is dropped),
 //   * tested in full otherwise (about one tile per segment) and, with the extra objective-1 compare, for the tiles that
 //     may share a segment with the block.
+// For three objectives a "fast" tile leaves a single condition, word_1(source) <= word_1(target); every block therefore
+// also publishes its records as a staircase -- sorted by that word, with the running maximum of rank + 1 -- and a target
+// resolves a fast tile with one 7-step binary search instead of 128 pair tests (two objectives: the tile maximum).
 // Bands are compared on 8-bit floor-quantised words (conservative in both directions) held in shared memory.
 struct RankSeg {
   const uint32_t* c1rec = nullptr;      // [npad] objective-1 id per position (0xFFFFFFFF for the padding)
   const uint32_t* seg_start = nullptr;  // [nseg + 1] first position whose segment is >= s
   const uint16_t* tile_q = nullptr;     // [nblocks] low byte = min, high byte = max of the quantised first compare word
+  unsigned long long* stair = nullptr;  // [npad] per tile: entry t = (t-th smallest last compare word of the tile, low 32
+                                        // bits; max (rank + 1) over the t+1 records with the smallest words, high 32 bits)
   int sshift = 0;                       // id1 >> sshift = segment
   int qshift = 0;                       // word >> qshift = 8-bit band coordinate (clamped to 255)
 };
@@ -297,6 +310,7 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
   __shared__ uint32_t c1t[SEG ? 2 * T : 1];
   __shared__ uint16_t sq16[SEG ? RANK_SEG_MAXT : 1];
   __shared__ uint32_t sh_band[SEG ? 2 * NW : 1];
+  __shared__ uint32_t skey[SEG ? T : 1];  // the block's last compare words in ascending order (staircase keys)
 
   const int tid = threadIdx.x;
 
@@ -345,10 +359,33 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
     const uint32_t first_gid = reinterpret_cast<const uint32_t*>(&tile[0])[M - 1];  // group of the block's first record
     uint32_t bq_lo = 0u, bq_hi = 255u;
     int kc = 0;  // tiles >= kc may hold sources of the block's own segment(s): full test incl. objective 1, never skipped
+    int kg = 0;  // tiles >= kg may hold a copy of one of the block's vectors ("not identical" test needed)
+    int spos = tid;  // position of this record in the block's staircase order
     if (SEG) {
       bq_lo = min(min(sh_band[0], sh_band[1]), min(sh_band[2], sh_band[3]));
       bq_hi = max(max(sh_band[NW], sh_band[NW + 1]), max(sh_band[NW + 2], sh_band[NW + 3]));
       kc = (int)(sg.seg_start[c1own[0] >> sg.sshift] / (uint32_t)T);
+      {  // first position whose group id is >= the block's first group id (group ids grow along the order)
+        int64_t lo = 0, hi = (int64_t)b * T;
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (rec[mid * W + (M - 1)] < first_gid) lo = mid + 1; else hi = mid;
+        }
+        kg = (int)(lo / T);
+      }
+      if (M == 3) {  // rank of the own last compare word inside the block (ties by position): 128 compares per thread
+        const uint32_t key = v[1];
+        int cnt = 0;
+#pragma unroll 8
+        for (int s = 0; s < T; ++s) {
+          const uint32_t ks = reinterpret_cast<const uint32_t*>(&tile[s * NV])[1];
+          cnt += (ks < key || (ks == key && s < tid)) ? 1 : 0;
+        }
+        spos = cnt;
+        skey[spos] = key;
+      } else {
+        skey[tid] = 0u;
+      }
     }
 
     // ---- in-block successor bitmasks: succ[j] = { i > j in this block : j dominates i }; independent of any rank
@@ -428,10 +465,10 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
     int best = 0;
     // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
     RANK_TRACE(1);
-    // Software pipelined: the record of the next tile (static words and, speculatively, its rank word) is requested
-    // before the pair tests of the current one, and the shared tile is double buffered, so a block that is behind the
-    // wavefront pays one barrier and the pair tests per tile, not an L2 round trip on top; a block at the wavefront
-    // only waits for the rank word.  In the segmented order whole tiles are skipped (see RankSeg).
+    // Software pipelined: the data of the next tile (static words and, speculatively, its rank word -- or its staircase
+    // entry) is requested before the current tile is evaluated, and the shared tile is double buffered, so a block that is
+    // behind the wavefront pays one barrier and the evaluation per tile, not an L2 round trip on top; a block at the
+    // wavefront only waits for the rank word.  In the segmented order whole tiles are skipped (see RankSeg).
     {
       auto next_tile = [&](int k) {
         if (SEG) {
@@ -440,52 +477,89 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
         }
         return k;
       };
+      // tile kinds: 2 = staircase (earlier segment, every first word below the band, no copy of a block vector),
+      //             1 = pair tests incl. objective 1 (may share a segment), 0 = pair tests
+      auto kind_of = [&](int k) {
+        if (!SEG) return 0;
+        if (k >= kc) return 1;
+        return ((uint32_t)(sq16[k] >> 8) < bq_lo && k < kg) ? 2 : 0;
+      };
       uint4 cur[NV];
       uint32_t cur_c1 = 0u;
-      int k = next_tile(0);
-      if (k < b - 1) {
-        const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
+      unsigned long long cur_st = 0ull;
+      auto request = [&](int k, int kind) {
+        if (SEG && kind == 2) {
+          cur_st = ld_relaxed_u64(sg.stair + (int64_t)k * T + tid);
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
 #pragma unroll
-        for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
-        if (SEG && k >= kc) cur_c1 = sg.c1rec[(int64_t)k * T + tid];
-      }
+          for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
+          if (SEG && kind == 1) cur_c1 = sg.c1rec[(int64_t)k * T + tid];
+        }
+      };
+      int k = next_tile(0);
+      int kind = k < b - 1 ? kind_of(k) : 0;
+      if (k < b - 1) request(k, kind);
       int pb = 0;  // stream buffer parity
       while (k < b - 1) {
         if (k == b - 2) RANK_TRACE(2);
         {
-          const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
           unsigned spins = 0;
-          while (word_of(cur[RQ], RC) == 0u) {  // not final yet: this block has caught up with the wavefront
-            __nanosleep(spins < 8 ? 100 : 400);
-            cur[RQ] = ld_relaxed_v4(src + RQ);
-            if ((++spins & 0xFFu) == 0u && (spins > (1u << 21) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
-              atomicExch(errflag, 1);
-              break;
+          if (SEG && kind == 2) {
+            const unsigned long long* src = sg.stair + (int64_t)k * T + tid;
+            while ((cur_st >> 32) == 0ull) {  // the owner has not published its staircase yet
+              __nanosleep(spins < 8 ? 100 : 400);
+              cur_st = ld_relaxed_u64(src);
+              if ((++spins & 0xFFu) == 0u && (spins > (1u << 21) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
+                atomicExch(errflag, 1);
+                break;
+              }
+            }
+          } else {
+            const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)k * T + tid) * W);
+            while (word_of(cur[RQ], RC) == 0u) {  // not final yet: this block has caught up with the wavefront
+              __nanosleep(spins < 8 ? 100 : 400);
+              cur[RQ] = ld_relaxed_v4(src + RQ);
+              if ((++spins & 0xFFu) == 0u && (spins > (1u << 21) || ld_relaxed_u32((const uint32_t*)errflag) != 0u)) {
+                atomicExch(errflag, 1);
+                break;
+              }
             }
           }
         }
         uint4* tb = (DBUF && pb) ? tile2 : tile;
         if (!DBUF) __syncthreads();  // single buffer: everyone must be done with the previous tile
+        if (SEG && kind == 2) {
+          reinterpret_cast<unsigned long long*>(tb)[tid] = cur_st;
+        } else {
 #pragma unroll
-        for (int q = 0; q < NV; ++q) tb[tid * NV + q] = cur[q];
-        const bool c1need = SEG && k >= kc;
-        if (c1need) c1t[pb * T + tid] = cur_c1;
+          for (int q = 0; q < NV; ++q) tb[tid * NV + q] = cur[q];
+          if (SEG && kind == 1) c1t[pb * T + tid] = cur_c1;
+        }
         // Group ids grow along the order, so a tile whose last record is in an earlier group than this block's first
         // record holds no copy of any of this block's vectors: the "not identical" test can be dropped (one compare
         // per pair less).  The owner of the tile's last record votes through the tile barrier.
-        const bool last_shares = (tid == T - 1) && (word_of(cur[(M - 1) / 4], (M - 1) % 4) >= first_gid);
+        const bool last_shares = !(SEG && kind == 2) && (tid == T - 1) && (word_of(cur[(M - 1) / 4], (M - 1) % 4) >= first_gid);
         const int kn = next_tile(k + 1);
-        if (kn < b - 1) {  // request the next record now; it is consumed after this tile's pair tests
-          const uint4* src = reinterpret_cast<const uint4*>(rec + ((int64_t)kn * T + tid) * W);
-#pragma unroll
-          for (int q = 0; q < NV; ++q) cur[q] = ld_relaxed_v4(src + q);
-          if (SEG && kn >= kc) cur_c1 = sg.c1rec[(int64_t)kn * T + tid];
-        }
+        const int kind_n = kn < b - 1 ? kind_of(kn) : 0;
+        if (kn < b - 1) request(kn, kind_n);  // consumed after this tile's evaluation
         // one barrier per tile: a stream buffer is rewritten two tiles later, after the next tile's barrier
         const bool may_share_group = __syncthreads_or(last_shares ? 1 : 0) != 0;
         if (k == b - 2) RANK_TRACE(3);
         const uint32_t* c1tb = c1t + (SEG ? pb * T : 0);
-        if (c1need) {
+        if (SEG && kind == 2) {
+          const uint2* st = reinterpret_cast<const uint2*>(tb);  // .x = key (ascending), .y = running max of rank + 1
+          if (M == 3) {
+            int idx = 0;  // number of keys <= v[1]
+#pragma unroll
+            for (int step = T / 2; step >= 1; step >>= 1)
+              if (st[idx + step - 1].x <= v[1]) idx += step;
+            if (idx < T && st[idx].x <= v[1]) ++idx;  // T is a power of two: the steps cover T - 1 positions
+            if (idx > 0) best = max(best, (int)st[idx - 1].y);
+          } else {
+            best = max(best, (int)st[T - 1].y);  // two objectives: every record of the tile dominates the block
+          }
+        } else if (kind == 1) {
           best = rank_pair_tests<M, W, NV, T, false, true, true>(tb, c1tb, v, gidv, c1v, best);
         } else if (SEG && (uint32_t)(sq16[k] >> 8) < bq_lo) {  // every source word below the block's band
           best = may_share_group ? rank_pair_tests<M, W, NV, T, true, true, false>(tb, c1tb, v, gidv, c1v, best)
@@ -495,6 +569,7 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
                                  : rank_pair_tests<M, W, NV, T, false, false, false>(tb, c1tb, v, gidv, c1v, best);
         }
         k = kn;
+        kind = kind_n;
         pb ^= 1;
       }
     }
@@ -555,6 +630,24 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
     st_relaxed_u32(rec + i * W + M, (uint32_t)(r + 1));  // publish: the rank word doubles as the ready flag
     rankS[i] = r;
     RANK_TRACE(6);
+    if (SEG) {
+      // staircase of this tile for the blocks of later segments (off the critical path: they are at least a segment
+      // away): running maximum of rank + 1 in ascending order of the last compare word; key and value travel in one
+      // 64-bit store, a non-zero value marks the entry as published
+      __syncthreads();
+      sh_r1[spos] = r + 1;
+      __syncthreads();
+      int val = sh_r1[tid];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, val, off);
+        if ((tid & 31) >= off) val = max(val, o);
+      }
+      if ((tid & 31) == 31) sh_band[tid >> 5] = (uint32_t)val;
+      __syncthreads();
+      for (int w = 0; w < (tid >> 5); ++w) val = max(val, (int)sh_band[w]);
+      st_relaxed_u64(sg.stair + i, ((unsigned long long)(uint32_t)val << 32) | (unsigned long long)skey[tid]);
+    }
     __syncthreads();
   }
 #undef RANK_TRACE
@@ -929,7 +1022,10 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
   RankSeg sg;
   DevBuf<uint32_t> c1rec, seg_start;
   DevBuf<uint16_t> tile_q;
+  DevBuf<unsigned long long> stair;
   if (use_seg) {
+    DMO_TRY(stair.alloc(ctx, npad));
+    DMO_CUDA(cudaMemsetAsync(stair.p, 0, (size_t)npad * sizeof(unsigned long long), ctx->stream));
     const int nseg = (int)(((uint32_t)(n - 1)) >> sshift) + 1;
     int qshift = bits - 8;
     if (qshift < 0) qshift = 0;
@@ -943,6 +1039,7 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
     sg.c1rec = c1rec.p;
     sg.seg_start = seg_start.p;
     sg.tile_q = tile_q.p;
+    sg.stair = stair.p;
     sg.sshift = sshift;
     sg.qshift = qshift;
     if (M == 2) {
