@@ -463,6 +463,36 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
     __syncthreads();
 
     int best = 0;
+    // ---- the last streamed tile (block b-2) is the second serial dependency: its ranks arrive one link before this
+    // block's turn.  Its dominance pattern does not depend on ranks, so it is evaluated now into a 128-bit mask per
+    // thread (kept in the successor-mask storage, which the table walks no longer need); when the ranks arrive only a
+    // maximum over the set bits remains.
+    bool sparse_b2 = false;
+    if (SEG && b >= 2) {
+      const int64_t p2 = (int64_t)(b - 2) * T + tid;
+      tile2[tid] = *reinterpret_cast<const uint4*>(rec + p2 * W);  // static words; NV == 1 in the segmented kernels
+      c1t[T + tid] = sg.c1rec[p2];
+      __syncthreads();
+      uint32_t mk[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        uint32_t m = 0u;
+#pragma unroll 8
+        for (int s2 = 0; s2 < 32; ++s2) {
+          const uint32_t* sp = reinterpret_cast<const uint32_t*>(&tile2[w * 32 + s2]);
+          bool dom = (sp[M - 1] != gidv) && (c1t[T + w * 32 + s2] <= c1v);
+#pragma unroll
+          for (int j = 0; j < M - 1; ++j) dom = dom && (sp[j] <= v[j]);
+          m |= (dom ? 1u : 0u) << s2;
+        }
+        mk[w] = m;
+      }
+      sh_succ[tid] = make_uint4(mk[0], mk[1], mk[2], mk[3]);  // own slot only; all table walks finished at the barrier above
+      // the set-bit walk only pays when the masks are sparse (a converged population: few dominators per point);
+      // dense masks (random data) keep the pair tests, whose 128 steps pipeline better than a long dependent walk
+      sparse_b2 = __syncthreads_or((__popc(mk[0]) + __popc(mk[1]) + __popc(mk[2]) + __popc(mk[3])) > 8 ? 1 : 0) == 0;
+    }
+
     // ---- stream every earlier block except the predecessor: best = max over dominators of (rank + 1)
     RANK_TRACE(1);
     // Software pipelined: the data of the next tile (static words and, speculatively, its rank word -- or its staircase
@@ -478,9 +508,11 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
         return k;
       };
       // tile kinds: 2 = staircase (earlier segment, every first word below the band, no copy of a block vector),
-      //             1 = pair tests incl. objective 1 (may share a segment), 0 = pair tests
+      //             1 = pair tests incl. objective 1 (may share a segment), 0 = pair tests,
+      //             3 = the last tile: maximum over the precomputed dominance mask
       auto kind_of = [&](int k) {
         if (!SEG) return 0;
+        if (k == b - 2 && sparse_b2) return 3;  // sparse dominance mask precomputed above
         if (k >= kc) return 1;
         return ((uint32_t)(sq16[k] >> 8) < bq_lo && k < kg) ? 2 : 0;
       };
@@ -559,6 +591,15 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
           } else {
             best = max(best, (int)st[T - 1].y);  // two objectives: every record of the tile dominates the block
           }
+        } else if (SEG && kind == 3) {
+          const uint4 mk4 = sh_succ[tid];
+          const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            for (uint32_t mm = mk[w]; mm != 0u; mm &= mm - 1u) {
+              const int s2 = w * 32 + __ffs(mm) - 1;
+              best = max(best, (int)reinterpret_cast<const uint32_t*>(&tb[s2 * NV])[M]);
+            }
         } else if (kind == 1) {
           best = rank_pair_tests<M, W, NV, T, false, true, true>(tb, c1tb, v, gidv, c1v, best);
         } else if (SEG && (uint32_t)(sq16[k] >> 8) < bq_lo) {  // every source word below the block's band
