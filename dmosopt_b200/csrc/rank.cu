@@ -344,11 +344,14 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
     }
     const uint32_t gidv = v[M - 1];
     uint32_t c1v = 0u;
+    uint32_t wq_lo = 0u, wq_hi = 255u;  // band of this warp's 32 records (a quarter of the block's band)
     if (SEG) {
       c1v = sg.c1rec[i];
       c1own[tid] = c1v;
       const uint32_t q = min(v[0] >> sg.qshift, 255u);
       const uint32_t qlo = __reduce_min_sync(0xFFFFFFFFu, q), qhi = __reduce_max_sync(0xFFFFFFFFu, q);
+      wq_lo = qlo;
+      wq_hi = qhi;
       if ((tid & 31) == 0) {
         sh_band[tid >> 5] = qlo;
         sh_band[NW + (tid >> 5)] = qhi;
@@ -602,7 +605,9 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
             }
         } else if (kind == 1) {
           best = rank_pair_tests<M, W, NV, T, false, true, true>(tb, c1tb, v, gidv, c1v, best);
-        } else if (SEG && (uint32_t)(sq16[k] >> 8) < bq_lo) {  // every source word below the block's band
+        } else if (SEG && (uint32_t)(sq16[k] & 0xFFu) > wq_hi) {
+          // straddles the block's band but lies entirely above this warp's: nothing in it dominates these 32 records
+        } else if (SEG && (uint32_t)(sq16[k] >> 8) < wq_lo) {  // every source word below this warp's band
           best = may_share_group ? rank_pair_tests<M, W, NV, T, true, true, false>(tb, c1tb, v, gidv, c1v, best)
                                  : rank_pair_tests<M, W, NV, T, true, false, false>(tb, c1tb, v, gidv, c1v, best);
         } else {
