@@ -52,3 +52,10 @@ if os.environ.get("RANK_REAL_TRACE"):
         ok = (t[:, a] > 0) & (t[:, b] > 0)
         dd = (c[:, b] - c[:, a])[ok]
         print(f"  {nm:16s} cycles mean {dd.mean():10.0f} median {np.median(dd):10.0f} p90 {np.percentile(dd, 90):10.0f}")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import rank_trace
+    gg = g - g[:, 0].min()
+    rank_trace.dump_gaps(gg, pub, k=24)
+    link = np.diff(pub)
+    big = link > 8000
+    print("links > 8 us:", int(big.sum()), "of", len(link), "sum", link[big].sum() / 1e3, "us; blocks:", np.flatnonzero(big)[:40] + 1)
