@@ -173,7 +173,9 @@ class NSGA2(MOEA):
             st.population_parm = np.array(new, dtype=st.population_parm.dtype)
 
     def get_population_strategy(self):
-        return self.state.population_parm.copy(), self.state.population_obj.copy()
+        """NSGA2.py:238-242: copies, as in the reference.  The parameter matrix is copied into a recycled page-locked
+        buffer (no first-touch page faults on 8*pop*d bytes every generation); the result is an ordinary writable array."""
+        return _lib.copy_into_pooled(self.state.population_parm), self.state.population_obj.copy()
 
     def update_population_size(self):
         """NSGA2.py:244-266."""

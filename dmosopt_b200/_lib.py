@@ -355,6 +355,23 @@ def mirrored_readonly(a):
     return view, base
 
 
+def copy_into_pooled(a):
+    """Writable copy of ``a`` in a pooled page-locked buffer; a plain ``a.copy()`` when no CUDA context exists."""
+    a = np.asarray(a)
+    if a.nbytes < (1 << 20):
+        return a.copy()
+    try:
+        out = pinned_empty(a.shape, a.dtype)
+    except DmoError:
+        return a.copy()
+    m = mirror_ptr(a)
+    if m is not None:  # the DMA engine copies device -> pinned host faster than one host thread copies host -> host
+        memcpy(out, m, a.nbytes)
+    else:
+        np.copyto(out, a)
+    return out
+
+
 def pinned_like(a):
     """Page-locked copy of ``a`` (same dtype / values); falls back to a plain copy when no context exists yet."""
     a = np.asarray(a)

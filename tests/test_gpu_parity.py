@@ -343,6 +343,48 @@ def test_gp_predict_tensor_path(L, N, d, M, P):
     h.close()
 
 
+def test_device_mirror_semantics(L):
+    """The offspring matrix and NSGA2's population state are read-only host arrays mirrored on the device: handing them
+    back costs no host->device traffic, a copy is an ordinary writable array that takes the host-buffer path and gives
+    the same result, and replacing the state array turns the mirror off without changing results."""
+    import dmosopt_b200 as b2
+
+    rng = np.random.default_rng(5)
+    d, M, pop = 6, 2, 4096
+    xlb, xub = np.zeros(d), np.ones(d)
+    Xtr = rng.random((200, d))
+    sm = b2.GPR_Matern(Xtr, np.column_stack((Xtr[:, 0], 1 + Xtr[:, 1:].sum(1) - Xtr[:, 0])), d, M, xlb, xub, optimizer=None)
+    opt = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=b2.Model(objective=sm), distance_metric=None)
+    x0 = rng.random((pop, d))
+    opt.initialize_strategy(x0, sm.evaluate(x0).astype(np.float32), np.column_stack((xlb, xub)), np.random.default_rng(1))
+    x_gen, st = opt.generate()
+    assert not x_gen.flags.writeable and not opt.state.population_parm.flags.writeable
+    with pytest.raises(ValueError):
+        x_gen[0, 0] = 0.5
+    h0, _ = L.transfer_bytes()
+    y_dev = sm.evaluate(x_gen)  # mirrored: nothing goes up
+    h1, _ = L.transfer_bytes()
+    xc = x_gen.copy()
+    assert xc.flags.writeable
+    y_host = sm.evaluate(xc)  # ordinary array: the whole matrix goes up
+    h2, _ = L.transfer_bytes()
+    assert h1 - h0 < 4096 and h2 - h1 >= xc.nbytes
+    assert np.array_equal(y_dev, y_host)
+    # same update through the mirror and through plain host arrays
+    import copy
+
+    opt2 = copy.copy(opt)
+    opt2.state = b2.Struct(**{k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in opt.state.__dict__.items()})
+    opt2._pop_base = None
+    opt.update(x_gen, y_dev, st)
+    opt2.update(xc, y_host, st)
+    assert np.array_equal(opt.state.population_parm, opt2.state.population_parm)
+    assert np.array_equal(opt.state.population_obj, opt2.state.population_obj)
+    assert np.array_equal(opt.state.rank, opt2.state.rank)
+    px, py = opt.population_objectives
+    assert px.flags.writeable and np.array_equal(px, opt.state.population_parm)
+
+
 # ------------------------------------------------------------------------------------------ A19 (parity unpinned)
 @pytest.mark.parametrize("precision", ["fp64", "tensor"])
 def test_egp_linear_mean_vs_oracle(L, precision):
