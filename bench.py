@@ -239,6 +239,17 @@ class ResidentStep:
         L, lib, ctx = self.L, self.L.load_library(), self.L.context()
         pop, d, M = self.pop, self.d, self.M
         chk = L._check
+        if self.world == 1:
+            # one C call per generation: the fused resident step (include/dmosopt_b200.h, dmo_nsga2_step)
+            import ctypes
+
+            out = ctypes.c_double(0.0)
+            chk(lib.dmo_nsga2_step(ctx, self.gp._h, self.pop_x.ptr, self.pop_y.ptr, self.rank.ptr, pop, d, M, 0.9, 0.1, 1.0 / d, self.dic.ptr,
+                                   self.dim.ptr, self.xlb.ptr, self.xub.ptr, self.seed, self.stream + 1, self.precision, 1, 1,
+                                   self.ref.ctypes.data, self.nch.ctypes.data, ctypes.byref(out)), "nsga2_step")
+            self.stream += 2
+            self.hv = out.value
+            return int(self.nch[0])
         self.stream += 1
         chk(lib.dmo_tournament(ctx, self.rank.ptr, None, pop, pop // 2, self.seed, self.stream, self.pool.ptr, None), "tournament")
         self.stream += 1

@@ -157,6 +157,20 @@ int dmo_nsga2_generate(dmo_ctx* ctx, const double* pop_x, int64_t npop, int d,
                        const double* xlb, const double* xub, uint64_t seed, uint64_t stream_id,
                        double* x_gen, int32_t* child_kind, int64_t* n_children, double* draws);
 
+/* ---- A10 + A20: one resident NSGA-II surrogate generation ----------------------
+ * the body of MOASMO.optimize's loop (dmosopt/MOASMO.py:105-116) for NSGA2 (dmosopt/NSGA2.py:116-236) with a
+ * GP surrogate, population resident in HBM: tournament -> variation -> GP posterior mean [+ variance] ->
+ * vstack(children, parents) -> rank + stable truncation -> float32 rounding of the stored objectives
+ * (NSGA2.py:228-230) -> optional hypervolume of the survivors (hv_ref / hv_out host pointers, may be NULL).
+ * pop_x (pop,d), pop_y (pop,M), rank (pop,) are DEVICE buffers, updated in place; Philox streams
+ * stream_id (tournament) and stream_id + 1 (variation) are consumed; n_children (host) receives P. */
+int dmo_nsga2_step(dmo_ctx* ctx, dmo_gp* gp, double* pop_x, double* pop_y, int32_t* rank, int64_t pop,
+                   int d, int M, double crossover_prob, double mutation_prob, double mutation_rate,
+                   const double* di_crossover, const double* di_mutation, const double* xlb,
+                   const double* xub, uint64_t seed, uint64_t stream_id, int precision,
+                   int with_variance, int round_to_f32, const double* hv_ref, int64_t* n_children,
+                   double* hv_out);
+
 /* ---- A18: exact-GP posterior (GPR_Matern / GPR_RBF predict) -------------------
  * replaces GPR_Matern.predict / .evaluate (dmosopt/model.py:1254-1275; GPR_RBF :1343-1364),
  * i.e. per objective sklearn GaussianProcessRegressor.predict(return_std=True) ** 2.

@@ -343,6 +343,49 @@ def test_gp_predict_tensor_path(L, N, d, M, P):
     h.close()
 
 
+def test_fused_resident_step_equals_the_separate_calls(L):
+    """dmo_nsga2_step (one C call per generation, population resident) against the same generation composed from the
+    individual entry points with the same Philox streams: bit-identical population, ranks and hypervolume."""
+    import ctypes
+
+    import dmosopt_b200 as b2
+
+    rng = np.random.default_rng(9)
+    d, M, pop = 7, 3, 3001  # odd population: pool size round-half-even
+    xlb, xub = np.zeros(d), np.ones(d)
+    Xtr = rng.random((300, d))
+    Ytr = np.column_stack([Xtr[:, 0] + 0.1 * Xtr[:, 3:].sum(1), (1 - Xtr[:, 0]) * (1 + Xtr[:, 1]), Xtr[:, 2] ** 2 + Xtr[:, 1]])
+    sm = b2.GPR_Matern(Xtr, Ytr, d, M, xlb, xub, optimizer=None)
+    x0 = rng.random((pop, d))
+    y0 = sm.evaluate(x0).astype(np.float32).astype(np.float64)
+    r0 = L.rank_nd(y0).astype(np.int32)
+    lib, ctx = L.load_library(), L.context()
+    DA = L.DeviceArray
+    dic, dim = DA((d,)).upload(np.full(d, 1.0)), DA((d,)).upload(np.full(d, 20.0))
+    dlb, dub = DA((d,)).upload(xlb), DA((d,)).upload(xub)
+    ref = y0.max(axis=0) + 0.1
+    seed, stream = 777, 5
+
+    # fused
+    fx, fy, fr = DA((pop, d)).upload(x0), DA((pop, M)).upload(y0), DA((pop,), np.int32).upload(r0)
+    nch = np.zeros(1, dtype=np.int64)
+    hv_f = ctypes.c_double(0.0)
+    L._check(lib.dmo_nsga2_step(ctx, sm._gp._h, fx.ptr, fy.ptr, fr.ptr, pop, d, M, 0.9, 0.1, 1.0 / d, dic.ptr, dim.ptr, dlb.ptr, dub.ptr,
+                                seed, stream, L.GP_FP64, 1, 1, ref.ctypes.data, nch.ctypes.data, ctypes.byref(hv_f)), "nsga2_step")
+    # separate calls
+    poolsize = int(round(pop / 2.0))
+    pool = L.tournament(r0, poolsize, seed, stream)
+    x_gen, kind = L.nsga2_generate(x0, pool, pop, 0.9, 0.1, 1.0 / d, np.full(d, 1.0), np.full(d, 20.0), xlb, xub, seed, stream + 1)
+    assert int(nch[0]) == x_gen.shape[0]
+    y_gen, _ = sm._gp.predict(np.array(x_gen), return_var=True, precision=L.GP_FP64)
+    Xo, Yo, rk, perm = L.remove_worst(np.vstack((x_gen, x0)), np.vstack((y_gen, y0)), pop)
+    Yo = Yo.astype(np.float32).astype(np.float64)
+    assert np.array_equal(fx.download(), Xo)
+    assert np.array_equal(fy.download(), Yo)
+    assert np.array_equal(fr.download(), rk.astype(np.int32))
+    assert hv_f.value == L.hypervolume(Yo, ref)
+
+
 def test_device_mirror_semantics(L):
     """The offspring matrix and NSGA2's population state are read-only host arrays mirrored on the device: handing them
     back costs no host->device traffic, a copy is an ordinary writable array that takes the host-buffer path and gives
