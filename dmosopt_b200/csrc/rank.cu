@@ -8,17 +8,20 @@
 //      (order- and equality-preserving, so float64 inputs are ranked exactly with 32-bit compares);
 //   2. lexicographic order of the integer vectors (LSD radix passes); in that order a point can only
 //      be dominated by points before it, and identical vectors are adjacent (one "group id" each);
-//   3. one persistent kernel evaluates the chain recurrence block by block in that order:
-//      a block of T targets streams every earlier block through shared memory (coalesced 16-byte
-//      records, broadcast reads, one dominance predicate per pair); the rank word of a record (rank + 1,
-//      0 = not final) is its own ready flag, so a consumer polls only when it catches up with its
-//      predecessor; in-block dependencies are resolved warp by warp with per-thread dominator bitmasks,
-//      ballots and shared-memory folds, and each warp publishes its ranks as soon as they are final.
-//      Blocks are handed out by an atomic ticket, so a block only ever waits for blocks whose CTAs are
-//      already running (no co-residency assumption, no deadlock).
+//      (two and three objectives, up to 1024 blocks: the segmented order of `RankSeg` below -- another linear extension
+//      of the dominance order -- which lets whole tiles be skipped or answered from a per-tile staircase);
+//   3. one persistent kernel evaluates the chain recurrence block by block in that order: a block of T = 128 targets
+//      streams the earlier blocks through shared memory (coalesced 16-byte records, broadcast reads, one dominance
+//      predicate per pair); the rank word of a record (rank + 1, 0 = not final) is its own ready flag, so a consumer
+//      polls only when it catches up with the wavefront.  In-block chains and the chains entering from the predecessor
+//      block are precomputed as longest-path tables (int8, breadth-first walks over 128-bit successor masks) before
+//      any rank is needed, so that the serial part of a block is two packed max-plus products and one store.
+//      Blocks are handed out by an atomic ticket, so a block only ever waits for blocks whose CTAs are already running
+//      (no co-residency assumption, no deadlock); every wait is bounded by a watchdog that raises an error flag.
 //
-// Algorithmic bytes: 8 n M read + 4 n written; comparisons <= n^2 M / 2 (compare-throughput bound,
-// see DESIGN.md).
+// Rank-0-only queries (the hypervolume's filter) take the cell-grid kernels `ndg_*` (M <= 3) or a plain block scan.
+//
+// Algorithmic bytes: 8 n M read + 4 n written; pair tests <= n^2 / 2 (compare / latency bound).
 #include <stdlib.h>
 
 #include <cstdio>
