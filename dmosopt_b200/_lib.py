@@ -324,7 +324,7 @@ def mirror_ptr(a, require_readonly=True):
     ent = _mirrors.get(addr)
     if ent is not None:
         return ent[1].ptr if a.nbytes <= ent[0] and ent[1].ptr else None
-    for base, (nbytes, dev) in _mirrors.items():
+    for base, (nbytes, dev) in list(_mirrors.items()):  # a finaliser may drop an entry while we look
         if base <= addr and addr + a.nbytes <= base + nbytes and dev.ptr:
             return dev.ptr + (addr - base)
     return None
