@@ -74,7 +74,45 @@ def gp_sweep():
         print(f"gp {name} (DMO_GP_TC={os.environ.get('DMO_GP_TC', 'default')}): total {ms:.3f} ms [{parts}]{err}", flush=True)
 
 
+def stream_sweep():
+    """The HBM-bound kernels at the BASELINE shape: crowding / euclidean distance (n = 131072, M = 3), SBX + mutation
+    (pop 65536, d 30), mean kernel's neighbours, hypervolume of a 65536-point 3-D front.  Prints time and the achieved
+    fraction of the algorithmic bytes; run under ncu for the DRAM counters (profiles/README.md)."""
+    L.context()
+    rng = np.random.default_rng(2)
+    lib, ctx = L.load_library(), L.context()
+    n, M = 131072, 3
+    Y = L.DeviceArray((n, M)).upload(rng.random((n, M)))
+    D = L.DeviceArray((n,))
+    for name, fn in (("crowding", lib.dmo_crowding_distance), ("euclidean", lib.dmo_euclidean_distance)):
+        ms = timed(lambda: L._check(fn(ctx, Y.ptr, n, M, D.ptr), name))
+        print(f"{name} n={n} M={M}: {ms:.3f} ms; minimum bytes 8nM + 8n = {(8 * n * M + 8 * n) / 1e6:.1f} MB -> {(8 * n * M + 8 * n) / ms / 1e6:.1f} GB/s on the algorithmic bytes", flush=True)
+    pop, d = 65536, 30
+    X = L.DeviceArray((pop, d)).upload(rng.random((pop, d)))
+    pool = L.DeviceArray((pop // 2,), np.int64).upload(rng.permutation(pop)[: pop // 2].astype(np.int64))
+    Xg = L.DeviceArray((pop + 1, d))
+    kind = L.DeviceArray((pop + 1,), np.int32)
+    nch = np.zeros(1, dtype=np.int64)
+    one, twenty = L.DeviceArray((d,)).upload(np.full(d, 1.0)), L.DeviceArray((d,)).upload(np.full(d, 20.0))
+    lb, ub = L.DeviceArray((d,)).upload(np.zeros(d)), L.DeviceArray((d,)).upload(np.ones(d))
+    ms = timed(lambda: L._check(lib.dmo_nsga2_generate(ctx, X.ptr, pop, d, pool.ptr, pop // 2, pop, 0.9, 0.1, 1.0 / d, one.ptr, twenty.ptr, lb.ptr, ub.ptr,
+                                                      7, 1, Xg.ptr, kind.ptr, nch.ctypes.data, None), "generate"))
+    by = 8 * d * 2 * int(nch[0])
+    print(f"variation pop={pop} d={d}: {ms:.3f} ms for {int(nch[0])} children; 8d B read + 8d B written per child = {by / 1e6:.1f} MB -> {by / ms / 1e6:.1f} GB/s", flush=True)
+    x = rng.random((pop, 3))
+    F = L.DeviceArray((pop, 3)).upload(x / np.linalg.norm(x, axis=1, keepdims=True))
+    import ctypes
+
+    out = ctypes.c_double(0.0)
+    ref = np.full(3, 1.1)
+    ms = timed(lambda: L._check(lib.dmo_hypervolume(ctx, F.ptr, pop, 3, ref.ctypes.data, ctypes.byref(out)), "hv"), reps=2)
+    print(f"hypervolume n={pop} M=3 (whole set non-dominated): {ms:.3f} ms, value {out.value:.6f}", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "stream":
+        stream_sweep()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gp":
         gp_sweep()
         sys.exit(0)
