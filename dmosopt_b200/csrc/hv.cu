@@ -182,16 +182,26 @@ __global__ void __launch_bounds__(HV_T) hv3_kernel(const double* __restrict__ xs
     sy[threadIdx.x] = j < n ? ys[j] : INFINITY;
     sz[threadIdx.x] = j < n ? zo[j] : 0xFFFFFFFFu;
     __syncthreads();
-    const int cnt = (int)((n - t0) < HV_T ? (n - t0) : HV_T);
-#pragma unroll 8
-    for (int s = 0; s < cnt; ++s) {
-      const double yj = sy[s];
-      if (sz[s] < zk && yj < m) {  // a point below k in z that lowers the staircase
-        const double xj = fmax(sx[s], xk);
-        const double h = ry - fmax(m, yk);  // m = inf -> negative -> no area yet
-        covered += (xj - xcur) * fmax(h, 0.0);
-        xcur = xj;
-        m = yj;
+    // A point lowers the staircase only O(log n) times per sweep, but a data-dependent branch per point serialises the
+    // loop.  Test eight points at a time against the current minimum without branching (a stale, larger minimum can
+    // only produce false alarms, never a miss; the padding never fires) and fall into the exact loop only on a hit.
+    for (int s0 = 0; s0 < HV_T; s0 += 8) {
+      bool hit = false;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) hit |= (sz[s0 + u] < zk) & (sy[s0 + u] < m);
+      if (hit) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int s = s0 + u;
+          const double yj = sy[s];
+          if (sz[s] < zk && yj < m) {  // a point below k in z that lowers the staircase
+            const double xj = fmax(sx[s], xk);
+            const double h = ry - fmax(m, yk);  // m = inf -> negative -> no area yet
+            covered += (xj - xcur) * fmax(h, 0.0);
+            xcur = xj;
+            m = yj;
+          }
+        }
       }
     }
   }
