@@ -123,7 +123,10 @@ class ClockSampler:
         sel = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
         if not sel and self.t1 is not None:  # region shorter than a sampling period: the last rows taken under the same load
             sel = [r for r in rows if r[0] <= self.t1][-3:]
-            window = "warm-up steps immediately before the timed region (region shorter than one 50 ms sample)"
+            window = "steps immediately before the timed region (region shorter than one 50 ms sample)"
+        if not sel and rows and self.t1 is not None:  # nvidia-smi came up late: the row nearest to the region
+            sel = [min(rows, key=lambda r: abs((r[0] - self.t1).total_seconds()))]
+            window = "nearest sample to the timed region (nvidia-smi started late)"
         if sel:
             reasons = sorted({nm for r in sel for nm in r[3]})
             out = {"sm_mhz": float(np.median([r[1] for r in sel])), "sm_max_mhz": float(max(r[2] for r in sel)), "reasons": reasons,
@@ -301,6 +304,10 @@ def run_ours(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L.context(local_rank)
+    # started now (spawning nvidia-smi can take longer than a short timed region); rows are time-stamped and filtered later
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     pop, d, M, N = args.pop, args.dim, args.obj, args.ntrain
     prec = L.GP_TENSOR if args.precision == "tensor" else L.GP_FP64
     w = workload(pop, d, M, N)
@@ -362,9 +369,6 @@ def run_ours(args):
     rs = ResidentStep(L, sm._gp, pop, d, M, w["xlb"], w["xub"], opt.state.population_parm, opt.state.population_obj.astype(np.float64), rank0, ref,
                       args.seed, world, rank, dist, torch)
     rs.precision = prec
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     for _ in range(args.warmup):
         rs.step()
     barrier()
