@@ -427,6 +427,25 @@ def test_device_mirror_semantics(L):
     px, py = opt.population_objectives
     assert px.flags.writeable and np.array_equal(px, opt.state.population_parm)
 
+    # a host-evaluated (callable) distance metric takes the general sortMO path: the mirrored state is rewritten
+    # through its writable base and the device copy is refreshed -- same result as with plain host arrays
+    metric = lambda y: -np.abs(y - y.mean(axis=0)).sum(axis=1)  # noqa: E731
+    for o in (opt, opt2):
+        o.y_distance_metrics = [metric]
+    x_gen, st = opt.generate()
+    y_gen = sm.evaluate(x_gen)
+    opt2.state.population_parm = np.array(opt2.state.population_parm)
+    opt.update(x_gen, y_gen, st)
+    opt2.update(np.array(x_gen), np.array(y_gen), st)
+    assert not opt.state.population_parm.flags.writeable  # still the mirrored array
+    assert np.array_equal(opt.state.population_parm, opt2.state.population_parm)
+    assert np.array_equal(opt.state.rank, opt2.state.rank)
+    dev = L.mirror_ptr(opt.state.population_parm)  # the device copy was refreshed with the new survivors
+    assert dev is not None
+    back = np.empty_like(opt2.state.population_parm)
+    L.memcpy(back, dev, back.nbytes)
+    assert np.array_equal(back, opt.state.population_parm)
+
 
 # ------------------------------------------------------------------------------------------ A19 (parity unpinned)
 @pytest.mark.parametrize("precision", ["fp64", "tensor"])
