@@ -178,21 +178,62 @@ __global__ void seg_start_kernel(const uint32_t* __restrict__ c1rec, int64_t n, 
   seg_start[sgi] = (uint32_t)lo;
 }
 
-// one warp per tile: quantised min / max of the first compare word
+// one warp per tile: quantised min / max of the first compare word.  A tile whose first compare word is not ascending
+// (it spans a segment boundary, or holds padding) is given the full band [0, 255]: it is then never skipped, never
+// "fast", and the pair tests take the generic loop instead of the sorted-prefix loop.
 __global__ void seg_tile_band_kernel(const uint32_t* __restrict__ rec, int nblocks, int T, int qshift,
                                      uint16_t* __restrict__ tile_q) {
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (k >= nblocks) return;
   uint32_t lo = 255u, hi = 0u;
+  bool sorted = true;
   for (int t = lane; t < T; t += 32) {
-    const uint32_t q = min(rec[((int64_t)k * T + t) * 4] >> qshift, 255u);
+    const uint32_t w = rec[((int64_t)k * T + t) * 4];
+    const uint32_t q = min(w >> qshift, 255u);
     lo = min(lo, q);
     hi = max(hi, q);
+    if (t > 0) sorted = sorted && (rec[((int64_t)k * T + t - 1) * 4] <= w);
   }
   lo = __reduce_min_sync(0xFFFFFFFFu, lo);
   hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+  sorted = __all_sync(0xFFFFFFFFu, sorted);
+  if (!sorted) {
+    lo = 0u;
+    hi = 255u;
+  }
   if (lane == 0) tile_q[k] = (uint16_t)(lo | (hi << 8));
+}
+
+// Pair tests against a tile whose first compare word is ascending: only the prefix with word_0 <= v[0] can dominate, so
+// one binary search replaces that compare and the loop stops at the longest prefix of the warp (the 32 targets of a warp
+// are neighbours in the same order, their prefixes are close).
+template <int M, int W, int NV, int T, bool GID>
+__device__ __forceinline__ int rank_pair_tests_sorted(const uint4* tb, const uint32_t* v, uint32_t gidv, int best) {
+  int p = 0;  // number of records with word_0 <= v[0]
+#pragma unroll
+  for (int step = T / 2; step >= 1; step >>= 1)
+    if (reinterpret_cast<const uint32_t*>(&tb[(p + step - 1) * NV])[0] <= v[0]) p += step;
+  if (p < T && reinterpret_cast<const uint32_t*>(&tb[p * NV])[0] <= v[0]) ++p;
+  const int pmax = __reduce_max_sync(0xFFFFFFFFu, p);
+  int acc[4] = {best, 0, 0, 0};
+#pragma unroll 8
+  for (int s = 0; s < pmax; ++s) {
+    uint32_t sw[W];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const uint4 a4 = tb[s * NV + q];
+      sw[4 * q + 0] = a4.x;
+      sw[4 * q + 1] = a4.y;
+      sw[4 * q + 2] = a4.z;
+      sw[4 * q + 3] = a4.w;
+    }
+    bool dom = (s < p) && (GID ? (sw[M - 1] != gidv) : true);
+#pragma unroll
+    for (int j = 1; j < M - 1; ++j) dom = dom && (sw[j] <= v[j]);
+    acc[s & 3] = dom ? max(acc[s & 3], (int)sw[M]) : acc[s & 3];
+  }
+  return max(max(acc[0], acc[1]), max(acc[2], acc[3]));
 }
 
 // 128 pair tests of one streamed tile against this thread's record.  SKIP0: the first compare word is known to pass;
@@ -613,6 +654,9 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
         } else if (SEG && (uint32_t)(sq16[k] >> 8) < wq_lo) {  // every source word below this warp's band
           best = may_share_group ? rank_pair_tests<M, W, NV, T, true, true, false>(tb, c1tb, v, gidv, c1v, best)
                                  : rank_pair_tests<M, W, NV, T, true, false, false>(tb, c1tb, v, gidv, c1v, best);
+        } else if (SEG && sq16[k] != 0xFF00u) {  // ascending first word (the full band marks the tiles that are not)
+          best = may_share_group ? rank_pair_tests_sorted<M, W, NV, T, true>(tb, v, gidv, best)
+                                 : rank_pair_tests_sorted<M, W, NV, T, false>(tb, v, gidv, best);
         } else {
           best = may_share_group ? rank_pair_tests<M, W, NV, T, false, true, false>(tb, c1tb, v, gidv, c1v, best)
                                  : rank_pair_tests<M, W, NV, T, false, false, false>(tb, c1tb, v, gidv, c1v, best);
