@@ -69,3 +69,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_plain_c_host_compiles_and_links_against_the_header(lib_path, tmp_path):
+    """include/dmosopt_b200.h is valid C99 and examples/nsga2_step.c (a non-Python host of the fused generation step)
+    links against the shared library with nothing but gcc; without a GPU the program stops at dmo_create."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "nsga2_step")
+    libdir = os.path.dirname(lib_path)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "nsga2_step.c"),
+                        "-L", libdir, "-ldmosopt_b200", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "generation 4:" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode != 0 and "dmo_create" in run.stderr
