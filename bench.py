@@ -248,7 +248,7 @@ class ResidentStep:
 
             out = ctypes.c_double(0.0)
             chk(lib.dmo_nsga2_step(ctx, self.gp._h, self.pop_x.ptr, self.pop_y.ptr, self.rank.ptr, pop, d, M, 0.9, 0.1, 1.0 / d, self.dic.ptr,
-                                   self.dim.ptr, self.xlb.ptr, self.xub.ptr, self.seed, self.stream + 1, self.precision, 1, 1,
+                                   self.dim.ptr, self.xlb.ptr, self.xub.ptr, self.seed, self.stream + 1, self.precision, self.metric, 1, 1,
                                    self.ref.ctypes.data, self.nch.ctypes.data, ctypes.byref(out)), "nsga2_step")
             self.stream += 2
             self.hv = out.value
@@ -277,7 +277,7 @@ class ResidentStep:
         # stack parents under the children (NSGA2.py:205-206), rank + stable truncation, float32 state rounding
         L.memcpy(self.Xs.offset(P * d), self.pop_x.ptr, pop * d * 8)
         L.memcpy(self.Ys.offset(P * M), self.pop_y.ptr, pop * M * 8)
-        chk(lib.dmo_remove_worst(ctx, self.Xs.ptr, self.Ys.ptr, P + pop, d, M, L.METRIC_NONE, None, 0, pop, self.pop_x.ptr, self.pop_y.ptr,
+        chk(lib.dmo_remove_worst(ctx, self.Xs.ptr, self.Ys.ptr, P + pop, d, M, self.metric, None, 0, pop, self.pop_x.ptr, self.pop_y.ptr,
                                  self.rank.ptr, self.perm.ptr), "remove_worst")
         L.round_f32(self.pop_y.ptr, pop * M)
         import ctypes
@@ -309,7 +309,7 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     pop, d, M, N = args.pop, args.dim, args.obj, args.ntrain
-    prec = L.GP_TENSOR if args.precision == "tensor" else L.GP_FP64
+    prec = {"auto": L.GP_AUTO, "tensor": L.GP_TENSOR, "fp64": L.GP_FP64}[args.precision]
     w = workload(pop, d, M, N)
     t0 = time.time()
     sm = b2.GPR_Matern(w["Xtr"], w["Ytr"], d, M, w["xlb"], w["xub"], optimizer=None, precision=args.precision)
@@ -336,7 +336,7 @@ def run_ours(args):
     from dmosopt_b200.parallel import ShardedSurrogate
 
     sm_e2e = ShardedSurrogate(sm, device=torch.device("cuda", local_rank)) if world > 1 else sm
-    opt = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=mdl, distance_metric=None)
+    opt = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=mdl, distance_metric=None if args.distance_metric == "none" else args.distance_metric)
     opt.initialize_strategy(w["X0"], y0, np.column_stack((w["xlb"], w["xub"])), np.random.default_rng(args.seed))
     hv_ind = Hypervolume(ref_point=ref)
 
@@ -369,6 +369,7 @@ def run_ours(args):
     rs = ResidentStep(L, sm._gp, pop, d, M, w["xlb"], w["xub"], opt.state.population_parm, opt.state.population_obj.astype(np.float64), rank0, ref,
                       args.seed, world, rank, dist, torch)
     rs.precision = prec
+    rs.metric = {"none": L.METRIC_NONE, "crowding": L.METRIC_CROWDING, "euclidean": L.METRIC_EUCLIDEAN}[args.distance_metric]
     for _ in range(args.warmup):
         rs.step()
     barrier()
@@ -478,7 +479,11 @@ def main():
     ap.add_argument("--ntrain", type=int, default=4096)
     # tensor = the tcgen05 split-fp16 variance kernel the north star names (<= 1e-5 of the prior variance, tests/test_gpu_parity.py);
     # fp64 = the float64 CUDA-core path that matches scikit-learn to 1e-8 (parity anchor, ~12x slower)
-    ap.add_argument("--precision", default=os.environ.get("DMOSOPT_B200_GP", "tensor"), choices=["fp64", "tensor"])
+    # auto = the plugin default: tensor path where the per-model calibration admits it, float64 rows where it does not
+    ap.add_argument("--precision", default=os.environ.get("DMOSOPT_B200_GP", "auto"), choices=["auto", "fp64", "tensor"])
+    # MOASMO.epoch constructs its optimizer with distance_metric=None (dmosopt/MOASMO.py:365-373): rank ties keep
+    # children-first index order.  "crowding" is NSGA2's stand-alone default (NSGA2.py:25).
+    ap.add_argument("--distance-metric", default="none", choices=["none", "crowding", "euclidean"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--cpu-sample", type=int, default=768)
     ap.add_argument("--e2e-steps", type=int, default=5)

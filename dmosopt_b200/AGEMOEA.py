@@ -229,6 +229,7 @@ class AGEMOEA(MOEA):
         popsize = self.opt_params.popsize
         population_parm = np.vstack((st.population_parm, x_gen))
         population_obj = np.vstack((st.population_obj, y_gen))
+        _lib.mirror_drop(x_gen)  # consumed (stacked above): release the HBM copy of the offspring matrix
         population_parm, population_obj = remove_duplicates(population_parm, population_obj)
         population_parm, population_obj, rank, crowd_dist = environmental_selection(
             self.local_random, population_parm, population_obj, popsize, self.nInput, self.nOutput, logger=self.logger

@@ -20,6 +20,18 @@ import numpy as np
 
 from . import _lib
 
+
+
+def crowding_distance_metric(Y):
+    """indicators.crowding_distance_metric (dmosopt/indicators.py:12-51), re-exported like the reference's MOEA module does."""
+    return _lib.crowding_distance(Y)
+
+
+def euclidean_distance_metric(Y):
+    """indicators.euclidean_distance_metric (dmosopt/indicators.py:54-62)."""
+    return _lib.euclidean_distance(Y)
+
+
 _METRIC_CODES = {None: _lib.METRIC_NONE, "crowding": _lib.METRIC_CROWDING, "euclidean": _lib.METRIC_EUCLIDEAN}
 
 
@@ -272,10 +284,12 @@ def crossover_sbx(local_random, parent1, parent2, di_crossover, xlb, xub, nchild
 
 
 def get_duplicates(X, Y=None, eps=1e-16):
-    """MOEA.get_duplicates (MOEA.py:426-437) for the X-vs-itself case used by the optimizers."""
-    if Y is not None and Y is not X:
-        raise NotImplementedError("get_duplicates(X, Y): only the self-comparison used on the hot path is accelerated")
-    return _lib.get_duplicates(X, eps)
+    """MOEA.get_duplicates (MOEA.py:426-437): the self-comparison the optimizers use (AGEMOEA.py:203-205) and the
+    two-set form of MOASMO's resample step (MOASMO.py:442): row i of X is a duplicate when a row j < i of Y is within
+    eps (the reference masks the upper triangle of cdist(X, Y) including the diagonal)."""
+    if Y is None or Y is X:
+        return _lib.get_duplicates(X, eps)
+    return _lib.get_duplicates(X, eps, Y=Y)
 
 
 def remove_duplicates(population_parm, population_obj, eps=1e-16):

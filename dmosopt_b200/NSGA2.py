@@ -147,6 +147,7 @@ class NSGA2(MOEA):
                 population_parm, population_obj, popsize,
                 x_distance_metrics=self.x_distance_metrics, y_distance_metrics=self.y_distance_metrics, return_perm=True,
             )
+        _lib.mirror_drop(x_gen)  # consumed: the caller may keep the host array, the HBM copy is released
         st.successful_crossovers += np.count_nonzero(np.isin(state["crossover_indices"], perm, assume_unique=True)) / 2
         st.successful_mutations += np.count_nonzero(np.isin(state["mutation_indices"], perm, assume_unique=True))
         if self.opt_params.adaptive_population_size:

@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(_HERE, "libdmosopt_b200.so")
 
 METRIC_NONE, METRIC_CROWDING, METRIC_EUCLIDEAN = 0, 1, 2
 KERNEL_MATERN52, KERNEL_RBF = 0, 1
-GP_FP64, GP_TENSOR = 0, 1
+GP_FP64, GP_TENSOR, GP_AUTO = 0, 1, 2
+HV_MAX_OBJECTIVES = 5  # dmo_hypervolume: exact slicing for M <= 5 (csrc/hv.cu)
 
 _c_i64 = ctypes.c_int64
 _c_u64 = ctypes.c_uint64
@@ -58,6 +59,7 @@ _SIGNATURES = {
     "dmo_tournament": (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_u64, _c_u64, _vp, _vp]),
     "dmo_mutation_u": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _vp]),
     "dmo_sbx_u": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp, _vp, _vp]),
+    "dmo_nsga2_plan_length": (_c_i64, [_c_i64, _c_dbl, _c_dbl]),
     "dmo_nsga2_generate": (
         _c_int,
         [_vp, _vp, _c_i64, _c_int, _vp, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _vp, _vp, _c_u64, _c_u64, _vp, _vp, _vp, _vp],
@@ -66,11 +68,14 @@ _SIGNATURES = {
     "dmo_gp_destroy": (_c_int, [_vp, _vp]),
     "dmo_gp_set_linear_mean": (_c_int, [_vp, _vp, _vp, _vp]),
     "dmo_gp_predict": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _c_int]),
+    "dmo_gp_auto_info": (_c_int, [_vp, _vp, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_dbl),
+                                  ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_i64)]),
     "dmo_nsga2_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _vp, _vp, _c_u64, _c_u64,
-                                _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+                                _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "dmo_hypervolume": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp, ctypes.POINTER(_c_dbl)]),
     "dmo_ehvi_select": (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp, _c_int, _c_i64, _vp, _vp]),
     "dmo_get_duplicates": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_dbl, _vp]),
+    "dmo_get_duplicates_pair": (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _c_int, _c_dbl, _vp]),
     "dmo_age_survival": (_c_int, [_vp, _vp, _vp, _c_i64, _c_int, _c_dbl, _vp, _c_int, _vp]),
     "dmo_smpso_velocity": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _vp]),
     "dmo_mutate_groups": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _c_u64, _c_u64, _vp, _vp]),
@@ -260,6 +265,10 @@ def memcpy(dst, src, nbytes):
 _pin_pool = {}
 _pin_pool_bytes = 0
 _PIN_POOL_LIMIT = 1 << 30
+# page-locked bytes currently handed out (not pooled).  Callers such as MOASMO.optimize keep every offspring matrix of
+# an epoch alive (x_new history): beyond this budget new offspring matrices are ordinary pageable arrays.
+_pin_live_bytes = 0
+_PIN_LIVE_LIMIT = int(os.environ.get("DMOSOPT_B200_PINNED_LIMIT", str(4 << 30)))
 # Device mirrors of read-only host arrays the library itself produced (offspring matrix, population state):
 # {host address: (nbytes, DeviceArray)}.  ``_in`` substitutes the device address, so data that was born on the GPU is
 # not shipped back over PCIe when the caller hands it to the next call.  Only non-writeable arrays qualify: a
@@ -268,7 +277,8 @@ _mirrors = {}
 
 
 def _pin_release(ptr, nbytes):
-    global _pin_pool_bytes
+    global _pin_pool_bytes, _pin_live_bytes
+    _pin_live_bytes -= nbytes
     _mirrors.pop(ptr, None)
     lst = _pin_pool.setdefault(nbytes, [])
     if len(lst) < 4 and _pin_pool_bytes + nbytes <= _PIN_POOL_LIMIT:
@@ -280,7 +290,7 @@ def _pin_release(ptr, nbytes):
 
 def pinned_empty(shape, dtype=np.float64):
     """NumPy array backed by page-locked host memory (pooled; recycled when the last view is collected)."""
-    global _pin_pool_bytes
+    global _pin_pool_bytes, _pin_live_bytes
     import weakref
 
     lib = load_library()
@@ -298,6 +308,7 @@ def pinned_empty(shape, dtype=np.float64):
             raise DmoError("dmo_host_alloc failed")
         addr = p.value
     buf = (ctypes.c_char * nbytes).from_address(addr)
+    _pin_live_bytes += nbytes
     weakref.finalize(buf, _pin_release, addr, nbytes)
     return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
 
@@ -305,6 +316,25 @@ def pinned_empty(shape, dtype=np.float64):
 def mirror_register(host, dev):
     """Declare ``dev`` (DeviceArray) the device copy of the pinned array ``host`` (from pinned_empty)."""
     _mirrors[host.ctypes.data] = (host.nbytes, dev)
+
+
+def mirror_drop(a):
+    """Forget (and free) the device copy of ``a``: the host array stays valid, later uses simply upload it again.
+
+    The optimizers call this once ``update`` has consumed an offspring matrix, so a caller that keeps every x_gen of an
+    epoch (MOASMO.optimize's history) holds host memory only, not one HBM buffer per generation."""
+    if not isinstance(a, np.ndarray):
+        return
+    addr = a.ctypes.data
+    ent = _mirrors.get(addr)
+    if ent is None:
+        for base, (nbytes, dev) in list(_mirrors.items()):
+            if base <= addr < base + nbytes:
+                addr, ent = base, (nbytes, dev)
+                break
+    if ent is not None:
+        _mirrors.pop(addr, None)
+        ent[1].free()
 
 
 def mirror_upload(host):
@@ -525,13 +555,16 @@ def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, muta
 
     Returns (x_gen (P, d), child_kind (P,) int32 [0/1 = SBX child 1/2, 2 = mutant][, draws]).
     ``draws`` (if requested) is a dict with the random draws the kernel used, for replay on the
-    CPU oracle: u_cross (T,), u_mut (T,), pair (T, 2), single (T,), u_genes (T, 2, d), T = 2*popsize+64.
+    CPU oracle: u_cross (T,), u_mut (T,), pair (T, 2), single (T,), u_genes (T, 2, d), T = dmo_nsga2_plan_length
+    (2*popsize+64 for the default rates).
     """
     pop_x = _f64(pop_x)
     npop, d = pop_x.shape
     pool_idx = np.ascontiguousarray(pool_idx, dtype=np.int64)
     popsize = int(popsize)
-    T = 2 * popsize + 64
+    T = int(load_library().dmo_nsga2_plan_length(popsize, float(crossover_prob), float(mutation_prob)))
+    if T <= 0:
+        raise DmoError("nsga2_generate: crossover_prob / mutation_prob too small to plan the variation loop")
     # the offspring matrix stays on the device as the mirror of the (read-only, page-locked) array handed back
     x_dev = DeviceArray((popsize + 1, d), np.float64)
     kind = np.empty(popsize + 1, dtype=np.int32)
@@ -549,7 +582,13 @@ def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, muta
         "dmo_nsga2_generate",
     )
     P = int(nch[0])
-    x_gen = pinned_empty((popsize + 1, d), np.float64)
+    if _pin_live_bytes < _PIN_LIVE_LIMIT:
+        x_gen = pinned_empty((popsize + 1, d), np.float64)
+    else:  # the caller is hoarding offspring matrices: pageable memory from here on (mirror dropped with the array)
+        import weakref
+
+        x_gen = np.empty((popsize + 1, d), dtype=np.float64)
+        weakref.finalize(x_gen, _mirrors.pop, x_gen.ctypes.data, None)
     if P:
         memcpy(x_gen, x_dev.ptr, P * d * 8)
     mirror_register(x_gen, x_dev)
@@ -613,6 +652,15 @@ class GPHandle:
         _check(load_library().dmo_gp_predict(context(), self._h, _in(X), P, _ptr(mean), _ptr(var), int(precision)), "dmo_gp_predict")
         return mean, var
 
+    def auto_info(self):
+        """What precision=GP_AUTO does for this model (runs the one-off calibration if needed)."""
+        mt, vt, rows = _c_int(0), _c_int(0), _c_i64(0)
+        em, ev, th = _c_dbl(0.0), _c_dbl(0.0), _c_dbl(0.0)
+        _check(load_library().dmo_gp_auto_info(context(), self._h, ctypes.byref(mt), ctypes.byref(vt), ctypes.byref(em), ctypes.byref(ev),
+                                               ctypes.byref(th), ctypes.byref(rows)), "dmo_gp_auto_info")
+        return {"mean_tensor": bool(mt.value), "var_tensor": bool(vt.value), "mean_err": em.value, "var_err": ev.value, "theta": th.value,
+                "last_refined": int(rows.value)}
+
     def close(self):
         if getattr(self, "_h", None) is not None and _lib is not None and _ctx is not None:
             _lib.dmo_gp_destroy(_ctx, self._h)
@@ -655,11 +703,16 @@ def ehvi_select(F, means, variances, ref, k, nds=True, return_scores=False):
 
 
 # --------------------------------------------------------------------------- A21
-def get_duplicates(X, eps=1e-16):
+def get_duplicates(X, eps=1e-16, Y=None):
     X = _f64(X)
     n, d = X.shape
     out = np.empty(n, dtype=np.uint8)
-    _check(load_library().dmo_get_duplicates(context(), _ptr(X), n, d, float(eps), _ptr(out)), "dmo_get_duplicates")
+    if Y is None:
+        _check(load_library().dmo_get_duplicates(context(), _in(X), n, d, float(eps), _ptr(out)), "dmo_get_duplicates")
+    else:
+        Y = _f64(Y)
+        assert Y.ndim == 2 and Y.shape[1] == d, (X.shape, Y.shape)
+        _check(load_library().dmo_get_duplicates_pair(context(), _in(X), n, _in(Y), Y.shape[0], d, float(eps), _ptr(out)), "dmo_get_duplicates_pair")
     return out.astype(bool)
 
 

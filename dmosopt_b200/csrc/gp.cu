@@ -370,6 +370,164 @@ int gp_predict_fp64(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, doub
   return DMO_OK;
 }
 
+namespace {
+
+// ---- DMO_GP_AUTO ---------------------------------------------------------------------------------------------
+// The tensor path computes K_* in fp32 and the contraction in split-fp16 with fp32 accumulation: its errors are a few
+// 1e-7 of the *operands*, so what reaches the posterior depends on the conditioning of the model (alpha and L^-1 of a
+// fitted, nearly noise-free GP amplify them by orders of magnitude) and, for the variance, on how much of the prior
+// cancels.  AUTO therefore measures instead of assuming: once per model, both paths predict the same 512 probe
+// candidates (uniform in the unit cube, and training points displaced by 1e-4 .. 0.3) and
+//   * the mean goes through fp32 K_* only if its probe error is <= 2.5e-6 of max(|mean|, y_std)  (bar: 1e-5, 4x margin);
+//   * the variance goes through the tensor cores only if its probe error E is <= 4.5e-6 of the prior variance; rows whose
+//     variance comes out below theta * prior, theta = max(0.02, 2 E / 1e-5), are then recomputed in float64, so every
+//     returned variance is within 1e-5 of its own value (not just of the prior) -- the float64 path is the one that
+//     matches scikit-learn to 1e-8.
+constexpr int CAL_PROBES = 512;
+
+__global__ void probe_points_kernel(const double* __restrict__ Xt, int64_t N, int d, int n_uniform, int n_total,
+                                    double* __restrict__ Xn) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_total) return;
+  Philox ph(0x9E3779B97F4A7C15ull);
+  const uint4 h = ph((uint64_t)p, 0x51ull);
+  const int64_t src = (int64_t)(h.x % (uint32_t)N);
+  const double scale = pow(10.0, -4.0 + 3.5 * u01_53(h.y, h.z));
+  for (int j = 0; j < d; ++j) {
+    const uint4 r = ph((uint64_t)p, (uint64_t)(j + 1) << 8);
+    const double u = u01_53(r.x, r.y);
+    double x = u;
+    if (p >= n_uniform) x = fmin(1.0, fmax(0.0, Xt[src * d + j] + scale * (2.0 * u - 1.0)));
+    Xn[(int64_t)p * d + j] = x;
+  }
+}
+
+__global__ void flag_small_var_kernel(const double* __restrict__ var, int64_t P, int M, const double* __restrict__ constant,
+                                      const double* __restrict__ noise, const double* __restrict__ ystd, double theta,
+                                      int32_t* __restrict__ flag) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int f = 0;
+  for (int m = 0; m < M; ++m) {
+    const double prior = (constant[m] + noise[m]) * ystd[m] * ystd[m];
+    if (!(var[p * M + m] >= theta * prior)) f = 1;  // NaN counts as small
+  }
+  flag[p] = f;
+}
+
+__global__ void compact_rows_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int64_t P, int d,
+                                    const double* __restrict__ Xn, int32_t* __restrict__ idx, double* __restrict__ Xsub) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P || !flag[p]) return;
+  const int32_t o = pos[p];
+  idx[o] = (int32_t)p;
+  for (int j = 0; j < d; ++j) Xsub[(int64_t)o * d + j] = Xn[p * d + j];
+}
+
+__global__ void scatter_rows_kernel(const int32_t* __restrict__ idx, int64_t n, int M, const double* __restrict__ msub,
+                                    const double* __restrict__ vsub, double* __restrict__ mean, double* __restrict__ var) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * M) return;
+  const int64_t r = t / M;
+  const int m = (int)(t - r * M);
+  const int64_t p = idx[r];
+  mean[p * M + m] = msub[t];
+  var[p * M + m] = vsub[t];
+}
+
+int gp_calibrate(dmo_ctx* ctx, dmo_gp* gp) {
+  if (gp->calibrated) return DMO_OK;
+  const int M = gp->M, d = gp->d;
+  const int P = CAL_PROBES;
+  gp->auto_mean_tensor = gp->auto_var_tensor = false;
+  gp->cal_mean_err = gp->cal_var_err = INFINITY;
+  gp->refine_theta = 1.0;
+  if (M > 16 || d > 64) {  // outside the tensor path's shape limits: float64 only
+    gp->calibrated = true;
+    return DMO_OK;
+  }
+  DevBuf<double> xn, m64, v64, mt, vt;
+  DMO_TRY(xn.alloc(ctx, (size_t)P * d));
+  DMO_TRY(m64.alloc(ctx, (size_t)P * M));
+  DMO_TRY(v64.alloc(ctx, (size_t)P * M));
+  DMO_TRY(mt.alloc(ctx, (size_t)P * M));
+  DMO_TRY(vt.alloc(ctx, (size_t)P * M));
+  DMO_LAUNCH(probe_points_kernel, (unsigned)ceil_div(P, 128), 128, 0, gp->Xt.p, gp->N, d, P / 2, P, xn.p);
+  DMO_CHECK_LAUNCH();
+  const bool prof = ctx->profiling;
+  ctx->profiling = false;  // calibration launches are not part of any timed step
+  int rc = gp_predict_fp64(ctx, gp, xn.p, P, m64.p, v64.p);
+  if (rc == DMO_OK) rc = gp_predict_tensor(ctx, gp, xn.p, P, mt.p, vt.p);
+  ctx->profiling = prof;
+  if (rc != DMO_OK) return rc;
+  std::vector<double> h((size_t)4 * P * M);
+  DMO_CUDA(cudaMemcpyAsync(h.data(), m64.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaMemcpyAsync(h.data() + (size_t)P * M, v64.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaMemcpyAsync(h.data() + (size_t)2 * P * M, mt.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaMemcpyAsync(h.data() + (size_t)3 * P * M, vt.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  const double *a64 = h.data(), *b64 = a64 + (size_t)P * M, *at = b64 + (size_t)P * M, *bt = at + (size_t)P * M;
+  double em = 0.0, ev = 0.0;
+  for (int p = 0; p < P; ++p)
+    for (int m = 0; m < M; ++m) {
+      const double ys = gp->h_ystd[m];
+      const double prior = (gp->h_constant[m] + gp->h_noise[m]) * ys * ys;
+      const double dm = fabs(at[p * M + m] - a64[p * M + m]) / fmax(fabs(a64[p * M + m]), ys);
+      const double dv = fabs(bt[p * M + m] - b64[p * M + m]) / prior;
+      em = (dm > em || dm != dm) ? (dm != dm ? INFINITY : dm) : em;
+      ev = (dv > ev || dv != dv) ? (dv != dv ? INFINITY : dv) : ev;
+    }
+  gp->cal_mean_err = em;
+  gp->cal_var_err = ev;
+  gp->auto_mean_tensor = em <= 2.5e-6;
+  gp->auto_var_tensor = gp->auto_mean_tensor && ev <= 4.5e-6;
+  gp->refine_theta = fmax(0.02, 2.0 * ev / 1e-5);
+  gp->calibrated = true;
+  return DMO_OK;
+}
+
+// AUTO predict on normalised inputs: tensor path where the calibration allows it, float64 for the rest
+int gp_predict_auto(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var) {
+  DMO_TRY(gp_calibrate(ctx, gp));
+  gp->last_refined = 0;
+  if (!gp->auto_mean_tensor || (d_var && !gp->auto_var_tensor)) {
+    gp->last_refined = P;
+    return gp_predict_fp64(ctx, gp, dXn, P, d_mean, d_var);
+  }
+  DMO_TRY(gp_predict_tensor(ctx, gp, dXn, P, d_mean, d_var));
+  if (!d_var) return DMO_OK;
+  const int M = gp->M, d = gp->d;
+  DevBuf<int32_t> flag, pos;
+  DMO_TRY(flag.alloc(ctx, (size_t)P + 1));
+  DMO_TRY(pos.alloc(ctx, (size_t)P + 1));
+  DMO_CUDA(cudaMemsetAsync(flag.p + P, 0, sizeof(int32_t), ctx->stream));
+  DMO_LAUNCH(flag_small_var_kernel, (unsigned)ceil_div(P, 256), 256, 0, d_var, P, M, gp->constant.p, gp->noise.p, gp->ystd.p,
+             gp->refine_theta, flag.p);
+  DMO_TRY(prim_exclusive_sum_i32(ctx, flag.p, pos.p, P + 1));
+  int32_t n_ref = 0;
+  DMO_CUDA(cudaMemcpyAsync(&n_ref, pos.p + P, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  gp->last_refined = n_ref;
+  if (n_ref == 0) return DMO_OK;
+  DevBuf<int32_t> idx;
+  DevBuf<double> xs, ms, vs;
+  DMO_TRY(idx.alloc(ctx, (size_t)n_ref));
+  DMO_TRY(xs.alloc(ctx, (size_t)n_ref * d));
+  DMO_TRY(ms.alloc(ctx, (size_t)n_ref * M));
+  DMO_TRY(vs.alloc(ctx, (size_t)n_ref * M));
+  DMO_LAUNCH(compact_rows_kernel, (unsigned)ceil_div(P, 256), 256, 0, flag.p, pos.p, P, d, dXn, idx.p, xs.p);
+  {
+    ProfileScope ps(ctx, "gp_refine_fp64");
+    DMO_TRY(gp_predict_fp64(ctx, gp, xs.p, n_ref, ms.p, vs.p));
+  }
+  DMO_LAUNCH(scatter_rows_kernel, (unsigned)ceil_div((int64_t)n_ref * M, 256), 256, 0, idx.p, (int64_t)n_ref, M, ms.p, vs.p,
+             d_mean, d_var);
+  DMO_CHECK_LAUNCH();
+  return DMO_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int dmo_gp_create(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const double* X_train, const double* alpha,
@@ -534,6 +692,21 @@ int dmo_gp_set_linear_mean(dmo_ctx* ctx, dmo_gp* gp, const double* weight, const
   return DMO_OK;
 }
 
+int dmo_gp_auto_info(dmo_ctx* ctx, dmo_gp* gp, int* mean_tensor, int* var_tensor, double* mean_err, double* var_err,
+                     double* theta, int64_t* last_refined) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(gp, "gp_auto_info: null model");
+  DMO_TRY(gp_calibrate(ctx, gp));
+  if (mean_tensor) *mean_tensor = gp->auto_mean_tensor ? 1 : 0;
+  if (var_tensor) *var_tensor = gp->auto_var_tensor ? 1 : 0;
+  if (mean_err) *mean_err = gp->cal_mean_err;
+  if (var_err) *var_err = gp->cal_var_err;
+  if (theta) *theta = gp->refine_theta;
+  if (last_refined) *last_refined = gp->last_refined;
+  return DMO_OK;
+}
+
 int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double* mean, double* var, int precision) {
   if (!ctx) return DMO_ERR_ARG;
   DMO_CUDA(cudaSetDevice(ctx->device));
@@ -552,6 +725,8 @@ int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double*
     DMO_TRY(gp_predict_fp64(ctx, gp, xn.p, P, om.d, ov.d));
   } else if (precision == DMO_GP_TENSOR) {
     DMO_TRY(gp_predict_tensor(ctx, gp, xn.p, P, om.d, ov.d));
+  } else if (precision == DMO_GP_AUTO) {
+    DMO_TRY(gp_predict_auto(ctx, gp, xn.p, P, om.d, ov.d));
   } else {
     return dmo_fail(ctx, DMO_ERR_ARG, "gp_predict: unknown precision %d", precision);
   }

@@ -23,6 +23,14 @@ struct dmo_gp {
   DevBuf<uint16_t> Lhi, Llo;  // (M, Npad, Npad) fp16 split of the row-scaled L^-1
   DevBuf<float> Lscale;       // (M, Npad) 1 / (row scale * K_* scale), powers of two
   DevBuf<int> Kexp;           // (M,) K_* scaling exponents
+  // DMO_GP_AUTO: per-model calibration of the tensor path against the float64 path on probe candidates (gp.cu)
+  bool calibrated = false;
+  bool auto_mean_tensor = false;  // fp32-K_* mean holds 1e-5 on the probes (with margin)
+  bool auto_var_tensor = false;   // split-fp16 variance holds 1e-5 * prior on the probes (with margin)
+  double cal_mean_err = 0.0;      // max |mean_t - mean_64| / max(|mean_64|, y_std) over the probes
+  double cal_var_err = 0.0;       // max |var_t - var_64| / prior over the probes
+  double refine_theta = 1.0;      // rows with var_t < theta * prior are recomputed in float64
+  int64_t last_refined = 0;       // rows recomputed by the last DMO_GP_AUTO predict
 };
 
 int gp_predict_fp64(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var);

@@ -1,4 +1,4 @@
-// GP posterior variance on the 5th-generation tensor cores (DMO_GP_TENSOR).
+// GP posterior variance on the 5th-generation tensor cores (DMO_GP_TENSOR, and the fast leg of DMO_GP_AUTO).
 //
 //   ||L^-1 K_*^T||^2 per candidate  ==  row sums of  D^2,   D[p][i] = sum_k K_*[p][k] * Linv[i][k]
 //
@@ -7,20 +7,21 @@
 //   * split precision: every float operand x is carried as two fp16 numbers hi + lo (22 significand bits) after an
 //     exact power-of-two scaling (per Linv row, per objective for K_*) that keeps both halves in fp16's normal range;
 //     D accumulates hi*hi + hi*lo + lo*hi in fp32 (three MMAs per product, the lo*lo term is below fp32 resolution);
-//   * A operand = K_* tile (128 candidates x 64 k), B operand = Linv tile (256 rows x 64 k), so one TMEM lane is one
-//     candidate and the epilogue's sum of squares is a private per-thread accumulation (no cross-lane reduction);
+//   * A operand = K_* tile (2 x 128 candidates x 32 k), B operand = Linv tile (256 rows x 32 k), so one TMEM lane is
+//     one candidate and the epilogue's sum of squares is a private per-thread accumulation (no cross-lane reduction);
 //   * Linv is lower triangular: the row block [256 j, 256 j + 256) only needs k < 256 (j + 1) -- half the MMAs skipped;
-//   * operand tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 2-stage shared-memory ring, completion
+//   * operand tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_64B) into a 3-stage shared-memory ring, completion
 //     on mbarriers; one elected thread issues the MMAs; tcgen05.commit releases the ring slots and publishes the
-//     accumulator; four epilogue warps drain TMEM with tcgen05.ld while the next row block is being multiplied
-//     (two accumulator buffers of 256 columns);
-//   * persistent CTAs (one per SM) walk the (objective, candidate block) work list.
+//     accumulator; four epilogue warps drain TMEM with tcgen05.ld;
+//   * persistent CTAs (one per SM) walk a list of equal-cost work items (version 3, below) while the K_* producer and
+//     the posterior-mean pass run beside them on the context's second stream.
 //
-// K_* itself and the posterior mean are produced by kstar_tensor_kernel in fp32 (relative error ~1e-6 on K_*),
-// the mean reduction is accumulated in float64 in a fixed order (deterministic).
+// K_* itself is produced by kstar_tensor_kernel in fp32 (relative error ~1e-6 on K_*), the mean reduction is
+// accumulated in float64 in a fixed order (deterministic).
 //
-// Accuracy contract of this path: |var - var_ref| <= 1e-5 * prior variance (tests/test_gpu_parity.py); the float64
-// path (gp.cu) is the one that matches scikit-learn to ~1e-10.
+// Accuracy contract of this path: |var - var_ref| <= 1e-5 * prior variance and |mean - mean_ref| <= 1e-5 on
+// well-conditioned posteriors (tests/test_gpu_parity.py); DMO_GP_AUTO (gp.cu) measures both against the float64 path
+// on probe candidates per model and recomputes in float64 what this path cannot hold to 1e-5 relative.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cudaTypedefs.h>
@@ -30,16 +31,10 @@
 
 namespace {
 
-constexpr int TM = 128;      // candidates per tile  (UMMA M, TMEM lanes)
-constexpr int TN = 256;      // Linv rows per tile   (UMMA N, TMEM columns per accumulator)
-constexpr int TK = 64;       // k elements per stage (128 bytes of fp16 = one swizzle atom row)
+constexpr int TM = 128;      // candidates per UMMA tile  (UMMA M, TMEM lanes)
+constexpr int TN = 256;      // Linv rows per tile        (UMMA N, TMEM columns per accumulator)
 constexpr int UK = 16;       // UMMA K for 16-bit inputs
-constexpr int STAGES = 2;
-constexpr int A_BYTES = TM * TK * 2;   // 16 KiB
-constexpr int B_BYTES = TN * TK * 2;   // 32 KiB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands: 96 KiB
 constexpr int NTHREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,164 +132,6 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): fp16 A/B (format 0), fp32 accumulate (c_format 1),
 // both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-
-// ------------------------------------------------------------------------------------------------ the GEMM
-struct GemmParams {
-  int M;           // objectives
-  int n_pb;        // candidate blocks (of TM) in this chunk
-  int n_jt;        // Linv row blocks (of TN)
-  int64_t k_rows;  // rows per objective in the K_* tensor maps (= Pc_alloc)
-  int64_t l_rows;  // rows per objective in the Linv tensor maps (= Npad)
-  const float* inv_scale;  // [M][Npad]  1 / (row scale * K_* scale)
-  double* vnorm;           // [M][vn_ld]
-  int64_t vn_ld;
-  int* abort_flag;
-};
-
-__global__ void __launch_bounds__(NTHREADS, 1)
-    gp_var_tc_kernel(const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl,
-                     const __grid_constant__ CUtensorMap map_lh, const __grid_constant__ CUtensorMap map_ll,
-                     const GemmParams prm) {
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte aligned tile area (SWIZZLE_128B atoms are 1024 B)
-  uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(tiles + (size_t)STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
-  uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
-  uint64_t* acc_full = bars + 2 * STAGES;      // [2]  MMA -> epilogue
-  uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2]  epilogue -> MMA
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
-  volatile int* abort_flag = prm.abort_flag;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // one arrival per epilogue warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {  // TMEM: 512 columns = two 128 x 256 fp32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int n_work = prm.M * prm.n_pb;
-
-  if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int m = w / prm.n_pb, pb = w - m * prm.n_pb;
-        const int a_row = (int)(m * prm.k_rows + (int64_t)pb * TM);
-        for (int jt = 0; jt < prm.n_jt; ++jt) {
-          const int b_row = (int)(m * prm.l_rows + (int64_t)jt * TN);
-          const int nkc = (jt + 1) * (TN / TK);
-          for (int kc = 0; kc < nkc; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1u, abort_flag);
-            uint8_t* st = tiles + (size_t)stage * STAGE_BYTES;
-            mbar_expect_tx(&full[stage], STAGE_BYTES);
-            tma_load_2d(&map_kh, &full[stage], st, kc * TK, a_row);
-            tma_load_2d(&map_kl, &full[stage], st + A_BYTES, kc * TK, a_row);
-            tma_load_2d(&map_lh, &full[stage], st + 2 * A_BYTES, kc * TK, b_row);
-            tma_load_2d(&map_ll, &full[stage], st + 2 * A_BYTES + B_BYTES, kc * TK, b_row);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        for (int jt = 0; jt < prm.n_jt; ++jt) {
-          mbar_wait(&acc_empty[acc], acc_phase ^ 1u, abort_flag);  // epilogue has drained this accumulator
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * TN;
-          const int nkc = (jt + 1) * (TN / TK);
-          for (int kc = 0; kc < nkc; ++kc) {
-            mbar_wait(&full[stage], phase, abort_flag);  // TMA bytes have landed
-            tc_fence_after();
-            const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
-            const uint64_t a_hi = make_sdesc(sa), a_lo = make_sdesc(sa + A_BYTES);
-            const uint64_t b_hi = make_sdesc(sa + 2 * A_BYTES), b_lo = make_sdesc(sa + 2 * A_BYTES + B_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < TK / UK; ++ks) {
-              const uint64_t adv = (uint64_t)((ks * UK * 2) >> 4);  // +32 bytes per UMMA_K inside the swizzle atom
-              tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kc | ks) ? 1u : 0u);
-              tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-              tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1u);
-            }
-            tc_commit(&empty[stage]);  // ring slot reusable once these MMAs have read it
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-          tc_commit(&acc_full[acc]);  // accumulator complete
-          acc ^= 1u;
-          if (acc == 0) acc_phase ^= 1u;
-        }
-      }
-    }
-  } else {
-    // ===================================================== epilogue: TMEM -> registers -> sum of squares
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-    const int row = quarter * 32 + lane;  // candidate within the tile
-    uint32_t acc = 0, acc_phase = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int m = w / prm.n_pb, pb = w - m * prm.n_pb;
-      const float* isc = prm.inv_scale + (int64_t)m * prm.l_rows;
-      double total = 0.0;
-      for (int jt = 0; jt < prm.n_jt; ++jt) {
-        mbar_wait(&acc_full[acc], acc_phase, abort_flag);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
-        float part = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-          uint32_t r[32];
-          tc_ld_32x32(t_addr + c0, r);
-          tc_wait_ld();
-          const float* sc = isc + jt * TN + c0;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float t = __uint_as_float(r[e]) * __ldg(sc + e);
-            part = fmaf(t, t, part);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        total += (double)part;
-        acc ^= 1u;
-        if (acc == 0) acc_phase ^= 1u;
-      }
-      prm.vnorm[(int64_t)m * prm.vn_ld + (int64_t)pb * TM + row] = total;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ the GEMM, version 2
 // Same contraction, 1.5x less L2 -> shared-memory traffic per MMA: a work item owns 256 candidates (two M = 128
@@ -472,6 +309,220 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 }
 }  // namespace v2
 
+// ------------------------------------------------------------------------------------------------ the GEMM, version 3
+// Same tiles and pipeline as version 2; what changes is the work list and where K_* comes from.
+//   * A work item is (objective, 256 candidates, PAIR of Linv row blocks {q, n_jt - 1 - q}): every item costs the same
+//     n_jt + 1 k-blocks, so a static round-robin over the persistent CTAs has a tail of at most one item in
+//     M * n_pb * ceil(n_jt / 2) (6144 at the BASELINE shape, 41.5 rounds on 148 SMs).
+//   * Items are ordered (objective, candidate block, pair): the ceil(n_jt / 2) CTAs that hold the same candidate block
+//     start together at k = 0 and walk k at the same (MMA-bound) rate, so one of them pulls a K_* tile from DRAM and the
+//     others hit it in L2; version 2 ran 148 different candidate blocks at once and re-read every K_* tile from DRAM
+//     once per row block (22.6 GB per launch for 3.2 GB of operands).
+//   * The kernel is launched while the K_* producer (kstar_tensor_kernel, on the context's second stream) is still
+//     running: the TMA thread waits for the producer's per-candidate-block completion counter before the first load of
+//     an item (ld.acquire.gpu + fence.proxy.async), so K_* generation and the posterior mean overlap the contraction
+//     instead of preceding it.
+namespace v3 {
+using v2::make_sdesc64;
+using v2::STAGE_BYTES2;
+using v2::STAGES2;
+using v2::TILE_BYTES2;
+using v2::TK2;
+using v2::TM2;
+using v2::TN2;
+using v2::GEMM_SMEM2;
+
+struct GemmParams3 {
+  int M, n_pb, n_jt, n_q;
+  int64_t k_rows, l_rows;
+  const float* inv_scale;
+  double* vnorm;  // [n_q][M][vn_ld]
+  int64_t vn_ld;
+  int* abort_flag;
+  const unsigned* ready;  // [n_pb] completion counters of the K_* producer (nullptr: K_* is complete at launch)
+  unsigned ready_target;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+    gp_var_tc3_kernel(const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl,
+                      const __grid_constant__ CUtensorMap map_lh, const __grid_constant__ CUtensorMap map_ll,
+                      const GemmParams3 prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(tiles + (size_t)STAGES2 * STAGE_BYTES2);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES2;
+  uint64_t* acc_full = bars + 2 * STAGES2;
+  uint64_t* acc_empty = bars + 2 * STAGES2 + 1;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES2 + 2);
+  volatile int* abort_flag = prm.abort_flag;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_m = prm.n_pb * prm.n_q;
+  const int n_work = prm.M * per_m;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int m = w / per_m, r = w - m * per_m;
+        const int pb = r / prm.n_q, q = r - pb * prm.n_q;
+        if (prm.ready) {  // the K_* rows of this candidate block must have been written (by another kernel, generic proxy)
+          uint32_t spins = 0;
+          while (ld_acquire_u32(prm.ready + pb) < prm.ready_target) {
+            __nanosleep(256);
+            if ((++spins & 0xFFu) == 0u) {
+              if (*abort_flag) break;
+              if (spins > (1u << 23)) {  // ~2 s: the producer is not running
+                *abort_flag = 2;
+                break;
+              }
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");  // order the TMA (async proxy) reads after the acquire
+        }
+        const int a_row = (int)(m * prm.k_rows + (int64_t)pb * TM2);
+        const int jhi = prm.n_jt - 1 - q;
+        for (int s = 0; s < 2; ++s) {
+          const int jt = s ? q : jhi;
+          if (s && q == jhi) break;
+          const int b_row = (int)(m * prm.l_rows + (int64_t)jt * TN2);
+          const int nkc = (jt + 1) * (TN2 / TK2);
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1u, abort_flag);
+            uint8_t* st = tiles + (size_t)stage * STAGE_BYTES2;
+            mbar_expect_tx(&full[stage], STAGE_BYTES2);
+            tma_load_2d(&map_kh, &full[stage], st, kc * TK2, a_row);
+            tma_load_2d(&map_kl, &full[stage], st + TILE_BYTES2, kc * TK2, a_row);
+            tma_load_2d(&map_lh, &full[stage], st + 2 * TILE_BYTES2, kc * TK2, b_row);
+            tma_load_2d(&map_ll, &full[stage], st + 3 * TILE_BYTES2, kc * TK2, b_row);
+            if (++stage == STAGES2) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int r = w % per_m;
+        const int q = r % prm.n_q;
+        const int jhi = prm.n_jt - 1 - q;
+        for (int s = 0; s < 2; ++s) {
+          const int jt = s ? q : jhi;
+          if (s && q == jhi) break;
+          mbar_wait(acc_empty, acc_phase ^ 1u, abort_flag);
+          tc_fence_after();
+          const int nkc = (jt + 1) * (TN2 / TK2);
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&full[stage], phase, abort_flag);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t d_tmem = tmem_base + h * TN2;
+              const uint32_t a_off = h * (128 * TK2 * 2);
+              const uint64_t a_hi = make_sdesc64(sa + a_off), a_lo = make_sdesc64(sa + TILE_BYTES2 + a_off);
+              const uint64_t b_hi = make_sdesc64(sa + 2 * TILE_BYTES2), b_lo = make_sdesc64(sa + 3 * TILE_BYTES2);
+#pragma unroll
+              for (int ks = 0; ks < TK2 / UK; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UK * 2) >> 4);
+                tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kc | ks) ? 1u : 0u);
+                tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+                tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1u);
+              }
+            }
+            tc_commit(&empty[stage]);
+            if (++stage == STAGES2) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          tc_commit(acc_full);
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int m = w / per_m, r = w - m * per_m;
+      const int pb = r / prm.n_q, q = r - pb * prm.n_q;
+      const float* isc = prm.inv_scale + (int64_t)m * prm.l_rows;
+      const int jhi = prm.n_jt - 1 - q;
+      double total0 = 0.0, total1 = 0.0;
+      for (int s = 0; s < 2; ++s) {
+        const int jt = s ? q : jhi;
+        if (s && q == jhi) break;
+        mbar_wait(acc_full, acc_phase, abort_flag);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN2; c0 += 32) {
+          uint32_t r0[32], r1[32];
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c0;
+          tc_ld_32x32(t_addr, r0);
+          tc_ld_32x32(t_addr + TN2, r1);
+          tc_wait_ld();
+          const float* sc = isc + jt * TN2 + c0;
+          // four independent fp32 partial sums per sub-tile over 8 squares each, folded into float64 every 32 columns:
+          // the rounding of the sum of squares stays at the 2^-24 * sqrt(8) level instead of growing with N
+          float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float sv = __ldg(sc + e);
+            const float t0 = __uint_as_float(r0[e]) * sv, t1 = __uint_as_float(r1[e]) * sv;
+            p0[e & 3] = fmaf(t0, t0, p0[e & 3]);
+            p1[e & 3] = fmaf(t1, t1, p1[e & 3]);
+          }
+          total0 += ((double)p0[0] + (double)p0[1]) + ((double)p0[2] + (double)p0[3]);
+          total1 += ((double)p1[0] + (double)p1[1]) + ((double)p1[2] + (double)p1[3]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        acc_phase ^= 1u;
+      }
+      double* out = prm.vnorm + ((int64_t)q * prm.M + m) * prm.vn_ld + (int64_t)pb * TM2 + quarter * 32 + lane;
+      out[0] = total0;
+      out[128] = total1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+}  // namespace v3
+
 // ------------------------------------------------------------------------------------------------ operand preparation
 // Linv row -> scaled fp16 hi / lo.  One block per (objective, row).
 __global__ void split_linv_kernel(const double* __restrict__ Linv, int64_t Npad, int M, const int* __restrict__ k_exp,
@@ -547,7 +598,7 @@ __global__ void __launch_bounds__(KT_TN)
                         const double* __restrict__ Xt, int64_t N, int d, int M, int kind,
                         const double* __restrict__ inv_ls, const double* __restrict__ constant,
                         const int* __restrict__ k_exp, int64_t ldk, int64_t plane, uint16_t* __restrict__ Kh,
-                        uint16_t* __restrict__ Kl) {
+                        uint16_t* __restrict__ Kl, unsigned* __restrict__ ready) {
   extern __shared__ __align__(16) float sxf[];  // [KT_TP][DMAX] candidate tile, then [M][DMAX] 1/l, [M] c * 2^kexp
   float* s_il = sxf + KT_TP * DMAX;
   float* s_c = s_il + M * DMAX;
@@ -574,13 +625,12 @@ __global__ void __launch_bounds__(KT_TN)
                         (j1 < d && n0 + 1 < N) ? (float)Xt[(n0 + 1) * d + j1] : 0.f);
   }
   __syncthreads();
-  if (n0 >= ldk) return;
   const bool live_a = n0 < N, live_b = n0 + 1 < N;
   uint32_t* Kh32 = reinterpret_cast<uint32_t*>(Kh);
   uint32_t* Kl32 = reinterpret_cast<uint32_t*>(Kl);
   for (int q = 0; q < KT_TP; ++q) {
     const int64_t pl = pt0 + q;
-    if (pl >= Pcpad) break;
+    if (pl >= Pcpad || n0 >= ldk) break;
     const float4* xc = reinterpret_cast<const float4*>(sxf + q * DMAX);
     float sa = 0.f, sb = 0.f;
     if (ISO) {
@@ -638,6 +688,15 @@ __global__ void __launch_bounds__(KT_TN)
       Kl32[o] = *reinterpret_cast<const uint32_t*>(&l);
     }
   }
+  if (ready) {
+    // publish this block's rows to the variance kernel that is already running (v3::gp_var_tc3_kernel): every thread's
+    // stores happen-before the barrier, the fence makes them visible at GPU scope before the counter moves
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(ready + pt0 / 256, 1u);
+    }
+  }
 }
 
 // mean[p][m] = y_std * sum_n K_*[p][n] alpha[n] + y_mean from the split K_* (hi + lo = 22 bits): HBM-bound pass,
@@ -675,8 +734,8 @@ __global__ void var_finish_tc_kernel(const double* __restrict__ vnorm, int nplan
   if (t >= Pc * M) return;
   int64_t pl = t / M;
   int m = (int)(t - pl * M);
-  double vn = vnorm[(int64_t)m * ld + pl];
-  if (nplanes == 2) vn += vnorm[((int64_t)M + m) * ld + pl];  // the two halves of the Linv row blocks, fixed order
+  double vn = 0.0;
+  for (int q = 0; q < nplanes; ++q) vn += vnorm[((int64_t)q * M + m) * ld + pl];  // partial sums of the work items, fixed order
   double v = (constant[m] + noise[m]) - vn;
   if (v < 0.0) v = 0.0;
   double sd = sqrt(v * (ystd[m] * ystd[m]));
@@ -696,9 +755,9 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// 2-D fp16 tensor [rows][cols] (cols contiguous), box = box_rows x 64 columns, 128-byte swizzle
+// 2-D fp16 tensor [rows][cols] (cols contiguous), box = box_rows x box_cols
 int make_map(dmo_ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-             uint32_t box_cols = TK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+             uint32_t box_cols, CUtensorMapSwizzle swz) {
   auto fn = get_encode_fn();
   if (!fn) return dmo_fail(ctx, DMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {cols, rows};
@@ -743,51 +802,64 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   DMO_REQUIRE(d <= 64, "gp_predict(tensor): at most 64 input dimensions (got %d); use DMO_GP_FP64", d);
   DMO_REQUIRE(Npad % TN == 0, "gp_predict(tensor): internal padding error");
   DMO_TRY(prepare_tensor_state(ctx, gp));
+  // kernel version: 3 (default) = equal-cost paired row blocks in L2-friendly order, overlapped with the K_* producer;
+  // 2 = previous schedule, K_* / mean / variance back to back on one stream (DMO_GP_TC=2, kept for comparison)
+  int version = 3;
+  if (const char* e = getenv("DMO_GP_TC")) version = atoi(e) == 2 ? 2 : 3;
+  const bool overlap = version == 3 && !(getenv("DMO_GP_NO_OVERLAP") && atoi(getenv("DMO_GP_NO_OVERLAP")));
+  constexpr int64_t TMv = v2::TM2;
   // candidate chunk: K_* hi/lo (2 x M x Pc x Npad fp16) within ~6 GiB
   int64_t Pc_max = ((int64_t)6 << 30) / ((int64_t)M * Npad * 4);
-  Pc_max = (Pc_max / TM) * TM;
-  if (Pc_max < TM) Pc_max = TM;
-  // kernel version: 2 (default) = 256-candidate work items, SWIZZLE_64B, 3 stages; 1 = first version (DMO_GP_TC=1)
-  int version = 2;
-  if (const char* e = getenv("DMO_GP_TC")) version = atoi(e) == 1 ? 1 : 2;
-  const int64_t TMv = version == 2 ? v2::TM2 : TM;
   Pc_max = (Pc_max / TMv) * TMv;
   if (Pc_max < TMv) Pc_max = TMv;
   const int64_t Pc_alloc = P < Pc_max ? ceil_div(P, TMv) * TMv : Pc_max;
+  const int n_jt = (int)(Npad / v2::TN2);
+  const int n_q = version == 3 ? (n_jt + 1) / 2 : 2;
+  const int64_t n_chunks = ceil_div(P, Pc_alloc);
+  const int n_pb_alloc = (int)(Pc_alloc / TMv);
   DevBuf<uint16_t> Kh, Kl;
   DevBuf<double> vnorm;
   DevBuf<int> abort_flag;
+  DevBuf<unsigned> ready;
   DMO_TRY(Kh.alloc(ctx, (size_t)M * Pc_alloc * Npad));
   DMO_TRY(Kl.alloc(ctx, (size_t)M * Pc_alloc * Npad));
-  DMO_TRY(vnorm.alloc(ctx, (size_t)2 * M * Pc_alloc));
+  DMO_TRY(vnorm.alloc(ctx, (size_t)n_q * M * Pc_alloc));
   DMO_TRY(abort_flag.alloc(ctx, 1));
+  DMO_TRY(ready.alloc(ctx, (size_t)n_chunks * n_pb_alloc));
   DMO_CUDA(cudaMemsetAsync(abort_flag.p, 0, sizeof(int), ctx->stream));
+  DMO_CUDA(cudaMemsetAsync(ready.p, 0, (size_t)n_chunks * n_pb_alloc * sizeof(unsigned), ctx->stream));
   CUtensorMap map_kh, map_kl, map_lh, map_ll;
-  if (version == 2) {
-    DMO_TRY(make_map(ctx, &map_kh, Kh.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
-    DMO_TRY(make_map(ctx, &map_kl, Kl.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
-    DMO_TRY(make_map(ctx, &map_lh, gp->Lhi.p, (uint64_t)M * Npad, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
-    DMO_TRY(make_map(ctx, &map_ll, gp->Llo.p, (uint64_t)M * Npad, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
-    DMO_CUDA(cudaFuncSetAttribute(v2::gp_var_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::GEMM_SMEM2));
-  } else {
-    DMO_TRY(make_map(ctx, &map_kh, Kh.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, TM));
-    DMO_TRY(make_map(ctx, &map_kl, Kl.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, TM));
-    DMO_TRY(make_map(ctx, &map_lh, gp->Lhi.p, (uint64_t)M * Npad, (uint64_t)Npad, TN));
-    DMO_TRY(make_map(ctx, &map_ll, gp->Llo.p, (uint64_t)M * Npad, (uint64_t)Npad, TN));
-    DMO_CUDA(cudaFuncSetAttribute(gp_var_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-  }
+  DMO_TRY(make_map(ctx, &map_kh, Kh.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
+  DMO_TRY(make_map(ctx, &map_kl, Kl.p, (uint64_t)M * Pc_alloc, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
+  DMO_TRY(make_map(ctx, &map_lh, gp->Lhi.p, (uint64_t)M * Npad, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
+  DMO_TRY(make_map(ctx, &map_ll, gp->Llo.p, (uint64_t)M * Npad, (uint64_t)Npad, 256, v2::TK2, CU_TENSOR_MAP_SWIZZLE_64B));
+  DMO_CUDA(cudaFuncSetAttribute(v2::gp_var_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::GEMM_SMEM2));
+  DMO_CUDA(cudaFuncSetAttribute(v3::gp_var_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::GEMM_SMEM2));
   const int64_t kplane = Pc_alloc * Npad;
-  for (int64_t p_base = 0; p_base < P; p_base += Pc_alloc) {
+  // producer side (K_* and the mean) on the second stream when overlapping, else in line
+  cudaStream_t ps = overlap ? ctx->aux : ctx->stream;
+  if (overlap) {
+    DMO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));  // allocations, memsets and Xn are ready
+    DMO_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+  }
+  int64_t chunk = 0;
+  for (int64_t p_base = 0; p_base < P; p_base += Pc_alloc, ++chunk) {
     const int64_t Pc = (P - p_base) < Pc_alloc ? (P - p_base) : Pc_alloc;
     const int64_t Pcpad = ceil_div(Pc, TMv) * TMv;
+    unsigned* rdy = ready.p + chunk * n_pb_alloc;
+    dim3 gk((unsigned)(Npad / (2 * KT_TN)), (unsigned)ceil_div(Pcpad, KT_TP));
+    if (overlap && chunk > 0) {  // the K_* buffers are reused: the previous chunk's contraction must have drained them
+      DMO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+      DMO_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    }
     {
-      ProfileScope ps(ctx, "gp_kstar");
-      dim3 gk((unsigned)(Npad / (2 * KT_TN)), (unsigned)ceil_div(Pcpad, KT_TP));
+      ProfileScope ps_(ctx, "gp_kstar", ps);
       const int dmax = d <= 32 ? 32 : 64;
       size_t smem = (size_t)(KT_TP * dmax + M * dmax + M) * sizeof(float);
-#define KSTAR_LAUNCH(ISO_, DM_)                                                                                      \
-  DMO_LAUNCH((kstar_tensor_kernel<ISO_, DM_>), gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M, gp->kernel, \
-             gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p)
+#define KSTAR_LAUNCH(ISO_, DM_)                                                                                   \
+  DMO_LAUNCH_ON(ps, (kstar_tensor_kernel<ISO_, DM_>), gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M,    \
+                gp->kernel, gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p,                    \
+                (overlap && d_var) ? rdy : nullptr)
       if (gp->isotropic) {
         if (d <= 32)
           KSTAR_LAUNCH(true, 32);
@@ -802,15 +874,38 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
 #undef KSTAR_LAUNCH
     }
     {
-      ProfileScope ps(ctx, "gp_mean");
-      DMO_LAUNCH(mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane, M,
-                 gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
+      ProfileScope ps_(ctx, "gp_mean", ps);
+      DMO_LAUNCH_ON(ps, mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane,
+                    M, gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
     }
-    if (d_var && version == 2) {
+    if (overlap) DMO_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
+    if (d_var && version == 3) {
+      v3::GemmParams3 prm;
+      prm.M = M;
+      prm.n_pb = (int)(Pcpad / TMv);
+      prm.n_jt = n_jt;
+      prm.n_q = n_q;
+      prm.k_rows = Pc_alloc;
+      prm.l_rows = Npad;
+      prm.inv_scale = gp->Lscale.p;
+      prm.vnorm = vnorm.p;
+      prm.vn_ld = Pc_alloc;
+      prm.abort_flag = abort_flag.p;
+      prm.ready = overlap ? rdy : nullptr;
+      prm.ready_target = 8u * gk.x;  // KT_TP = 32 candidates per producer block: 8 tile rows x gk.x column blocks per 256
+      const int n_work = prm.M * prm.n_pb * prm.n_q;
+      const int grid = n_work < ctx->sm_count ? n_work : ctx->sm_count;
+      {
+        ProfileScope ps_(ctx, "gp_var");
+        DMO_LAUNCH(v3::gp_var_tc3_kernel, grid, NTHREADS, v2::GEMM_SMEM2, map_kh, map_kl, map_lh, map_ll, prm);
+      }
+      DMO_LAUNCH(var_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, n_q, Pc, Pc_alloc, M,
+                 gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
+    } else if (d_var) {
       v2::GemmParams2 prm;
       prm.M = M;
       prm.n_pb = (int)(Pcpad / v2::TM2);
-      prm.n_jt = (int)(Npad / v2::TN2);
+      prm.n_jt = n_jt;
       // split the row blocks where the cumulative MMA count sum_{j < J} (j + 1) is closest to half of the total
       {
         const int64_t tot = (int64_t)prm.n_jt * (prm.n_jt + 1) / 2;
@@ -834,36 +929,20 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       const int n_work = prm.M * prm.n_pb * 2;
       const int grid = n_work < ctx->sm_count ? n_work : ctx->sm_count;
       {
-        ProfileScope ps(ctx, "gp_var");
+        ProfileScope ps_(ctx, "gp_var");
         DMO_LAUNCH(v2::gp_var_tc2_kernel, grid, NTHREADS, v2::GEMM_SMEM2, map_kh, map_kl, map_lh, map_ll, prm);
       }
       DMO_LAUNCH(var_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, 2, Pc, Pc_alloc, M,
                  gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
-    } else if (d_var) {
-      GemmParams prm;
-      prm.M = M;
-      prm.n_pb = (int)(Pcpad / TM);
-      prm.n_jt = (int)(Npad / TN);
-      prm.k_rows = Pc_alloc;
-      prm.l_rows = Npad;
-      prm.inv_scale = gp->Lscale.p;
-      prm.vnorm = vnorm.p;
-      prm.vn_ld = Pc_alloc;
-      prm.abort_flag = abort_flag.p;
-      const int n_work = prm.M * prm.n_pb;
-      const int grid = n_work < ctx->sm_count ? n_work : ctx->sm_count;
-      {
-        ProfileScope ps(ctx, "gp_var");
-        DMO_LAUNCH(gp_var_tc_kernel, grid, NTHREADS, GEMM_SMEM, map_kh, map_kl, map_lh, map_ll, prm);
-      }
-      DMO_LAUNCH(var_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, 1, Pc, Pc_alloc, M,
-                 gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
     }
+    if (overlap) DMO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // mean (and K_*) of this chunk done
   }
   DMO_CHECK_LAUNCH();
   int h_abort = 0;
   DMO_CUDA(cudaMemcpyAsync(&h_abort, abort_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   DMO_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h_abort) return dmo_fail(ctx, DMO_ERR_INTERNAL, "gp_predict(tensor): pipeline watchdog tripped");
+  if (h_abort)
+    return dmo_fail(ctx, DMO_ERR_INTERNAL, "gp_predict(tensor): pipeline watchdog tripped (%s)",
+                    h_abort == 2 ? "K_* producer did not deliver" : "mbarrier wait timed out");
   return DMO_OK;
 }

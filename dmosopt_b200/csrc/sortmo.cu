@@ -201,6 +201,49 @@ __global__ void first_coord_keys_kernel(const double* __restrict__ X, int64_t n,
     idx[i] = (uint32_t)i;
   }
 }
+// two-set form, MOEA.get_duplicates(X, Y) (MOEA.py:426-437 as MOASMO.py:442 calls it): row i of X is a duplicate when
+// some row j < i of Y lies within eps (cdist(X, Y) with the upper triangle INCLUDING the diagonal masked).  X and Y
+// rows share one sorted order on the first coordinate; ids >= n are rows of Y.
+__global__ void pair_keys_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Y, int64_t ny, int d,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n + ny) return;
+  keys[i] = f64_to_ordered(i < n ? X[i * d] : Y[(i - n) * d]);
+  idx[i] = (uint32_t)i;
+}
+
+__global__ void duplicates_pair_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Y, int64_t ny,
+                                       const uint64_t* __restrict__ skeys, const uint32_t* __restrict__ sidx, int d,
+                                       double eps, uint8_t* __restrict__ is_dup) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n + ny) return;
+  const uint32_t i = sidx[p];
+  if (i >= n) return;  // a row of Y: only probed, never flagged
+  const double x0 = ordered_to_f64(skeys[p]);
+  const double* xi = X + (int64_t)i * d;
+  bool dup = false;
+  for (int dir = -1; dir <= 1 && !dup; dir += 2) {
+    for (int64_t q = p + dir; q >= 0 && q < n + ny; q += dir) {
+      if (fabs(ordered_to_f64(skeys[q]) - x0) > eps) break;
+      const uint32_t jx = sidx[q];
+      if (jx < n) continue;              // another row of X
+      const uint32_t j = jx - (uint32_t)n;
+      if (j >= i) continue;              // np.triu_indices(len(X), m=len(Y)): only j < i is compared
+      const double* yj = Y + (int64_t)j * d;
+      double s = 0.0;
+      for (int c = 0; c < d; ++c) {
+        double t = xi[c] - yj[c];
+        s += t * t;
+      }
+      if (sqrt(s) <= eps) {
+        dup = true;
+        break;
+      }
+    }
+  }
+  is_dup[i] = dup ? 1 : 0;
+}
+
 __global__ void duplicates_kernel(const double* __restrict__ X, const uint64_t* __restrict__ skeys,
                                   const uint32_t* __restrict__ sidx, int64_t n, int d, double eps,
                                   uint8_t* __restrict__ is_dup) {
@@ -520,6 +563,34 @@ int dmo_get_duplicates(dmo_ctx* ctx, const double* X, int64_t n, int d, double e
   DMO_LAUNCH(first_coord_keys_kernel, g, 256, 0, x.d, n, d, k0.p, i0.p);
   DMO_TRY(prim_sort_pairs_u64(ctx, k0.p, k1.p, i0.p, i1.p, n, 0, 64));
   DMO_LAUNCH(duplicates_kernel, g, 256, 0, x.d, k1.p, i1.p, n, d, eps, o.d);
+  DMO_CHECK_LAUNCH();
+  DMO_TRY(o.finish(ctx));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
+
+int dmo_get_duplicates_pair(dmo_ctx* ctx, const double* X, int64_t n, const double* Y, int64_t ny, int d, double eps,
+                            uint8_t* is_dup) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return DMO_OK;
+  DMO_REQUIRE(n > 0 && ny >= 0 && X && is_dup && d >= 1 && (Y || ny == 0), "get_duplicates_pair: bad arguments");
+  In<double> x, y;
+  Out<uint8_t> o;
+  DMO_TRY(x.init(ctx, X, (size_t)n * d));
+  DMO_TRY(y.init(ctx, Y, (size_t)ny * d));
+  DMO_TRY(o.init(ctx, is_dup, (size_t)n));
+  const int64_t t = n + ny;
+  DevBuf<uint64_t> k0, k1;
+  DevBuf<uint32_t> i0, i1;
+  DMO_TRY(k0.alloc(ctx, t));
+  DMO_TRY(k1.alloc(ctx, t));
+  DMO_TRY(i0.alloc(ctx, t));
+  DMO_TRY(i1.alloc(ctx, t));
+  const unsigned g = (unsigned)ceil_div(t, 256);
+  DMO_LAUNCH(pair_keys_kernel, g, 256, 0, x.d, n, y.d, ny, d, k0.p, i0.p);
+  DMO_TRY(prim_sort_pairs_u64(ctx, k0.p, k1.p, i0.p, i1.p, t, 0, 64));
+  DMO_LAUNCH(duplicates_pair_kernel, g, 256, 0, x.d, n, y.d, ny, k1.p, i1.p, d, eps, o.d);
   DMO_CHECK_LAUNCH();
   DMO_TRY(o.finish(ctx));
   DMO_CUDA(cudaStreamSynchronize(ctx->stream));

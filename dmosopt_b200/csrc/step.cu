@@ -14,11 +14,13 @@ extern "C" {
 int dmo_nsga2_step(dmo_ctx* ctx, dmo_gp* gp, double* pop_x, double* pop_y, int32_t* rank, int64_t pop, int d, int M,
                    double crossover_prob, double mutation_prob, double mutation_rate, const double* di_crossover,
                    const double* di_mutation, const double* xlb, const double* xub, uint64_t seed, uint64_t stream_id,
-                   int precision, int with_variance, int round_to_f32, const double* hv_ref, int64_t* n_children,
+                   int precision, int distance_metric, int with_variance, int round_to_f32, const double* hv_ref, int64_t* n_children,
                    double* hv_out) {
   if (!ctx) return DMO_ERR_ARG;
   DMO_CUDA(cudaSetDevice(ctx->device));
   DMO_REQUIRE(gp && pop_x && pop_y && rank && pop >= 2 && d >= 1 && M >= 1, "nsga2_step: bad arguments");
+  DMO_REQUIRE(distance_metric == DMO_METRIC_NONE || distance_metric == DMO_METRIC_CROWDING || distance_metric == DMO_METRIC_EUCLIDEAN,
+              "nsga2_step: unknown distance metric %d", distance_metric);
   DMO_REQUIRE(dmo_is_device_ptr(pop_x) && dmo_is_device_ptr(pop_y) && dmo_is_device_ptr(rank),
               "nsga2_step: the population (pop_x, pop_y, rank) must be resident on the device");
   int64_t poolsize = pop / 2;  // int(round(popsize / 2.0)), NSGA2.py:64: Python rounds halves to even
@@ -45,7 +47,7 @@ int dmo_nsga2_step(dmo_ctx* ctx, dmo_gp* gp, double* pop_x, double* pop_y, int32
   // parents under the children (np.vstack((x_gen, population_parm)), NSGA2.py:205-206)
   DMO_CUDA(cudaMemcpyAsync(Xs.p + (size_t)P * d, pop_x, (size_t)pop * d * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   DMO_CUDA(cudaMemcpyAsync(Ys.p + (size_t)P * M, pop_y, (size_t)pop * M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  rc = dmo_remove_worst(ctx, Xs.p, Ys.p, P + pop, d, M, DMO_METRIC_NONE, nullptr, 0, pop, pop_x, pop_y, rank, perm.p);
+  rc = dmo_remove_worst(ctx, Xs.p, Ys.p, P + pop, d, M, distance_metric, nullptr, 0, pop, pop_x, pop_y, rank, perm.p);
   if (rc != DMO_OK) return rc;
   if (round_to_f32) {
     rc = dmo_round_f32(ctx, pop_y, pop * M);

@@ -259,6 +259,24 @@ int dmo_tournament(dmo_ctx* ctx, const int32_t* rank, const double* crowd, int64
   return DMO_OK;
 }
 
+// Iterations of the reference's variation loop (NSGA2.py:142-178) that are planned in parallel.  An iteration yields
+// two children with probability pc and one more with probability pm, so the loop needs about popsize / (2 pc + pm)
+// of them: the default rates (0.9 / 0.1) fit well inside 2 popsize + 64 (kept as the minimum, so recorded draw
+// layouts do not move), a mutation-only or low-rate configuration gets the mean plus 12 standard deviations.
+int64_t dmo_nsga2_plan_length(int64_t popsize, double crossover_prob, double mutation_prob) {
+  const double pc = crossover_prob > 0.0 ? (crossover_prob < 1.0 ? crossover_prob : 1.0) : 0.0;
+  const double pm = mutation_prob > 0.0 ? (mutation_prob < 1.0 ? mutation_prob : 1.0) : 0.0;
+  const double e = 2.0 * pc + pm;
+  const int64_t base = 2 * popsize + 64;
+  if (!(e > 0.0)) return base;
+  const double var = 4.0 * pc * (1.0 - pc) + pm * (1.0 - pm);  // variance of the children of one iteration
+  const double n = (double)(popsize + 1);
+  const double need = n / e + 12.0 * sqrt(var * n / e) / e + 64.0;
+  if (need > 2.0e9) return -1;
+  const int64_t t = (int64_t)ceil(need);
+  return t > base ? t : base;
+}
+
 int dmo_nsga2_generate(dmo_ctx* ctx, const double* pop_x, int64_t npop, int d, const int64_t* pool_idx, int64_t poolsize,
                        int64_t popsize, double crossover_prob, double mutation_prob, double mutation_rate,
                        const double* di_crossover, const double* di_mutation, const double* xlb, const double* xub,
@@ -271,7 +289,8 @@ int dmo_nsga2_generate(dmo_ctx* ctx, const double* pop_x, int64_t npop, int d, c
               "nsga2_generate: bad arguments");
   DMO_REQUIRE(poolsize >= 2 || crossover_prob <= 0.0, "nsga2_generate: crossover needs a pool of at least 2");
   DMO_REQUIRE(crossover_prob > 0.0 || mutation_prob > 0.0, "nsga2_generate: both probabilities are zero");
-  const int64_t T = 2 * popsize + 64;  // iterations planned; E[children / iteration] = 2 pc + pm
+  const int64_t T = dmo_nsga2_plan_length(popsize, crossover_prob, mutation_prob);
+  DMO_REQUIRE(T > 0, "nsga2_generate: crossover_prob / mutation_prob too small for popsize %lld", (long long)popsize);
   const int64_t cap = popsize + 1;
   In<double> ipx, idc, idm, ilb, iub;
   In<int64_t> ipool;

@@ -63,7 +63,7 @@ class _GPRBase:
         nan="remove",
         top_k=None,
         logger=None,
-        precision="fp64",
+        precision="auto",
         **kwargs,
     ):
         from sklearn.gaussian_process import GaussianProcessRegressor
@@ -76,7 +76,13 @@ class _GPRBase:
         self.xrg = self.xub - self.xlb
         self.logger = logger
         self.return_mean_variance = return_mean_variance
-        self.precision = _lib.GP_TENSOR if precision in ("tensor", _lib.GP_TENSOR) else _lib.GP_FP64
+        # "auto" (default): the tcgen05 path wherever a per-model calibration against the float64 path holds the
+        # 1e-5 bar, float64 for the rest (csrc/gp.cu, DMO_GP_AUTO); "tensor" / "fp64" force one arithmetic
+        codes = {"auto": _lib.GP_AUTO, "tensor": _lib.GP_TENSOR, "fp64": _lib.GP_FP64,
+                 _lib.GP_AUTO: _lib.GP_AUTO, _lib.GP_TENSOR: _lib.GP_TENSOR, _lib.GP_FP64: _lib.GP_FP64}
+        if precision not in codes:
+            raise ValueError(f"{self._name}: precision must be 'auto', 'tensor' or 'fp64' (got {precision!r})")
+        self.precision = codes[precision]
         self.stats = {}
 
         xin = np.asarray(xin, dtype=np.float64)

@@ -52,7 +52,7 @@ int main(void) {
     int64_t n_children = 0;
     double hv = 0.0;
     CHECK(dmo_nsga2_step(ctx, gp, (double*)d_x, (double*)d_y, (int32_t*)d_r, POP, D, M, 0.9, 0.1, 1.0 / D, di_c, di_m, xlb, xub,
-                         /*seed*/ 42u, /*stream*/ 2u * gen + 1u, DMO_GP_FP64, /*variance*/ 1, /*float32 state*/ 1, ref,
+                         /*seed*/ 42u, /*stream*/ 2u * gen + 1u, DMO_GP_AUTO, DMO_METRIC_CROWDING, /*variance*/ 1, /*float32 state*/ 1, ref,
                          &n_children, &hv));
     printf("generation %d: %lld children, hypervolume %.6f\n", gen, (long long)n_children, hv);
   }

@@ -52,6 +52,9 @@ extern "C" {
 /* arithmetic used for the GP posterior variance contraction */
 #define DMO_GP_FP64 0   /* CUDA-core float64 everywhere: matches sklearn to ~1e-10               */
 #define DMO_GP_TENSOR 1 /* tcgen05 split-fp16 (3 MMAs / product), fp32 accumulate in TMEM        */
+#define DMO_GP_AUTO 2   /* tensor path where a per-model calibration against the float64 path   *
+                         * holds 1e-5, float64 for the rest (rows with small variance, badly   *
+                         * conditioned models): see dmo_gp_auto_info                            */
 
 typedef struct dmo_ctx dmo_ctx;
 typedef struct dmo_gp dmo_gp;
@@ -149,7 +152,13 @@ int dmo_sbx_u(dmo_ctx* ctx, const double* parent1, const double* parent2, const 
  * x_gen has room for popsize+1 rows; child_kind (popsize+1,) gets 0/1 = SBX child 1/2,
  * 2 = mutant; n_children the number of rows produced.
  * draws (optional, may be NULL): receives the random draws actually used so the CPU
- * oracle can replay them: layout documented in dmosopt_b200/_lib.py (nsga2_generate). */
+ * oracle can replay them: T * (5 + 2 d) doubles, T = dmo_nsga2_plan_length(...) planned
+ * iterations, layout documented in dmosopt_b200/_lib.py (nsga2_generate).
+ * dmo_nsga2_plan_length: the number of loop iterations planned for the given rates
+ * (>= 2 popsize + 64; grows as 1 / (2 crossover_prob + mutation_prob) so that mutation-only
+ * and low-rate configurations terminate like the reference's while-loop); -1 if the rates
+ * are too small to plan. */
+int64_t dmo_nsga2_plan_length(int64_t popsize, double crossover_prob, double mutation_prob);
 int dmo_nsga2_generate(dmo_ctx* ctx, const double* pop_x, int64_t npop, int d,
                        const int64_t* pool_idx, int64_t poolsize, int64_t popsize,
                        double crossover_prob, double mutation_prob, double mutation_rate,
@@ -163,13 +172,15 @@ int dmo_nsga2_generate(dmo_ctx* ctx, const double* pop_x, int64_t npop, int d,
  * vstack(children, parents) -> rank + stable truncation -> float32 rounding of the stored objectives
  * (NSGA2.py:228-230) -> optional hypervolume of the survivors (hv_ref / hv_out host pointers, may be NULL).
  * pop_x (pop,d), pop_y (pop,M), rank (pop,) are DEVICE buffers, updated in place; Philox streams
- * stream_id (tournament) and stream_id + 1 (variation) are consumed; n_children (host) receives P. */
+ * stream_id (tournament) and stream_id + 1 (variation) are consumed; n_children (host) receives P.
+ * distance_metric: DMO_METRIC_* used to break rank ties in the truncation (NSGA2's own default is
+ * "crowding", NSGA2.py:25; MOASMO.epoch constructs it with distance_metric=None, MOASMO.py:370). */
 int dmo_nsga2_step(dmo_ctx* ctx, dmo_gp* gp, double* pop_x, double* pop_y, int32_t* rank, int64_t pop,
                    int d, int M, double crossover_prob, double mutation_prob, double mutation_rate,
                    const double* di_crossover, const double* di_mutation, const double* xlb,
                    const double* xub, uint64_t seed, uint64_t stream_id, int precision,
-                   int with_variance, int round_to_f32, const double* hv_ref, int64_t* n_children,
-                   double* hv_out);
+                   int distance_metric, int with_variance, int round_to_f32, const double* hv_ref,
+                   int64_t* n_children, double* hv_out);
 
 /* ---- A18: exact-GP posterior (GPR_Matern / GPR_RBF predict) -------------------
  * replaces GPR_Matern.predict / .evaluate (dmosopt/model.py:1254-1275; GPR_RBF :1343-1364),
@@ -194,6 +205,14 @@ int dmo_gp_destroy(dmo_ctx* ctx, dmo_gp* gp);
 int dmo_gp_set_linear_mean(dmo_ctx* ctx, dmo_gp* gp, const double* weight, const double* bias);
 int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double* mean,
                    double* var, int precision);
+/* What DMO_GP_AUTO decided for this model (runs the one-off calibration if it has not run yet):
+ * both arithmetic paths predict 512 probe candidates; mean_tensor / var_tensor = 1 when the fp32-K_*
+ * mean (error relative to max(|mean|, y_std)) / the tcgen05 variance (error relative to the prior
+ * variance) stay within the margins documented in csrc/gp.cu; theta: rows whose tensor variance is
+ * below theta * prior are recomputed in float64; last_refined: rows the last AUTO predict recomputed
+ * (= P when the whole call ran in float64).  Any output pointer may be NULL. */
+int dmo_gp_auto_info(dmo_ctx* ctx, dmo_gp* gp, int* mean_tensor, int* var_tensor, double* mean_err,
+                     double* var_err, double* theta, int64_t* last_refined);
 
 /* ---- A16: exact hypervolume ---------------------------------------------------
  * replaces hv.AdaptiveHyperVolume.compute_hypervolume(..., 'box') (dmosopt/hv.py:123-189)
@@ -217,6 +236,11 @@ int dmo_ehvi_select(dmo_ctx* ctx, const double* F, int64_t nf, const double* mea
  * replaces MOEA.get_duplicates (dmosopt/MOEA.py:426-437) at its default eps = 1e-16:
  * is_dup[i] = 1 iff an earlier row j < i has ||x_i - x_j||_2 <= eps. */
 int dmo_get_duplicates(dmo_ctx* ctx, const double* X, int64_t n, int d, double eps, uint8_t* is_dup);
+/* the two-set form MOASMO's resample step uses (dmosopt/MOASMO.py:442, MOEA.get_duplicates(best_x, x_0)):
+ * is_dup[i] = 1 when some row j < i of Y (ny, d) lies within eps of row i of X (n, d) -- the reference masks
+ * the upper triangle of cdist(X, Y) including the diagonal (MOEA.py:430). */
+int dmo_get_duplicates_pair(dmo_ctx* ctx, const double* X, int64_t n, const double* Y, int64_t ny, int d,
+                            double eps, uint8_t* is_dup);
 
 /* ---- A11: AGE-MOEA survival score (greedy part) -------------------------------------
  * replaces the O(m^2) greedy loop of AGEMOEA.survival_score (dmosopt/AGEMOEA.py:398-428):

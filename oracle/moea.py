@@ -127,13 +127,18 @@ def tournament_selection_gumbel(u, poolsize, *metrics, p=0.5):
     return order[top]
 
 
-def get_duplicates(X, eps=1e-16):
-    """MOEA.py:426-437: row i is a duplicate if some earlier row j<i has ||x_i-x_j|| <= eps."""
+def get_duplicates(X, eps=1e-16, Y=None):
+    """MOEA.py:426-437: row i of X is a duplicate if some row j<i of Y (default: X itself) has ||x_i-y_j|| <= eps
+    (``np.triu_indices(len(X), m=len(Y))`` masks j >= i, diagonal included, also in the two-set form)."""
     X = np.asarray(X, dtype=np.float64)
+    Y = X if Y is None else np.asarray(Y, dtype=np.float64)
     n = X.shape[0]
     dup = np.zeros(n, dtype=bool)
     for i in range(1, n):
-        dd = np.sqrt(((X[:i] - X[i]) ** 2).sum(axis=1))
+        hi = min(i, Y.shape[0])
+        if hi == 0:
+            continue
+        dd = np.sqrt(((Y[:hi] - X[i]) ** 2).sum(axis=1))
         dd[np.isnan(dd)] = np.inf
         dup[i] = np.any(dd <= eps)
     return dup

@@ -137,8 +137,8 @@ def ehvi_select(F, means, variances, ref, k, nds=True, return_scores=False):
     return (sel.astype(np.int64), score) if return_scores else sel.astype(np.int64)
 
 
-def get_duplicates(X, eps=1e-16):
-    return moea.get_duplicates(X, eps)
+def get_duplicates(X, eps=1e-16, Y=None):
+    return moea.get_duplicates(X, eps, Y=Y)
 
 
 def age_survival(yn, nn, p, extreme):

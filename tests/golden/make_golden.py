@@ -261,6 +261,14 @@ def gen_duplicates(rng):
     X[51] = X[30]
     out["X"] = X
     out["dup"] = MOEA.get_duplicates(X)
+    # the two-set form of MOASMO's resample step (MOASMO.py:442): rows of X against EARLIER rows of Y
+    Y = rng.random((60, 6))
+    Y[3] = X[10]   # j = 3 < i = 10: duplicate
+    Y[40] = X[12]  # j = 40 > i = 12: masked by the upper triangle, not a duplicate
+    Y[5] = X[5]    # j == i: the diagonal is masked too
+    Y[0] = X[79]
+    out["Y"] = Y
+    out["dup_xy"] = MOEA.get_duplicates(X, Y)
     save("duplicates", **out)
 
 
