@@ -73,6 +73,7 @@ _SIGNATURES = {
     "dmo_nsga2_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _vp, _vp, _vp, _vp, _c_u64, _c_u64,
                                 _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "dmo_hypervolume": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp, ctypes.POINTER(_c_dbl)]),
+    "dmo_hypervolume_ranked": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, ctypes.POINTER(_c_dbl)]),
     "dmo_ehvi_select": (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp, _c_int, _c_i64, _vp, _vp]),
     "dmo_get_duplicates": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_dbl, _vp]),
     "dmo_get_duplicates_pair": (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _c_int, _c_dbl, _vp]),
@@ -165,6 +166,12 @@ def _f64(a):
 # --------------------------------------------------------------------------- context utilities
 def synchronize():
     _check(load_library().dmo_synchronize(context()), "dmo_synchronize")
+
+
+def stream_ptr():
+    """The CUDA stream (cudaStream_t as an integer) every library call is issued on: wrap it with
+    ``torch.cuda.ExternalStream`` to order torch / NCCL work with the library without device-wide synchronisation."""
+    return int(load_library().dmo_stream(context()))
 
 
 def launch_count():
@@ -674,14 +681,21 @@ class GPHandle:
 
 
 # --------------------------------------------------------------------------- A16/A17
-def hypervolume(F, ref):
+def hypervolume(F, ref, rank=None):
+    """Exact hypervolume; ``rank`` (optional): non-dominated ranks of the rows within the superset they were selected from
+    by rank (skips the non-dominated filter, see dmo_hypervolume_ranked)."""
     F = _f64(F)
     if F.ndim == 1:
         F = F.reshape(1, -1)
     n, M = F.shape
     ref = _f64(ref)
     out = _c_dbl(0.0)
-    _check(load_library().dmo_hypervolume(context(), _ptr(F), n, M, _ptr(ref), ctypes.byref(out)), "dmo_hypervolume")
+    if rank is None:
+        _check(load_library().dmo_hypervolume(context(), _ptr(F), n, M, _ptr(ref), ctypes.byref(out)), "dmo_hypervolume")
+    else:
+        rk = np.ascontiguousarray(rank, dtype=np.int32)
+        assert rk.shape == (n,)
+        _check(load_library().dmo_hypervolume_ranked(context(), _ptr(F), n, M, _ptr(ref), _ptr(rk), ctypes.byref(out)), "dmo_hypervolume_ranked")
     return float(out.value)
 
 

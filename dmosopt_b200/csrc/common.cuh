@@ -259,3 +259,6 @@ int euclidean_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, double* d
 int lexsort_device(dmo_ctx* ctx, const int32_t* d_rank, const double* const* d_desc_keys, int nkeys,
                    int64_t n, uint32_t* d_perm);
 int hypervolume_device(dmo_ctx* ctx, const double* dF, int64_t n, int M, const double* h_ref, double* h_out);
+// the same when the rows carry their non-dominated ranks within a superset (rank > 0 rows are skipped, no filter pass)
+int hypervolume_device_ranked(dmo_ctx* ctx, const double* dF, int64_t n, int M, const double* h_ref, const int32_t* d_rank,
+                              double* h_out);

@@ -341,6 +341,7 @@ struct GemmParams3 {
   int* abort_flag;
   const unsigned* ready;  // [n_pb] completion counters of the K_* producer (nullptr: K_* is complete at launch)
   unsigned ready_target;
+  int dbg;  // DMO_GP_DBG bits (diagnostics): 1 = no proxy fence, 2 = no nanosleep in the wait loop
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         if (prm.ready) {  // the K_* rows of this candidate block must have been written (by another kernel, generic proxy)
           uint32_t spins = 0;
           while (ld_acquire_u32(prm.ready + pb) < prm.ready_target) {
-            __nanosleep(256);
+            if (!(prm.dbg & 2)) __nanosleep(256);
             if ((++spins & 0xFFu) == 0u) {
               if (*abort_flag) break;
               if (spins > (1u << 23)) {  // ~2 s: the producer is not running
@@ -403,12 +404,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
               }
             }
           }
-          asm volatile("fence.proxy.async;" ::: "memory");  // order the TMA (async proxy) reads after the acquire
+          if (!(prm.dbg & 1)) asm volatile("fence.proxy.async;" ::: "memory");  // order the TMA (async proxy) reads after the acquire
         }
         const int a_row = (int)(m * prm.k_rows + (int64_t)pb * TM2);
         const int jhi = prm.n_jt - 1 - q;
-        for (int s = 0; s < 2; ++s) {
-          const int jt = s ? q : jhi;
+        for (int s = 0; s < 2; ++s) {  // short row block first: its K_* tiles are read again right away by the long one
+          const int jt = s ? jhi : q;
           if (s && q == jhi) break;
           const int b_row = (int)(m * prm.l_rows + (int64_t)jt * TN2);
           const int nkc = (jt + 1) * (TN2 / TK2);
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const int q = r % prm.n_q;
         const int jhi = prm.n_jt - 1 - q;
         for (int s = 0; s < 2; ++s) {
-          const int jt = s ? q : jhi;
+          const int jt = s ? jhi : q;
           if (s && q == jhi) break;
           mbar_wait(acc_empty, acc_phase ^ 1u, abort_flag);
           tc_fence_after();
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const int jhi = prm.n_jt - 1 - q;
       double total0 = 0.0, total1 = 0.0;
       for (int s = 0; s < 2; ++s) {
-        const int jt = s ? q : jhi;
+        const int jt = s ? jhi : q;
         if (s && q == jhi) break;
         mbar_wait(acc_full, acc_phase, abort_flag);
         tc_fence_after();
@@ -807,6 +808,8 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   int version = 3;
   if (const char* e = getenv("DMO_GP_TC")) version = atoi(e) == 2 ? 2 : 3;
   const bool overlap = version == 3 && !(getenv("DMO_GP_NO_OVERLAP") && atoi(getenv("DMO_GP_NO_OVERLAP")));
+  const int dbg = getenv("DMO_GP_DBG") ? atoi(getenv("DMO_GP_DBG")) : 0;  // 4: event instead of flags, 8: mean after var
+  const bool use_flags = overlap && !(dbg & 4);
   constexpr int64_t TMv = v2::TM2;
   // candidate chunk: K_* hi/lo (2 x M x Pc x Npad fp16) within ~6 GiB
   int64_t Pc_max = ((int64_t)6 << 30) / ((int64_t)M * Npad * 4);
@@ -859,7 +862,7 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
 #define KSTAR_LAUNCH(ISO_, DM_)                                                                                   \
   DMO_LAUNCH_ON(ps, (kstar_tensor_kernel<ISO_, DM_>), gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M,    \
                 gp->kernel, gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p,                    \
-                (overlap && d_var) ? rdy : nullptr)
+                (use_flags && d_var) ? rdy : nullptr)
       if (gp->isotropic) {
         if (d <= 32)
           KSTAR_LAUNCH(true, 32);
@@ -873,7 +876,11 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       }
 #undef KSTAR_LAUNCH
     }
-    {
+    if (overlap && (dbg & 4)) {  // diagnostics: the contraction waits for the whole K_* kernel by event, the mean still overlaps
+      DMO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->aux));
+      DMO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0));
+    }
+    if (!(dbg & 8)) {
       ProfileScope ps_(ctx, "gp_mean", ps);
       DMO_LAUNCH_ON(ps, mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane,
                     M, gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
@@ -891,7 +898,8 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       prm.vnorm = vnorm.p;
       prm.vn_ld = Pc_alloc;
       prm.abort_flag = abort_flag.p;
-      prm.ready = overlap ? rdy : nullptr;
+      prm.ready = use_flags ? rdy : nullptr;
+      prm.dbg = dbg;
       prm.ready_target = 8u * gk.x;  // KT_TP = 32 candidates per producer block: 8 tile rows x gk.x column blocks per 256
       const int n_work = prm.M * prm.n_pb * prm.n_q;
       const int grid = n_work < ctx->sm_count ? n_work : ctx->sm_count;
@@ -936,6 +944,11 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
                  gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
     }
     if (overlap) DMO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // mean (and K_*) of this chunk done
+    if (dbg & 8) {
+      ProfileScope ps_(ctx, "gp_mean");
+      DMO_LAUNCH(mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane, M,
+                 gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
+    }
   }
   DMO_CHECK_LAUNCH();
   int h_abort = 0;

@@ -14,21 +14,28 @@
 //          streamed through shared memory in coalesced tiles, no dynamic data structures.
 //   M >= 4: the same slicing identity applied recursively (see hv_slice_kernel), O(n^(M-1)).
 // All arithmetic is float64; block partial sums are combined in a fixed order (deterministic result).
+#include <stdlib.h>
+
 #include "common.cuh"
+
+// hv3_tree.cu: O(n log^2 n) evaluation of the M = 3 slicing identity for large fronts
+int hv3_tree_device(dmo_ctx* ctx, const double* xs, const double* ys, const double* zs, const uint32_t* zo, int64_t n, double rx,
+                    double ry, double rz, double* partial, int64_t* n_partial);
 
 namespace {
 
 constexpr int HV_T = 128;
 
+// keep: optional (n,) array, rows with keep[i] != 0 are dropped up front (the caller knows they are dominated)
 __global__ void inside_flag_kernel(const double* __restrict__ F, int64_t n, int M, const double* __restrict__ ref,
-                                   int32_t* __restrict__ flag) {
+                                   const int32_t* __restrict__ drop, int32_t* __restrict__ flag) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   if (i == n) {
     flag[i] = 0;
     return;
   }
-  bool in = true;
+  bool in = drop == nullptr || drop[i] == 0;
   for (int j = 0; j < M; ++j) in = in && (ref[j] > F[i * M + j]);  // hv.py:159
   flag[i] = in ? 1 : 0;
 }
@@ -499,7 +506,19 @@ int sum_partials(dmo_ctx* ctx, DevBuf<double>& partial, int64_t nb, double* h_ou
 
 }  // namespace
 
+// d_rank (optional, device, (n,)): non-dominated ranks of the rows within a SUPERSET they were selected from by rank
+// (dmo_remove_worst).  Rows with rank > 0 are dominated by a rank-0 row of the same set, so they add no volume and are
+// dropped without running the non-dominated filter again; this stays true after a monotone rounding of the
+// coordinates (float64 -> float32 state), which can only turn strict dominance into weak dominance.
+int hypervolume_device_ranked(dmo_ctx* ctx, const double* dF, int64_t n, int M, const double* h_ref, const int32_t* d_rank,
+                              double* h_out);
+
 int hypervolume_device(dmo_ctx* ctx, const double* dF, int64_t n, int M, const double* h_ref, double* h_out) {
+  return hypervolume_device_ranked(ctx, dF, n, M, h_ref, nullptr, h_out);
+}
+
+int hypervolume_device_ranked(dmo_ctx* ctx, const double* dF, int64_t n, int M, const double* h_ref, const int32_t* d_rank,
+                              double* h_out) {
   *h_out = 0.0;
   if (n <= 0) return DMO_OK;
   DMO_REQUIRE(M >= 1 && M <= 5, "hypervolume: M=%d not supported (1..5; >= 10 objectives use Monte-Carlo in the reference)", M);
@@ -511,7 +530,7 @@ int hypervolume_device(dmo_ctx* ctx, const double* dF, int64_t n, int M, const d
   DevBuf<double> Fin;
   int64_t n1 = 0;
   DMO_TRY(flag.alloc(ctx, n + 1));
-  DMO_LAUNCH(inside_flag_kernel, (unsigned)ceil_div(n + 1, 256), 256, 0, dF, n, M, dref.p, flag.p);
+  DMO_LAUNCH(inside_flag_kernel, (unsigned)ceil_div(n + 1, 256), 256, 0, dF, n, M, dref.p, d_rank, flag.p);
   DMO_TRY(compact_rows(ctx, dF, n, M, flag, Fin, &n1));
   if (n1 == 0) return DMO_OK;
   if (M == 1) {
@@ -526,10 +545,15 @@ int hypervolume_device(dmo_ctx* ctx, const double* dF, int64_t n, int M, const d
     return DMO_OK;
   }
   // 2. non-dominated subset
-  DevBuf<double> Fnd;
+  DevBuf<double> Fnd_own;
   int64_t n2 = 0;
-  DMO_TRY(nondominated_subset(ctx, Fin.p, n1, M, Fnd, &n2));
-  if (n2 == 0) return DMO_OK;
+  if (d_rank) {
+    n2 = n1;  // already reduced to the rank-0 rows
+  } else {
+    DMO_TRY(nondominated_subset(ctx, Fin.p, n1, M, Fnd_own, &n2));
+    if (n2 == 0) return DMO_OK;
+  }
+  DevBuf<double>& Fnd = d_rank ? Fin : Fnd_own;
   DevBuf<uint32_t> sx;
   DMO_TRY(sort_by_column(ctx, Fnd.p, n2, M, 0, sx));
   if (M == 2) {
@@ -612,11 +636,22 @@ int hypervolume_device(dmo_ctx* ctx, const double* dF, int64_t n, int M, const d
   DMO_LAUNCH(gather_col_kernel, g, 256, 0, Fnd.p, sx.p, n2, M, 0, xs.p);
   DMO_LAUNCH(gather_col_kernel, g, 256, 0, Fnd.p, sx.p, n2, M, 1, ys.p);
   DMO_LAUNCH(gather_col_kernel, g, 256, 0, Fnd.p, sx.p, n2, M, 2, zs.p);
-  const int64_t nb = ceil_div(n2, HV_T);
+  int64_t nb = ceil_div(n2, HV_T);
   DevBuf<double> partial;
   DMO_TRY(partial.alloc(ctx, nb));
-  ProfileScope ps(ctx, "hv3");
-  DMO_LAUNCH(hv3_kernel, (unsigned)nb, HV_T, 0, xs.p, ys.p, zs.p, zo.p, n2, h_ref[0], h_ref[1], h_ref[2], partial.p);
+  // small fronts: one O(n) sweep per point (n^2 / 2 cheap tests, no set-up); large fronts: the merge-sort-tree walks of
+  // hv3_tree.cu (O(n log^2 n)).  DMO_HV3_TREE = 0 / 1 forces one or the other, any larger value moves the threshold.
+  int64_t tree_min = 4096;
+  if (const char* e = getenv("DMO_HV3_TREE")) {
+    const long v = atol(e);
+    tree_min = v == 0 ? INT64_MAX : (v == 1 ? 0 : v);
+  }
+  if (n2 >= tree_min) {
+    DMO_TRY(hv3_tree_device(ctx, xs.p, ys.p, zs.p, zo.p, n2, h_ref[0], h_ref[1], h_ref[2], partial.p, &nb));
+  } else {
+    ProfileScope ps(ctx, "hv3");
+    DMO_LAUNCH(hv3_kernel, (unsigned)nb, HV_T, 0, xs.p, ys.p, zs.p, zo.p, n2, h_ref[0], h_ref[1], h_ref[2], partial.p);
+  }
   DMO_TRY(sum_partials(ctx, partial, nb, h_out));
   return DMO_OK;
 }
@@ -635,6 +670,24 @@ int dmo_hypervolume(dmo_ctx* ctx, const double* F, int64_t n, int M, const doubl
   In<double> f;
   DMO_TRY(f.init(ctx, F, (size_t)n * M));
   DMO_TRY(hypervolume_device(ctx, f.d, n, M, h_ref, out));
+  return DMO_OK;
+}
+
+int dmo_hypervolume_ranked(dmo_ctx* ctx, const double* F, int64_t n, int M, const double* ref, const int32_t* rank,
+                           double* out) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(out && ref && n >= 0 && M >= 1 && M <= 16, "hypervolume_ranked: bad arguments");
+  *out = 0.0;
+  if (n == 0) return DMO_OK;
+  DMO_REQUIRE(F && rank, "hypervolume_ranked: null points / ranks");
+  double h_ref[16];
+  DMO_CUDA(cudaMemcpy(h_ref, ref, M * sizeof(double), cudaMemcpyDefault));
+  In<double> f;
+  In<int32_t> r;
+  DMO_TRY(f.init(ctx, F, (size_t)n * M));
+  DMO_TRY(r.init(ctx, rank, (size_t)n));
+  DMO_TRY(hypervolume_device_ranked(ctx, f.d, n, M, h_ref, r.d, out));
   return DMO_OK;
 }
 

@@ -54,7 +54,11 @@ int dmo_nsga2_step(dmo_ctx* ctx, dmo_gp* gp, double* pop_x, double* pop_y, int32
     if (rc != DMO_OK) return rc;
   }
   if (hv_ref && hv_out) {
-    rc = dmo_hypervolume(ctx, pop_y, pop, M, hv_ref, hv_out);
+    // the survivors carry their ranks within the merged set: rows of rank > 0 cannot add volume (hv.cu)
+    DMO_REQUIRE(M <= 16, "nsga2_step: too many objectives for the hypervolume");
+    double h_ref[16];
+    DMO_CUDA(cudaMemcpy(h_ref, hv_ref, M * sizeof(double), cudaMemcpyDefault));
+    rc = hypervolume_device_ranked(ctx, pop_y, pop, M, h_ref, rank, hv_out);
     if (rc != DMO_OK) return rc;
   }
   return DMO_OK;

@@ -221,6 +221,11 @@ int dmo_gp_auto_info(dmo_ctx* ctx, dmo_gp* gp, int* mean_tensor, int* var_tensor
  * strictly inside ref are ignored (hv.py:159).  True hypervolume (see DESIGN.md for the
  * reference's <=0-coordinate defect).  1 <= M <= 5 (M >= 4 is O(n^(M-1))). */
 int dmo_hypervolume(dmo_ctx* ctx, const double* F, int64_t n, int M, const double* ref, double* out);
+/* The same for a set that carries its non-dominated ranks within the superset it was selected from by rank
+ * (the survivors of dmo_remove_worst / MOEA.remove_worst, dmosopt/MOEA.py:398-423): rows with rank > 0 are dominated
+ * by a rank-0 row of the same set and add no volume, so the non-dominated filter pass is skipped.  rank (n,) int32. */
+int dmo_hypervolume_ranked(dmo_ctx* ctx, const double* F, int64_t n, int M, const double* ref,
+                           const int32_t* rank, double* out);
 
 /* ---- A17: HV-improvement (EHVI) candidate selection -----------------------------
  * replaces indicators.HypervolumeImprovement._do (dmosopt/indicators.py:295-313) ->

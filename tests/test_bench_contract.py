@@ -34,9 +34,17 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["unit"] == "candidates/s" and d["value"] > 0
     assert d["config"]["workload"].startswith("NSGA2 surrogate generation")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    has_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "dmosopt"))
+    assert cb["kind"] == ("reference" if has_ref else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_falls_back_to_the_port_without_the_reference_package(tmp_path):
+    r = _run({"DMOSOPT_REF": str(tmp_path)})  # an empty directory: no dmosopt package there, and baseline/_ref is not consulted
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["kind"] == "port"
 
 
 def test_reference_arm_other_ranks_stay_silent():

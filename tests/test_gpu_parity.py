@@ -515,7 +515,7 @@ def test_fused_resident_step_equals_the_separate_calls(L, metric):
     assert np.array_equal(fx.download(), Xo)
     assert np.array_equal(fy.download(), Yo)
     assert np.array_equal(fr.download(), rk.astype(np.int32))
-    assert hv_f.value == L.hypervolume(Yo, ref)
+    assert abs(hv_f.value - L.hypervolume(Yo, ref)) <= 1e-12 * abs(hv_f.value)  # same set up to dominated rows: summation order only
 
 
 def test_device_mirror_semantics(L):
@@ -684,6 +684,47 @@ def test_hv_large_sets_grid_filter(L, n, M, kind):
         assert len(sub) < 3000
         exp = hv.hypervolume(sub, ref)
         assert abs(v - exp) <= 1e-10 * exp
+
+
+@pytest.mark.parametrize("n,kind", [(3, "sphere"), (130, "sphere"), (1024, "sphere"), (1025, "cloud"), (2500, "sphere"), (5000, "dups"), (40000, "sphere"),
+                                    (65536, "sphere"), (70001, "ties")])
+def test_hv3_tree_equals_the_sweep_kernel_and_the_oracle(L, n, kind):
+    """M = 3: the merge-sort-tree walks (hv3_tree.cu, O(n log^2 n), the path for fronts of 4096 points and more) against
+    the O(n^2) sweep kernel on the same inputs -- forced either way with DMO_HV3_TREE -- and against the CPU oracle where
+    it finishes in seconds.  Sizes straddle the 1024-position shared-memory levels and the merge-path levels above."""
+    import os
+
+    rng = np.random.default_rng(n)
+    x = np.abs(rng.standard_normal((n, 3)))
+    F = x / np.linalg.norm(x, axis=1, keepdims=True) * (1.0 + 0.01 * rng.random((n, 1)))  # SURVEY 8d (iii): sphere x (1 + 0.01 u)
+    if kind == "cloud":
+        F = rng.random((n, 3))
+    elif kind == "dups":
+        F[: n // 5] = F[n // 2 : n // 2 + n // 5]
+        F[n // 5 : n // 4] = F[n // 2 : n // 2 + n // 4 - n // 5] + np.array([0.0, 0.01, 0.0])  # weakly dominated rows
+    elif kind == "ties":
+        F = np.round(F, 2)
+    ref = F.max(axis=0) + 0.1
+    vals = {}
+    for mode in ("0", "1"):
+        os.environ["DMO_HV3_TREE"] = mode
+        try:
+            vals[mode] = L.hypervolume(F, ref)
+        finally:
+            del os.environ["DMO_HV3_TREE"]
+    assert abs(vals["1"] - vals["0"]) <= 1e-12 * vals["0"], (vals, n, kind)
+    if n <= 5000:
+        exp = hv.hypervolume(F, ref)
+        assert abs(vals["1"] - exp) <= 1e-11 * exp
+    # the ranked entry point feeds dominated rows straight into the kernel: same value
+    if kind in ("cloud", "dups"):
+        rk = L.rank_nd(F)
+        os.environ["DMO_HV3_TREE"] = "1"
+        try:
+            v_rk = L.hypervolume(F, ref, rank=rk)
+        finally:
+            del os.environ["DMO_HV3_TREE"]
+        assert abs(v_rk - vals["0"]) <= 1e-12 * vals["0"]
 
 
 # ------------------------------------------------------------------------------------------ A17 EHVI

@@ -90,6 +90,7 @@ def test_reference_and_plugin_nsga2_agree_on_a_generation():
     sys.path.insert(0, ref)
     try:
         from dmosopt import NSGA2 as rNSGA2
+        from dmosopt import model as rmodel
     finally:
         sys.path.remove(ref)
     import dmosopt_b200 as b2
@@ -103,7 +104,7 @@ def test_reference_and_plugin_nsga2_agree_on_a_generation():
         return np.column_stack((x[:, 0] + x[:, 3:].sum(1) * 0.1, (1 - x[:, 0]) * (1 + x[:, 1]), x[:, 2] ** 2 + 0.5 * x[:, 1]))
 
     y0 = f(x0).astype(np.float32)
-    ro = rNSGA2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=None, distance_metric=None)
+    ro = rNSGA2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=rmodel.Model(), distance_metric=None)
     ro.initialize_strategy(x0.astype(np.float32), y0.copy(), bounds, np.random.default_rng(1))
     bo = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=None, distance_metric=None)
     bo.initialize_strategy(x0.astype(np.float32), y0.copy(), bounds, np.random.default_rng(1))
