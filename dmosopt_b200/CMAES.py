@@ -84,9 +84,12 @@ class CMAES(MOEA):
         dim, n = self.nInput, self.opt_params.popsize
         p = self.opt_params
         sigmas = np.asarray([p.sigma * (1.0 / (p.di_mutation + 1.0))] * n)
-        A = np.stack([np.identity(dim) for _ in range(n)])
-        Ainv = np.stack([np.identity(dim) for _ in range(n)])
-        pc = np.zeros((n, dim))
+        # the per-parent Cholesky factors, their inverses and the evolution paths live in HBM (_lib.ResidentRows): at pop
+        # 131 072, d = 24 they are 1.2 GB that the reference re-indexes on the host every generation; NumPy still sees
+        # them as arrays (np.asarray(state.A), state.A[i]) through a device -> host copy on demand
+        A = _lib.identity_rows(n, dim)
+        Ainv = _lib.identity_rows(n, dim)
+        pc = _lib.resident_rows(np.zeros((n, dim)))
         psucc = np.asarray([p.ptarg] * n)
         order, rank = sortMO(x, y, self.x_distance_metrics)
         idx = order[:n]
@@ -176,7 +179,8 @@ class CMAES(MOEA):
         off_psucc = (1.0 - cp) * st.psucc[par] + cp
         last_steps = st.sigmas[par].copy()
         off_sigmas = last_steps * fac(off_psucc)[:, None]
-        off_A, off_Ainv, off_pc = st.A[par], st.Ainv[par], st.pc[par]
+        A_d, Ainv_d, pc_d = _lib.resident_rows(st.A), _lib.resident_rows(st.Ainv), _lib.resident_rows(st.pc)
+        off_A, off_Ainv, off_pc = _lib.gather_rows(A_d, par), _lib.gather_rows(Ainv_d, par), _lib.gather_rows(pc_d, par)
         if len(ch_off) > 0:
             z = np.divide(candidates_x[ch_off] - parents_x[par], xub - xlb) / last_steps
             off_A, off_Ainv, off_pc = _lib.cmaes_update_cholesky(off_A, off_Ainv, off_pc, z, off_psucc, cc, ccov, pthresh)
@@ -207,11 +211,18 @@ class CMAES(MOEA):
         slot[ch_off] = np.arange(len(ch_off))
         src_par = pidx[ch]
         sigmas_n = st.sigmas[src_par].copy()
-        A_n, Ainv_n, pc_n, psucc_n = st.A[src_par].copy(), st.Ainv[src_par].copy(), st.pc[src_par].copy(), st.psucc[src_par].copy()
+        psucc_n = st.psucc[src_par].copy()
+        src_idx = src_par.astype(np.int64)
         if len(ch_off) > 0:
             o = slot[ch[ch_is_off]]
             sigmas_n[ch_is_off] = off_sigmas[o]
-            A_n[ch_is_off], Ainv_n[ch_is_off], pc_n[ch_is_off], psucc_n[ch_is_off] = off_A[o], off_Ainv[o], off_pc[o], off_psucc[o]
+            psucc_n[ch_is_off] = off_psucc[o]
+            src_idx[ch_is_off] = o  # these rows come from the updated offspring arrays
+        # one device-side gather per state array: a surviving parent keeps its factors, a chosen offspring brings its own
+        sel = ch_is_off if len(ch_off) > 0 else None
+        A_n = _lib.gather_rows(A_d, src_idx, alt=off_A if sel is not None else None, sel=sel)
+        Ainv_n = _lib.gather_rows(Ainv_d, src_idx, alt=off_Ainv if sel is not None else None, sel=sel)
+        pc_n = _lib.gather_rows(pc_d, src_idx, alt=off_pc if sel is not None else None, sel=sel)
         st.parents_x = candidates_x[chosen]
         st.parents_y = candidates_y[chosen]
         st.rank = rank[chosen]

@@ -108,8 +108,24 @@ class SMPSO(MOEA):
             population_parm[sl] = xs[:popsize]
             population_obj[sl] = ys[:popsize]
             ranks.append(rank_p)
+        self._swarms = None  # device-resident copy of (population_parm, population_obj, velocity), built on first use
         return Struct(bounds=bounds, population_parm=population_parm, population_obj=population_obj, ranks=ranks,
                       velocity=velocity, successful_children=0)
+
+    # ---- resident swarm state (csrc/smpso.cu).  The NumPy state arrays stay the interface (dmosopt reads and saves
+    # them); the device copy is rebuilt whenever the caller has replaced or resized them.
+    def _resident(self):
+        st, p = self.state, self.opt_params
+        if p.adaptive_population_size or getattr(_lib, "SmpsoSwarms", None) is None or self.x_distance_metrics is not None:
+            return None
+        if self.y_distance_metrics is not None and self.y_distance_metrics[0] not in ("crowding", "euclidean"):
+            return None
+        sw = getattr(self, "_swarms", None)
+        key = (id(st.population_parm), id(st.population_obj), id(st.velocity), st.population_parm.shape)
+        if sw is None or getattr(self, "_swarms_key", None) != key:
+            sw = self._swarms = _lib.SmpsoSwarms(st.population_parm, st.population_obj, st.velocity, p.swarm_size, p.popsize)
+            self._swarms_key = key
+        return sw
 
     def generate_strategy(self, **params):
         """SMPSO.py:143-185."""
@@ -117,6 +133,9 @@ class SMPSO(MOEA):
         popsize, swarm_size = p.popsize, p.swarm_size
         xlb, xub = st.bounds[:, 0], st.bounds[:, 1]
         seed = self._rng_seed()
+        sw = self._resident()
+        if sw is not None:  # one kernel: moved positions and mutants of every swarm, float32 out
+            return sw.generate(p.di_mutation, xlb, xub, p.mutation_rate, seed, self._next_stream()), {}
         mutants = _lib.mutate_groups(st.population_parm, popsize, swarm_size, popsize, p.di_mutation, xlb, xub,
                                      p.mutation_rate, seed, self._next_stream())
         blocks = []
@@ -130,6 +149,12 @@ class SMPSO(MOEA):
         st = self.state
         popsize = self.opt_params.popsize
         xlb, xub = st.bounds[:, 0], st.bounds[:, 1]
+        sw = self._resident()
+        if sw is not None:
+            self._update_resident(sw, x_gen, y_gen, xlb, xub)
+            if self.opt_params.adaptive_operator_rates:
+                self.update_operator_rates()
+            return
         for sl in self.pop_slices:
             D = _lib.crowding_distance(y_gen[sl])
             st.velocity[sl] = velocity_vector(self.local_random, st.population_parm[sl], st.velocity[sl], x_gen[sl], D, xlb, xub)
@@ -147,6 +172,37 @@ class SMPSO(MOEA):
             self.update_population_size()
         if self.opt_params.adaptive_operator_rates:
             self.update_operator_rates()
+
+    def _update_resident(self, sw, x_gen, y_gen, xlb, xub):
+        """update_strategy with the swarm state in HBM: the scalar draws of velocity_vector are taken from the caller's
+        generator in the reference's order (SMPSO.py:317-331, one swarm after the other), everything else is one call."""
+        st, p = self.state, self.opt_params
+        S, popsize = p.swarm_size, p.popsize
+        rng = self.local_random
+        sc = np.zeros((S, 8))
+        for k in range(S):
+            r1 = rng.uniform(low=0.0, high=1.0, size=1)[0]
+            r2 = rng.uniform(low=0.0, high=1.0, size=1)[0]
+            w = rng.uniform(low=0.1, high=0.5, size=1)[0]
+            c1 = rng.uniform(low=1.5, high=2.5, size=1)[0]
+            c2 = rng.uniform(low=1.5, high=2.5, size=1)[0]
+            phi = c1 + c2 if c1 + c2 > 4 else 0
+            chi = 2 / (2 - phi - ((phi**2) - 4 * phi) ** (1 / 2))
+            if popsize > 2:
+                ind_1, ind_2 = rng.integers(low=0, high=popsize, size=2)
+            else:
+                ind_1 = ind_2 = -1
+            sc[k] = (w, c1, r1, c2, r2, chi, ind_1, ind_2)
+        code = {None: _lib.METRIC_NONE, "crowding": _lib.METRIC_CROWDING, "euclidean": _lib.METRIC_EUCLIDEAN}[
+            None if self.y_distance_metrics is None else self.y_distance_metrics[0]]
+        ranks, perm = sw.update(x_gen, y_gen, sc, xlb, xub, code, st.population_parm, st.population_obj)
+        st.velocity[...] = sw.velocity()
+        total_children = np.asarray(x_gen).shape[0]
+        for k in range(S):
+            st.ranks[k] = ranks[k]
+            # np.isin(arange(total_children), perm): how many of the kept rows are indices below total_children -- all of them
+            # (perm indexes the swarm's 2 * popsize stacked rows and total_children = 2 * swarm_size * popsize), as in SMPSO.py:231-233
+            st.successful_children += int(np.count_nonzero(np.isin(np.arange(total_children), perm[k], assume_unique=True)))
 
     def get_population_strategy(self):
         """SMPSO.py:240-258 (the reference returns the de-duplicated population, not the truncated one)."""

@@ -82,6 +82,9 @@ _SIGNATURES = {
     "dmo_mutate_groups": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _c_u64, _c_u64, _vp, _vp]),
     "dmo_cmaes_sample": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp]),
     "dmo_cmaes_update_cholesky": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl]),
+    "dmo_gather_rows": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp]),
+    "dmo_smpso_generate": (_c_int, [_vp, _vp, _vp, _c_int, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _c_u64, _c_u64, _vp]),
+    "dmo_smpso_update": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -776,22 +779,144 @@ def mutate_groups(pop_x, group_size, n_groups, per_group, di_mutation, xlb, xub,
     return (out, par) if return_parents else out
 
 
+class SmpsoSwarms:
+    """The swarm state of SMPSO resident in HBM (dmo_smpso_generate / dmo_smpso_update, csrc/smpso.cu): positions and
+    objectives as float64 arrays holding float32-representable values, velocities in float64."""
+
+    def __init__(self, parm, obj, vel, swarms, pop):
+        parm, obj, vel = np.asarray(parm), np.asarray(obj), np.asarray(vel)
+        self.swarms, self.pop, self.d, self.M = int(swarms), int(pop), parm.shape[1], obj.shape[1]
+        n = self.swarms * self.pop
+        assert parm.shape[0] == n and obj.shape[0] == n and vel.shape == (n, self.d)
+        self.parm = DeviceArray((n, self.d)).upload(_f64(parm))
+        self.obj = DeviceArray((n, self.M)).upload(_f64(obj))
+        self.vel = DeviceArray((n, self.d)).upload(_f64(vel))
+
+    def generate(self, di_mutation, xlb, xub, mutation_rate, seed, stream_id):
+        """x_gen (2 * swarms * pop, d) float32, laid out as SMPSO.py:163-184 does."""
+        di = _f64(np.broadcast_to(np.asarray(di_mutation, dtype=np.float64), (self.d,)))
+        lb, ub = _f64(xlb), _f64(xub)
+        out = pinned_empty((2 * self.swarms * self.pop, self.d), np.float32)
+        _check(load_library().dmo_smpso_generate(context(), self.parm.ptr, self.vel.ptr, self.swarms, self.pop, self.d, _ptr(di), _ptr(lb), _ptr(ub),
+                                                 float(mutation_rate), int(seed) & (2**64 - 1), int(stream_id), _ptr(out)), "dmo_smpso_generate")
+        return out
+
+    def update(self, x_gen, y_gen, scalars, xlb, xub, metric, parm_out, obj_out):
+        """One update_strategy (SMPSO.py:187-238) on the resident state; writes the new float32 state into parm_out /
+        obj_out and returns (ranks (swarms, pop) intp, perm (swarms, pop) int64)."""
+        n = self.swarms * self.pop
+        x_gen = np.asarray(x_gen)
+        if x_gen.dtype == np.float32:
+            xg, is32 = np.ascontiguousarray(x_gen[:n]), 1
+        else:
+            xg, is32 = _f64(x_gen[:n]), 0
+        yg = _f64(np.asarray(y_gen)[:n])
+        sc = _f64(scalars)
+        assert sc.shape == (self.swarms, 8) and xg.shape == (n, self.d) and yg.shape == (n, self.M)
+        lb, ub = _f64(xlb), _f64(xub)
+        ranks = np.empty(n, dtype=np.int32)
+        perm = np.empty(n, dtype=np.int64)
+        po = parm_out if (parm_out.dtype == np.float32 and parm_out.flags.c_contiguous) else np.empty((n, self.d), np.float32)
+        oo = obj_out if (obj_out.dtype == np.float32 and obj_out.flags.c_contiguous) else np.empty((n, self.M), np.float32)
+        _check(load_library().dmo_smpso_update(context(), self.parm.ptr, self.obj.ptr, self.vel.ptr, _ptr(xg), is32, _ptr(yg), self.swarms, self.pop, self.d,
+                                               self.M, int(metric), _ptr(sc), _ptr(lb), _ptr(ub), _ptr(ranks), _ptr(perm), _ptr(po), _ptr(oo)), "dmo_smpso_update")
+        if po is not parm_out:
+            parm_out[...] = po
+        if oo is not obj_out:
+            obj_out[...] = oo
+        return ranks.astype(np.intp).reshape(self.swarms, self.pop), perm.reshape(self.swarms, self.pop)
+
+    def velocity(self):
+        return self.vel.download()
+
+
+# --------------------------------------------------------------------------- device-resident per-individual state
+class ResidentRows:
+    """(n, ...) float64 array that lives in HBM across generations (MO-CMA-ES keeps one (d, d) Cholesky factor, its
+    inverse and one evolution path per parent: 604 MB at pop 131 072, d = 24).  NumPy sees it through ``__array__`` /
+    indexing (a device -> host copy on demand), the kernels through ``ptr``."""
+
+    def __init__(self, dev, shape):
+        self.dev = dev
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(np.float64)
+        self.ndim = len(self.shape)
+
+    @property
+    def ptr(self):
+        return self.dev.ptr
+
+    @property
+    def row_elems(self):
+        return int(np.prod(self.shape[1:])) if len(self.shape) > 1 else 1
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        n = int(np.prod(self.shape))
+        a = self.dev.download(n).reshape(self.shape) if n else np.zeros(self.shape)
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, key):
+        return np.asarray(self)[key]
+
+    def copy(self):
+        return gather_rows(self, np.arange(self.shape[0], dtype=np.int64))
+
+
+def resident_rows(a):
+    """Upload a host array as a ResidentRows (no-op for one)."""
+    if isinstance(a, ResidentRows):
+        return a
+    a = _f64(a)
+    return ResidentRows(DeviceArray(a.shape, np.float64).upload(a), a.shape)
+
+
+def gather_rows(src, idx, alt=None, sel=None):
+    """ResidentRows with rows ``(alt if sel[i] else src)[idx[i]]`` (dmo_gather_rows): device -> device."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    n = idx.shape[0]
+    shape = (n,) + src.shape[1:]
+    out = ResidentRows(DeviceArray(shape, np.float64), shape)
+    if n == 0:
+        return out
+    sl = None if sel is None else np.ascontiguousarray(sel, dtype=np.uint8)
+    assert sel is None or (alt is not None and alt.shape[1:] == src.shape[1:] and sl.shape == (n,))
+    _check(load_library().dmo_gather_rows(context(), src.ptr, None if alt is None else alt.ptr, _ptr(sl), _ptr(idx), n, src.row_elems, out.ptr), "dmo_gather_rows")
+    return out
+
+
+def identity_rows(n, d):
+    """n copies of the d x d identity, resident (CMAES.py:137-141) -- built on the device from one uploaded matrix."""
+    return gather_rows(resident_rows(np.identity(d)[None, :, :]), np.zeros(n, dtype=np.int64))
+
+
 # --------------------------------------------------------------------------- A13 / A15 CMAES
 def cmaes_sample(parents_x, sigmas, A, p_idx, z):
     px = _f64(parents_x)
     sg = _f64(sigmas)
-    A = _f64(A)
+    A = A if isinstance(A, ResidentRows) else _f64(A)
     z = _f64(z)
     pi = np.ascontiguousarray(p_idx, dtype=np.int64)
     n, d = z.shape
     cols = 1 if sg.ndim == 1 else sg.shape[1]
     out = np.empty((n, d), dtype=np.float64)
-    _check(load_library().dmo_cmaes_sample(context(), _ptr(px), _ptr(sg), cols, _ptr(A), px.shape[0], _ptr(pi), _ptr(z), n, d, _ptr(out)), "dmo_cmaes_sample")
+    _check(load_library().dmo_cmaes_sample(context(), _ptr(px), _ptr(sg), cols, A.ptr if isinstance(A, ResidentRows) else _ptr(A), px.shape[0], _ptr(pi), _ptr(z), n, d,
+                                           _ptr(out)), "dmo_cmaes_sample")
     return out
 
 
 def cmaes_update_cholesky(A, Ainv, pc, z, psucc, cc, ccov, pthresh):
-    """Batched CMAES.updateCholesky (dmosopt/CMAES.py:489-537); returns new (A, Ainv, pc)."""
+    """Batched CMAES.updateCholesky (dmosopt/CMAES.py:489-537); returns new (A, Ainv, pc).  ResidentRows are updated in
+    place in HBM (no factor crosses the PCIe bus), host arrays are copied, staged and returned."""
+    if isinstance(A, ResidentRows):
+        n, d = pc.shape
+        if n:
+            z, ps = _f64(z), _f64(psucc)
+            _check(load_library().dmo_cmaes_update_cholesky(context(), A.ptr, Ainv.ptr, pc.ptr, _ptr(z), _ptr(ps), n, d, float(cc), float(ccov), float(pthresh)),
+                   "dmo_cmaes_update_cholesky")
+        return A, Ainv, pc
     A = np.array(A, dtype=np.float64, order="C")
     Ainv = np.array(Ainv, dtype=np.float64, order="C")
     pc = np.array(pc, dtype=np.float64, order="C")

@@ -261,9 +261,38 @@ __global__ void cmaes_cholesky_kernel(double* __restrict__ A, double* __restrict
   }
 }
 
+// dst[i, :] = (sel && sel[i] ? alt : src)[idx[i], :]: row gather between device-resident per-individual state arrays
+// (MO-CMA-ES Cholesky factors: CMAES.py:385-411 re-assembles the parent set from old parents and updated offspring)
+__global__ void gather_rows_kernel(const double* __restrict__ src, const double* __restrict__ alt, const uint8_t* __restrict__ sel,
+                                   const int64_t* __restrict__ idx, int64_t n, int64_t row, double* __restrict__ dst) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * row) return;
+  const int64_t i = t / row, c = t - i * row;
+  const double* s = (sel && sel[i]) ? alt : src;
+  dst[t] = s[idx[i] * row + c];
+}
+
 }  // namespace
 
 extern "C" {
+
+int dmo_gather_rows(dmo_ctx* ctx, const double* src, const double* alt, const uint8_t* sel, const int64_t* idx, int64_t n,
+                    int64_t row_elems, double* dst) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return DMO_OK;
+  DMO_REQUIRE(n > 0 && row_elems >= 1 && src && idx && dst && (sel == nullptr || alt != nullptr), "gather_rows: bad arguments");
+  DMO_REQUIRE(dmo_is_device_ptr(src) && dmo_is_device_ptr(dst) && (!alt || dmo_is_device_ptr(alt)),
+              "gather_rows: src / alt / dst are device-resident arrays");
+  In<int64_t> ii;
+  In<uint8_t> is;
+  DMO_TRY(ii.init(ctx, idx, (size_t)n));
+  DMO_TRY(is.init(ctx, sel, (size_t)n));
+  DMO_LAUNCH(gather_rows_kernel, (unsigned)ceil_div(n * row_elems, 256), 256, 0, src, alt, is.d, ii.d, n, row_elems, dst);
+  DMO_CHECK_LAUNCH();
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
 
 int dmo_age_survival(dmo_ctx* ctx, const double* yn, const double* nn, int64_t m, int M, double p, const int32_t* extreme,
                      int n_ext, double* crowd) {

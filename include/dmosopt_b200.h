@@ -270,6 +270,25 @@ int dmo_mutate_groups(dmo_ctx* ctx, const double* pop_x, int64_t group_size, int
                       int64_t per_group, int d, const double* di_mutation, const double* xlb,
                       const double* xub, double mutation_rate, uint64_t seed, uint64_t stream_id,
                       double* children, int64_t* parent_rows);
+/* SMPSO with the swarm state resident in HBM: one call per generate / update instead of per-swarm host loops.
+ * parm (swarms*pop, d), obj (swarms*pop, M), vel (swarms*pop, d): DEVICE float64 arrays owned by the caller; position and
+ * objective values are float32-representable (the reference's state arrays are float32, SMPSO.py:107-113).
+ * dmo_smpso_generate (SMPSO.py:143-185): x_gen (2*swarms*pop, d) float32, swarm-major, per swarm pop moved positions
+ *   clip(x + v) then pop polynomial mutants of uniformly drawn particles of that swarm (Philox seed / stream_id).
+ * dmo_smpso_update (SMPSO.py:187-238): consumes rows [0, swarms*pop) of x_gen (float32 when x_is_f32, else float64) and
+ *   y_gen (float64) exactly as the reference slices them; scalars (swarms, 8) HOST doubles per swarm = w, c1, r1, c2, r2,
+ *   chi, ind1, ind2 drawn by the caller in the reference's order (velocity_vector, SMPSO.py:316-335; ind < 0 = no draw);
+ *   the leader with the larger crowding distance of y_gen[swarm slice] goes first.  All velocities are updated against
+ *   the old positions, then every swarm keeps the best pop of vstack(offspring slice, particles) (MOEA.remove_worst).
+ *   ranks (swarms*pop,) int32 and perm (swarms*pop,) int64 (indices into the swarm's stacked 2*pop rows) are returned;
+ *   parm_f32 / obj_f32 (optional) receive the new state as float32 host arrays. */
+int dmo_smpso_generate(dmo_ctx* ctx, const double* parm, const double* vel, int swarms, int64_t pop, int d,
+                       const double* di_mutation, const double* xlb, const double* xub, double mutation_rate,
+                       uint64_t seed, uint64_t stream_id, float* x_gen);
+int dmo_smpso_update(dmo_ctx* ctx, double* parm, double* obj, double* vel, const void* x_gen, int x_is_f32,
+                     const double* y_gen, int swarms, int64_t pop, int d, int M, int metric, const double* scalars,
+                     const double* xlb, const double* xub, int32_t* ranks, int64_t* perm, float* parm_f32,
+                     float* obj_f32);
 
 /* ---- A13 / A15: MO-CMA-ES ----------------------------------------------------------------
  * dmo_cmaes_sample: individuals[i] = x_p + sigma_p * (A_p @ z_i), p = p_idx[i] (dmosopt/CMAES.py:263-267);
@@ -281,6 +300,12 @@ int dmo_cmaes_sample(dmo_ctx* ctx, const double* parents_x, const double* sigmas
                      int d, double* individuals);
 int dmo_cmaes_update_cholesky(dmo_ctx* ctx, double* A, double* Ainv, double* pc, const double* z,
                               const double* psucc, int64_t n, int d, double cc, double ccov, double pthresh);
+/* Row gather between DEVICE-resident per-individual state arrays (the (n, d, d) Cholesky factors and (n, d) paths of
+ * MO-CMA-ES stay in HBM across generations; CMAES.py:385-411 re-assembles the next parent set from old parents and
+ * updated offspring): dst[i, :] = (sel && sel[i] ? alt : src)[idx[i], :], rows of row_elems doubles.  idx (n,) int64 and
+ * sel (n,) uint8 (may be NULL, then alt is ignored) may be host arrays. */
+int dmo_gather_rows(dmo_ctx* ctx, const double* src, const double* alt, const uint8_t* sel, const int64_t* idx,
+                    int64_t n, int64_t row_elems, double* dst);
 
 #ifdef __cplusplus
 }

@@ -39,11 +39,11 @@ def targets(X, M, kind):
     return Y
 
 
-def run(name, cls, d, M, pop, N, kind, gens=2, **okw):
+def run(name, cls, d, M, pop, N, kind, gens=2, keep_last=None, **okw):
     rng = np.random.default_rng(20260921 + len(name))
     xlb, xub = np.zeros(d), np.ones(d)
     Xtr = rng.random((N, d))
-    sm = b2.GPR_Matern(Xtr, targets(Xtr, M, kind), d, M, xlb, xub, optimizer=None, precision="tensor")
+    sm = b2.GPR_Matern(Xtr, targets(Xtr, M, kind), d, M, xlb, xub, optimizer=None)  # precision = auto (the plugin default)
     mdl = b2.Model(objective=sm)
     opt = cls(popsize=pop, nInput=d, nOutput=M, model=mdl, **okw)
     bounds = np.column_stack((xlb, xub))
@@ -52,22 +52,31 @@ def run(name, cls, d, M, pop, N, kind, gens=2, **okw):
         x0 = rng.random((pop, d))
     y0 = sm.evaluate(x0).astype(np.float32)
     opt.initialize_strategy(x0, y0, bounds, rng)
-    times = []
+    times, parts = [], []
     for g in range(gens + 1):
+        if g == gens and keep_last is not None:  # the state the last update starts from (for exact re-computation by the tests)
+            keep_last["before"] = {k: np.array(v) for k, v in opt.state.items() if isinstance(v, np.ndarray)}
         L.synchronize()
         t0 = time.perf_counter()
         x_gen, st = opt.generate()
+        t1 = time.perf_counter()
         y_gen = sm.evaluate(x_gen)
+        t2 = time.perf_counter()
         opt.update(x_gen, y_gen, st)
         L.synchronize()
-        times.append(time.perf_counter() - t0)
+        t3 = time.perf_counter()
+        times.append(t3 - t0)
+        parts.append((t1 - t0, t2 - t1, t3 - t2))
+    if keep_last is not None:
+        keep_last.update(x_gen=np.array(x_gen), y_gen=np.array(y_gen), state_gen=st, ms=np.mean(times[1:]) * 1e3, surrogate=sm)
     px, py = opt.population_objectives
     assert px.shape[1] == d and py.shape[1] == M and np.all(np.isfinite(py)), name
     assert np.all(px >= xlb - 1e-12) and np.all(px <= xub + 1e-12), name
     ms = np.mean(times[1:]) * 1e3
     P = x_gen.shape[0]
-    print(f"{name}: pop={pop} d={d} M={M} N_train={N} offspring/generation={P}: {ms:.1f} ms/generation -> {P / ms * 1e3:,.0f} candidates/s; "
-          f"population {px.shape[0]} rows", flush=True)
+    gm, em, um = (np.mean([p[i] for p in parts[1:]]) * 1e3 for i in range(3))
+    print(f"{name}: pop={pop} d={d} M={M} N_train={N} offspring/generation={P}: {ms:.1f} ms/generation (generate {gm:.1f} + surrogate {em:.1f} + update {um:.1f}) "
+          f"-> {P / ms * 1e3:,.0f} candidates/s; population {px.shape[0]} rows", flush=True)
     return opt, px, py
 
 

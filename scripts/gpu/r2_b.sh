@@ -24,3 +24,11 @@ P=4608
 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python scripts/gpu/gp_overlap_probe.py 4608 > gpurun_out/r2b_sanitizer.log 2>&1
 tail -40 gpurun_out/r2b_sanitizer.log >> $LOG
 grep -v "^Traceback\|^  File\|^    " $LOG | tail -60
+# --- everything else with the in-line (non-overlapped) pipeline, so that one open bug does not hide the rest
+export DMO_GP_NO_OVERLAP=1
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -s -k "gp or hv or precision or fused" > gpurun_out/r2b_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/r2b_tests.log
+timeout 600 python -m pytest tests/test_gpu_reference_loop.py -q -s > gpurun_out/r2b_ref_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/r2b_ref_tests.log
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r2b_bench.log 2>&1
+tail -15 gpurun_out/r2b_tests.log; tail -15 gpurun_out/r2b_ref_tests.log; tail -2 gpurun_out/r2b_bench.log | cut -c1-3000

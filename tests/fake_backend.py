@@ -184,6 +184,44 @@ def mutate_groups(pop_x, group_size, n_groups, per_group, di_mutation, xlb, xub,
     return (out, pi) if return_parents else out
 
 
+class ResidentRows:
+    """NumPy-backed stand-in for _lib.ResidentRows (same surface: shape, __array__, indexing, copy)."""
+
+    def __init__(self, a):
+        self.a = np.array(a, dtype=np.float64)
+        self.shape, self.dtype, self.ndim = self.a.shape, self.a.dtype, self.a.ndim
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        return self.a if dtype is None else self.a.astype(dtype)
+
+    def __getitem__(self, key):
+        return self.a[key]
+
+    def copy(self):
+        return ResidentRows(self.a)
+
+
+def resident_rows(a):
+    return a if isinstance(a, ResidentRows) else ResidentRows(a)
+
+
+def gather_rows(src, idx, alt=None, sel=None):
+    idx = np.asarray(idx, dtype=np.int64)
+    out = np.asarray(src)[idx] if len(idx) else np.zeros((0,) + src.shape[1:])
+    if sel is not None and len(idx):
+        sel = np.asarray(sel, dtype=bool)
+        out = out.copy()
+        out[sel] = np.asarray(alt)[idx[sel]]
+    return ResidentRows(out)
+
+
+def identity_rows(n, d):
+    return ResidentRows(np.broadcast_to(np.identity(d), (n, d, d)))
+
+
 def cmaes_sample(parents_x, sigmas, A, p_idx, z):
     p_idx = np.asarray(p_idx)
     return np.asarray(parents_x)[p_idx] + np.asarray(sigmas)[p_idx] * np.einsum("ijk,ik->ij", np.asarray(A)[p_idx], np.asarray(z))
@@ -192,15 +230,18 @@ def cmaes_sample(parents_x, sigmas, A, p_idx, z):
 def cmaes_update_cholesky(A, Ainv, pc, z, psucc, cc, ccov, pthresh):
     from oracle import cmaes
 
+    resident = isinstance(A, ResidentRows)
     A, Ainv, pc = np.array(A, dtype=float), np.array(Ainv, dtype=float), np.array(pc, dtype=float)
     for i in range(pc.shape[0]):
         A[i], Ainv[i], pc[i] = cmaes.update_cholesky(A[i], Ainv[i], np.asarray(z)[i], float(np.asarray(psucc)[i]), pc[i], cc, ccov, pthresh)
-    return A, Ainv, pc
+    return (ResidentRows(A), ResidentRows(Ainv), ResidentRows(pc)) if resident else (A, Ainv, pc)
 
+
+SmpsoSwarms = None  # the CPU seam exercises the per-swarm host path of the SMPSO plugin; the resident path is a GPU test
 
 FUNCTIONS = ["rank_nd", "crowding_distance", "euclidean_distance", "order_mo", "remove_worst", "remove_worst_pair", "tournament", "mutation_u", "sbx_u",
              "nsga2_generate", "GPHandle", "hypervolume", "ehvi_select", "get_duplicates", "age_survival", "smpso_velocity", "mutate_groups",
-             "cmaes_sample", "cmaes_update_cholesky"]
+             "cmaes_sample", "cmaes_update_cholesky", "ResidentRows", "resident_rows", "gather_rows", "identity_rows", "SmpsoSwarms"]
 
 
 def install(monkeypatch):
