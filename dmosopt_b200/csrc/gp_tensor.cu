@@ -13,8 +13,7 @@
 //   * operand tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_64B) into a 3-stage shared-memory ring, completion
 //     on mbarriers; one elected thread issues the MMAs; tcgen05.commit releases the ring slots and publishes the
 //     accumulator; four epilogue warps drain TMEM with tcgen05.ld;
-//   * persistent CTAs (one per SM) walk a list of equal-cost work items (version 3, below) while the K_* producer and
-//     the posterior-mean pass run beside them on the context's second stream.
+//   * persistent CTAs (one per SM) walk a list of equal-cost work items in an L2-friendly order (version 3, below).
 //
 // K_* itself is produced by kstar_tensor_kernel in fp32 (relative error ~1e-6 on K_*), the mean reduction is
 // accumulated in float64 in a fixed order (deterministic).
@@ -318,10 +317,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 //     start together at k = 0 and walk k at the same (MMA-bound) rate, so one of them pulls a K_* tile from DRAM and the
 //     others hit it in L2; version 2 ran 148 different candidate blocks at once and re-read every K_* tile from DRAM
 //     once per row block (22.6 GB per launch for 3.2 GB of operands).
-//   * The kernel is launched while the K_* producer (kstar_tensor_kernel, on the context's second stream) is still
-//     running: the TMA thread waits for the producer's per-candidate-block completion counter before the first load of
-//     an item (ld.acquire.gpu + fence.proxy.async), so K_* generation and the posterior mean overlap the contraction
-//     instead of preceding it.
+//   * Optional (DMO_GP_OVERLAP=1, off by default -- measured slower under the 1 kW power cap, see gp_predict_tensor): the
+//     kernel can be launched while the K_* producer (kstar_tensor_kernel, on the context's second stream) is still
+//     running; the TMA thread then waits for the producer's per-candidate-block completion counter before the first
+//     load of an item (ld.acquire.gpu + fence.proxy.async).
 namespace v3 {
 using v2::make_sdesc64;
 using v2::STAGE_BYTES2;
@@ -807,7 +806,12 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   // 2 = previous schedule, K_* / mean / variance back to back on one stream (DMO_GP_TC=2, kept for comparison)
   int version = 3;
   if (const char* e = getenv("DMO_GP_TC")) version = atoi(e) == 2 ? 2 : 3;
-  const bool overlap = version == 3 && !(getenv("DMO_GP_NO_OVERLAP") && atoi(getenv("DMO_GP_NO_OVERLAP")));
+  // DMO_GP_OVERLAP=1 (experimental, off by default): launch the contraction while the K_* producer is still running on
+  // the context's second stream and let its TMA thread wait on per-candidate-block completion counters.  Measured on
+  // B200 (profiles/README.md, round 2): no gain -- the contraction is power-capped, co-running FP32 work lowers its clock
+  // by what the overlap hides (10.35 ms vs 9.98 ms per predict at P = 65 536) -- and the co-residency of the two kernels
+  // is not guaranteed by the hardware scheduler (a launch at P = 4608 failed), so the in-line order is the product path.
+  const bool overlap = version == 3 && getenv("DMO_GP_OVERLAP") && atoi(getenv("DMO_GP_OVERLAP"));
   const int dbg = getenv("DMO_GP_DBG") ? atoi(getenv("DMO_GP_DBG")) : 0;  // 4: event instead of flags, 8: mean after var
   const bool use_flags = overlap && !(dbg & 4);
   constexpr int64_t TMv = v2::TM2;

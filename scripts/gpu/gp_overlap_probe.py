@@ -14,7 +14,7 @@ from dmosopt_b200 import _lib as L  # noqa: E402
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 4608
 N, d, M = 4096, 30, 3
 w = bench.workload(P, d, M, N)
-cache = os.path.join(ROOT, "gpurun_out", "probe_state.npz")
+cache = "/tmp/dmo_probe_state.npz"  # not under gpurun_out/: it is 400 MB and gpurun copies that directory back
 if os.path.exists(cache):
     z = np.load(cache)
     alpha, Lf, ym, ys = z["alpha"], z["L"], z["ym"], z["ys"]

@@ -630,8 +630,53 @@ def gen_plugins(rng):
     save("plugins", **out)
 
 
+def gen_trs(rng):
+    """Trust-region search (dmosopt/TRS.py): initialize, then three generate / update rounds driven by one NumPy generator
+    (Sobol perturbations come from scipy's sampler seeded by that generator, so the plugin reproduces them exactly), and
+    the vectorised benchmark functions (dmosopt/benchmarks/moo_benchmarks.py) evaluated row by row."""
+    from dmosopt import TRS
+    from dmosopt.benchmarks import moo_benchmarks as mb
+
+    out = {}
+    d, M, pop = 8, 3, 36
+    bounds = np.column_stack((np.zeros(d), np.ones(d)))
+    W = rng.random((d, M))
+    f = lambda x: dtlz2(x, M) + 0.01 * (x @ W)  # noqa: E731
+    x0 = rng.random((pop + 12, d))
+    y0 = f(x0)
+    opt = TRS.TRS(popsize=pop, nInput=d, nOutput=M, model=model_mod.Model())
+    out["x0"], out["y0"] = x0.copy(), y0.copy()
+    opt.initialize_strategy(x0, y0, bounds, np.random.default_rng(31))
+    out["init_px"], out["init_py"], out["init_rank"] = opt.state.population_parm.copy(), opt.state.population_obj.copy(), opt.state.rank.copy()
+    for g in range(3):
+        xg, stg = opt.generate()
+        yg = f(xg)
+        opt.update(xg, yg, stg)
+        out[f"g{g}_xgen"], out[f"g{g}_ygen"] = xg.copy(), yg.copy()
+        out[f"g{g}_px"], out[f"g{g}_py"], out[f"g{g}_rank"] = opt.state.population_parm.copy(), opt.state.population_obj.copy(), opt.state.rank.copy()
+        out[f"g{g}_length"] = np.array(opt.state.tr.length)
+    # benchmark functions: the reference evaluates one row at a time
+    names = ["zdt1", "zdt2", "zdt3", "zdt4", "zdt6", "dtlz1", "dtlz2", "dtlz3", "dtlz4", "dtlz5", "dtlz6", "dtlz7"]
+    got = []
+    for nm in names:
+        fn = getattr(mb, nm, None)
+        if fn is None:
+            continue
+        for m_obj, n_var in ((2, 10),) if nm.startswith("zdt") else ((3, 12), (5, 22)):
+            X = rng.random((17, n_var))
+            try:
+                Y = np.vstack([np.asarray(fn(x, m_obj) if not nm.startswith("zdt") else fn(x), dtype=np.float64).ravel() for x in X])
+            except Exception:  # signature differs: skip, the test only covers what was recorded
+                continue
+            key = f"bm_{nm}_{m_obj}_{n_var}"
+            out[key + "_X"], out[key + "_Y"] = X, Y
+            got.append(key)
+    out["bm_keys"] = np.array(got)
+    save("trs", **out)
+
+
 def main():
-    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes", "plugins"]
+    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes", "plugins", "trs"]
     gens = {
         "dda": gen_dda,
         "distance": gen_distance,
@@ -647,6 +692,7 @@ def main():
         "smpso": gen_smpso,
         "cmaes": gen_cmaes,
         "plugins": gen_plugins,
+        "trs": gen_trs,
     }
     for i, name in enumerate(which):
         gens[name](np.random.default_rng(20260921 + i * 0 + sum(map(ord, name))))
