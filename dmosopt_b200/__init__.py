@@ -2,7 +2,7 @@
 
 Plugin import paths (dmosopt resolves them with ``config.import_object_by_path``):
 
-    optimizer_name         = "dmosopt_b200.NSGA2" | "dmosopt_b200.AGEMOEA" | "dmosopt_b200.SMPSO" | "dmosopt_b200.CMAES"
+    optimizer_name         = "dmosopt_b200.NSGA2" | "dmosopt_b200.AGEMOEA" | "dmosopt_b200.SMPSO" | "dmosopt_b200.CMAES" | "dmosopt_b200.TRS"
     surrogate_method_name  = "dmosopt_b200.GPR_Matern" | "dmosopt_b200.GPR_RBF"
 
 ``dmosopt_b200.install()`` additionally routes the controller-side helpers that dmosopt calls on its own modules
@@ -21,6 +21,7 @@ from .model import GPR_Matern, GPR_RBF, Model  # noqa: F401
 from .AGEMOEA import AGEMOEA  # noqa: F401
 from .CMAES import CMAES  # noqa: F401
 from .SMPSO import SMPSO  # noqa: F401
+from .TRS import TRS  # noqa: F401
 
 
 def install(package="dmosopt"):

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "dmo_cmaes_sample": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp]),
     "dmo_cmaes_update_cholesky": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl]),
     "dmo_gather_rows": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp]),
+    "dmo_benchmark_eval": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _c_int, _c_dbl, _vp]),
     "dmo_smpso_generate": (_c_int, [_vp, _vp, _vp, _c_int, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _c_u64, _c_u64, _vp]),
     "dmo_smpso_update": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
@@ -777,6 +778,18 @@ def mutate_groups(pop_x, group_size, n_groups, per_group, di_mutation, xlb, xub,
         "dmo_mutate_groups",
     )
     return (out, par) if return_parents else out
+
+
+BENCHMARKS = {"zdt1": 0, "zdt3": 1, "dtlz1": 10, "dtlz2": 11, "dtlz3": 12, "dtlz4": 13, "dtlz5": 14, "dtlz7": 16, "wfg4": 24}
+
+
+def benchmark_eval(name, X, n_obj, alpha=100.0):
+    """Rows of X through one of the reference's benchmark functions (dmosopt/benchmarks/moo_benchmarks.py), on the GPU."""
+    X = _f64(X)
+    n, d = X.shape
+    Y = np.empty((n, int(n_obj)), dtype=np.float64)
+    _check(load_library().dmo_benchmark_eval(context(), BENCHMARKS[name], _in(X), n, d, int(n_obj), float(alpha), _ptr(Y)), "dmo_benchmark_eval")
+    return Y
 
 
 class SmpsoSwarms:

@@ -307,6 +307,23 @@ int dmo_cmaes_update_cholesky(dmo_ctx* ctx, double* A, double* Ainv, double* pc,
 int dmo_gather_rows(dmo_ctx* ctx, const double* src, const double* alt, const uint8_t* sel, const int64_t* idx,
                     int64_t n, int64_t row_elems, double* dst);
 
+/* ---- N4: vectorised benchmark objective functions --------------------------------------------
+ * replaces the row-at-a-time Python functions of dmosopt/benchmarks/moo_benchmarks.py (dtlz1 :21, dtlz2 :59,
+ * dtlz3 :97, dtlz4 :136, dtlz5 :174, dtlz7 :218, wfg4 :335) and the example objectives ZDT1 / ZDT3
+ * (examples/example_dmosopt_zdt1.py:9-20, examples/example_dmosopt_zdt3.py:9-21): X (n, n_var) -> Y (n, n_obj).
+ * alpha is DTLZ4's bias exponent (the reference's default is 100), ignored elsewhere. */
+#define DMO_BM_ZDT1 0
+#define DMO_BM_ZDT3 1
+#define DMO_BM_DTLZ1 10
+#define DMO_BM_DTLZ2 11
+#define DMO_BM_DTLZ3 12
+#define DMO_BM_DTLZ4 13
+#define DMO_BM_DTLZ5 14
+#define DMO_BM_DTLZ7 16
+#define DMO_BM_WFG4 24
+int dmo_benchmark_eval(dmo_ctx* ctx, int problem, const double* X, int64_t n, int n_var, int n_obj, double alpha,
+                       double* Y);
+
 #ifdef __cplusplus
 }
 #endif

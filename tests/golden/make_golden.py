@@ -656,7 +656,7 @@ def gen_trs(rng):
         out[f"g{g}_px"], out[f"g{g}_py"], out[f"g{g}_rank"] = opt.state.population_parm.copy(), opt.state.population_obj.copy(), opt.state.rank.copy()
         out[f"g{g}_length"] = np.array(opt.state.tr.length)
     # benchmark functions: the reference evaluates one row at a time
-    names = ["zdt1", "zdt2", "zdt3", "zdt4", "zdt6", "dtlz1", "dtlz2", "dtlz3", "dtlz4", "dtlz5", "dtlz6", "dtlz7"]
+    names = ["dtlz1", "dtlz2", "dtlz3", "dtlz4", "dtlz5", "dtlz7", "wfg4"]
     got = []
     for nm in names:
         fn = getattr(mb, nm, None)
@@ -671,6 +671,18 @@ def gen_trs(rng):
             key = f"bm_{nm}_{m_obj}_{n_var}"
             out[key + "_X"], out[key + "_Y"] = X, Y
             got.append(key)
+    # ZDT1 / ZDT3: the objective functions of the reference's examples (examples/example_dmosopt_zdt1.py:9-20, _zdt3.py:9-21)
+    import importlib.util
+
+    for nm in ("zdt1", "zdt3"):
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(MOEA.__file__))), "examples", f"example_dmosopt_{nm}.py")
+        text = open(path).read()
+        src = text[text.index(f"def {nm}(") : text.index("def obj_fun")]  # the objective function only (the rest needs MPI / dmosopt.run)
+        ns = {"np": np}
+        exec(compile(src, path, "exec"), ns)
+        X = rng.random((17, 30))
+        out[f"bm_{nm}_2_30_X"], out[f"bm_{nm}_2_30_Y"] = X, np.vstack([np.asarray(ns[nm](x), dtype=np.float64).ravel() for x in X])
+        got.append(f"bm_{nm}_2_30")
     out["bm_keys"] = np.array(got)
     save("trs", **out)
 

@@ -894,3 +894,34 @@ def test_age_smpso_cmaes_plugins_golden_on_gpu(L):
     from test_host_plugins import _run_plugin_goldens
 
     _run_plugin_goldens(b2)
+
+
+# ------------------------------------------------------------------------------------------ N4: TRS + benchmark functions
+def test_trs_plugin_golden_sequence_on_gpu(L):
+    import dmosopt_b200 as b2
+    from test_host_plugins import _run_trs_golden
+
+    _run_trs_golden(b2)
+
+
+def test_benchmark_functions_on_gpu(L):
+    """dmo_benchmark_eval against the reference's own row-at-a-time outputs (tests/golden/trs.npz) and, at population size,
+    against the vectorised oracle."""
+    from dmosopt_b200 import benchmarks as bm
+    from oracle import benchmarks as ob
+
+    g = load_golden("trs")
+    for key in g["bm_keys"]:
+        key = str(key)
+        _, nm, M, d = key.split("_")
+        fn = getattr(bm, nm)
+        X = g[key + "_X"]
+        Y = fn(X) if nm.startswith("zdt") else fn(X, int(M))
+        np.testing.assert_allclose(Y, g[key + "_Y"], rtol=1e-12, atol=1e-300, equal_nan=True)
+        y1 = fn(X[3]) if nm.startswith("zdt") else fn(X[3], int(M))  # one decision vector, as the reference is called
+        assert y1.shape == (Y.shape[1],) and np.allclose(y1, Y[3], rtol=0, atol=0, equal_nan=True)
+    rng = np.random.default_rng(8)
+    X = rng.random((65536, 24))
+    np.testing.assert_allclose(bm.wfg4(X, 4), ob.wfg4(X, 4), rtol=1e-12)
+    np.testing.assert_allclose(bm.dtlz7(X[:, :22], 5), ob.dtlz7(X[:, :22], 5), rtol=1e-12)
+    np.testing.assert_allclose(bm.dtlz2(X[:, :12], 3), ob.dtlz2(X[:, :12], 3), rtol=1e-12)

@@ -153,6 +153,33 @@ def _run_plugin_goldens(b2):
     assert px.shape[1] == d and py.shape[1] == M
 
 
+def _run_trs_golden(b2):
+    """Trust-region search: exact state sequence of the reference over three generate / update rounds (tests/golden/trs.npz).
+    The Sobol perturbations come from scipy's sampler seeded by the caller's generator, so generate() itself is reproduced."""
+    g = load_golden("trs")
+    d, M = g["x0"].shape[1], g["y0"].shape[1]
+    pop = g["init_px"].shape[0]
+    bounds = np.column_stack((np.zeros(d), np.ones(d)))
+    opt = b2.TRS(popsize=pop, nInput=d, nOutput=M, model=b2.Model(), distance_metric=None)
+    opt.initialize_strategy(g["x0"].copy(), g["y0"].copy(), bounds, np.random.default_rng(31))
+    assert np.array_equal(opt.state.population_parm, g["init_px"]) and np.array_equal(opt.state.population_obj, g["init_py"])
+    assert np.array_equal(opt.state.rank, g["init_rank"])
+    for gi in range(3):
+        xg, stg = opt.generate()
+        assert np.array_equal(xg, g[f"g{gi}_xgen"]), gi
+        opt.update(xg, g[f"g{gi}_ygen"], stg)
+        assert np.array_equal(opt.state.population_parm, g[f"g{gi}_px"]), gi
+        assert np.array_equal(opt.state.population_obj, g[f"g{gi}_py"]), gi
+        assert np.array_equal(opt.state.rank, g[f"g{gi}_rank"]), gi
+        assert opt.state.tr.length == float(g[f"g{gi}_length"])
+
+
+def test_trs_plugin_reproduces_reference(fake):
+    import dmosopt_b200 as b2
+
+    _run_trs_golden(b2)
+
+
 def test_age_smpso_cmaes_plugins_reproduce_reference(fake):
     import dmosopt_b200 as b2
 
