@@ -109,6 +109,8 @@ class SMPSO(MOEA):
             population_obj[sl] = ys[:popsize]
             ranks.append(rank_p)
         self._swarms = None  # device-resident copy of (population_parm, population_obj, velocity), built on first use
+        # page-locked state arrays (same dtypes / values): the per-generation state read-back is a DMA, not a staged copy
+        population_parm, population_obj, velocity = _lib.pinned_like(population_parm), _lib.pinned_like(population_obj), _lib.pinned_like(velocity)
         return Struct(bounds=bounds, population_parm=population_parm, population_obj=population_obj, ranks=ranks,
                       velocity=velocity, successful_children=0)
 
@@ -196,7 +198,8 @@ class SMPSO(MOEA):
         code = {None: _lib.METRIC_NONE, "crowding": _lib.METRIC_CROWDING, "euclidean": _lib.METRIC_EUCLIDEAN}[
             None if self.y_distance_metrics is None else self.y_distance_metrics[0]]
         ranks, perm = sw.update(x_gen, y_gen, sc, xlb, xub, code, st.population_parm, st.population_obj)
-        st.velocity[...] = sw.velocity()
+        sw.velocity_into(st.velocity)
+        _lib.mirror_drop(x_gen)  # consumed: the HBM copy of the offspring matrix is released
         total_children = np.asarray(x_gen).shape[0]
         for k in range(S):
             st.ranks[k] = ranks[k]

@@ -84,7 +84,7 @@ _SIGNATURES = {
     "dmo_cmaes_update_cholesky": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl]),
     "dmo_gather_rows": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp]),
     "dmo_benchmark_eval": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _c_int, _c_dbl, _vp]),
-    "dmo_smpso_generate": (_c_int, [_vp, _vp, _vp, _c_int, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _c_u64, _c_u64, _vp]),
+    "dmo_smpso_generate": (_c_int, [_vp, _vp, _vp, _c_int, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _c_u64, _c_u64, _vp, _vp]),
     "dmo_smpso_update": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
@@ -806,12 +806,19 @@ class SmpsoSwarms:
         self.vel = DeviceArray((n, self.d)).upload(_f64(vel))
 
     def generate(self, di_mutation, xlb, xub, mutation_rate, seed, stream_id):
-        """x_gen (2 * swarms * pop, d) float32, laid out as SMPSO.py:163-184 does."""
+        """x_gen (2 * swarms * pop, d), laid out as SMPSO.py:163-184 does: the reference's float32 values, handed out as the
+        float64 array MOEA.generate turns them into (np.clip against float64 bounds, MOEA.py:155) -- read-only, page-locked,
+        with its device copy kept as a mirror so that evaluate(x_gen) / update(x_gen, ...) do not ship it back over PCIe."""
         di = _f64(np.broadcast_to(np.asarray(di_mutation, dtype=np.float64), (self.d,)))
         lb, ub = _f64(xlb), _f64(xub)
-        out = pinned_empty((2 * self.swarms * self.pop, self.d), np.float32)
+        rows = 2 * self.swarms * self.pop
+        x_dev = DeviceArray((rows, self.d), np.float64)
         _check(load_library().dmo_smpso_generate(context(), self.parm.ptr, self.vel.ptr, self.swarms, self.pop, self.d, _ptr(di), _ptr(lb), _ptr(ub),
-                                                 float(mutation_rate), int(seed) & (2**64 - 1), int(stream_id), _ptr(out)), "dmo_smpso_generate")
+                                                 float(mutation_rate), int(seed) & (2**64 - 1), int(stream_id), None, x_dev.ptr), "dmo_smpso_generate")
+        out = pinned_empty((rows, self.d), np.float64)
+        memcpy(out, x_dev.ptr, out.nbytes)
+        mirror_register(out, x_dev)
+        out.flags.writeable = False
         return out
 
     def update(self, x_gen, y_gen, scalars, xlb, xub, metric, parm_out, obj_out):
@@ -822,7 +829,7 @@ class SmpsoSwarms:
         if x_gen.dtype == np.float32:
             xg, is32 = np.ascontiguousarray(x_gen[:n]), 1
         else:
-            xg, is32 = _f64(x_gen[:n]), 0
+            xg, is32 = _f64(x_gen[:n]), 0  # a view of the caller's array: its device mirror (if any) is found by address
         yg = _f64(np.asarray(y_gen)[:n])
         sc = _f64(scalars)
         assert sc.shape == (self.swarms, 8) and xg.shape == (n, self.d) and yg.shape == (n, self.M)
@@ -831,7 +838,7 @@ class SmpsoSwarms:
         perm = np.empty(n, dtype=np.int64)
         po = parm_out if (parm_out.dtype == np.float32 and parm_out.flags.c_contiguous) else np.empty((n, self.d), np.float32)
         oo = obj_out if (obj_out.dtype == np.float32 and obj_out.flags.c_contiguous) else np.empty((n, self.M), np.float32)
-        _check(load_library().dmo_smpso_update(context(), self.parm.ptr, self.obj.ptr, self.vel.ptr, _ptr(xg), is32, _ptr(yg), self.swarms, self.pop, self.d,
+        _check(load_library().dmo_smpso_update(context(), self.parm.ptr, self.obj.ptr, self.vel.ptr, _in(xg), is32, _in(yg), self.swarms, self.pop, self.d,
                                                self.M, int(metric), _ptr(sc), _ptr(lb), _ptr(ub), _ptr(ranks), _ptr(perm), _ptr(po), _ptr(oo)), "dmo_smpso_update")
         if po is not parm_out:
             parm_out[...] = po
@@ -839,8 +846,12 @@ class SmpsoSwarms:
             obj_out[...] = oo
         return ranks.astype(np.intp).reshape(self.swarms, self.pop), perm.reshape(self.swarms, self.pop)
 
-    def velocity(self):
-        return self.vel.download()
+    def velocity_into(self, out):
+        """Copy the resident velocities into ``out`` (float64, C-contiguous; page-locked state arrays take the DMA path)."""
+        if out.dtype == np.float64 and out.flags.c_contiguous:
+            memcpy(out, self.vel.ptr, out.nbytes)
+        else:
+            out[...] = self.vel.download()
 
 
 # --------------------------------------------------------------------------- device-resident per-individual state

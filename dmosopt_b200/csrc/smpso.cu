@@ -27,7 +27,7 @@ __device__ __forceinline__ double mutate_gene_sm(double parent, double u, double
 __global__ void smpso_generate_kernel(const double* __restrict__ parm, const double* __restrict__ vel, int S, int64_t pop, int d,
                                       const double* __restrict__ di, const double* __restrict__ xlb,
                                       const double* __restrict__ xub, double rate, uint64_t seed, uint64_t stream_id,
-                                      float* __restrict__ out32) {
+                                      float* __restrict__ out32, double* __restrict__ out64) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 2 * (int64_t)S * pop * d) return;
   const int64_t r = t / d;
@@ -47,7 +47,8 @@ __global__ void smpso_generate_kernel(const double* __restrict__ parm, const dou
     const uint4 b = ph((uint64_t)(c * d + j), (stream_id << 8) | P_MUT_GENES);
     v = mutate_gene_sm(parm[prow * d + j], u01_53(b.x, b.y), di[j], xlb[j], xub[j], rate);
   }
-  out32[t] = (float)v;
+  if (out32) out32[t] = (float)v;
+  if (out64) out64[t] = (double)(float)v;  // the same float32 values, widened (what np.clip(x_gen, xlb, xub) hands on, MOEA.py:155)
 }
 
 // velocity of one swarm, in place (SMPSO.py:316-348).  Leaders are rows ind1 / ind2 of the swarm's archive slice; the one
@@ -98,22 +99,26 @@ extern "C" {
 
 int dmo_smpso_generate(dmo_ctx* ctx, const double* parm, const double* vel, int swarms, int64_t pop, int d,
                        const double* di_mutation, const double* xlb, const double* xub, double mutation_rate, uint64_t seed,
-                       uint64_t stream_id, float* x_gen) {
+                       uint64_t stream_id, float* x_gen, double* x_gen_f64) {
   if (!ctx) return DMO_ERR_ARG;
   DMO_CUDA(cudaSetDevice(ctx->device));
-  DMO_REQUIRE(parm && vel && swarms >= 1 && pop >= 1 && d >= 1 && di_mutation && xlb && xub && x_gen, "smpso_generate: bad arguments");
+  DMO_REQUIRE(parm && vel && swarms >= 1 && pop >= 1 && d >= 1 && di_mutation && xlb && xub && (x_gen || x_gen_f64),
+              "smpso_generate: bad arguments");
   DMO_REQUIRE(dmo_is_device_ptr(parm) && dmo_is_device_ptr(vel), "smpso_generate: the swarm state must be resident on the device");
   const int64_t rows = 2 * (int64_t)swarms * pop;
   In<double> idi, ilb, iub;
   Out<float> ox;
+  Out<double> ox64;
   DMO_TRY(idi.init(ctx, di_mutation, d));
   DMO_TRY(ilb.init(ctx, xlb, d));
   DMO_TRY(iub.init(ctx, xub, d));
   DMO_TRY(ox.init(ctx, x_gen, (size_t)rows * d));
+  DMO_TRY(ox64.init(ctx, x_gen_f64, (size_t)rows * d));
   DMO_LAUNCH(smpso_generate_kernel, (unsigned)ceil_div(rows * d, 256), 256, 0, parm, vel, swarms, pop, d, idi.d, ilb.d, iub.d,
-             mutation_rate, seed, stream_id, ox.d);
+             mutation_rate, seed, stream_id, ox.d, ox64.d);
   DMO_CHECK_LAUNCH();
   DMO_TRY(ox.finish(ctx));
+  DMO_TRY(ox64.finish(ctx));
   DMO_CUDA(cudaStreamSynchronize(ctx->stream));
   return DMO_OK;
 }

@@ -274,7 +274,9 @@ int dmo_mutate_groups(dmo_ctx* ctx, const double* pop_x, int64_t group_size, int
  * parm (swarms*pop, d), obj (swarms*pop, M), vel (swarms*pop, d): DEVICE float64 arrays owned by the caller; position and
  * objective values are float32-representable (the reference's state arrays are float32, SMPSO.py:107-113).
  * dmo_smpso_generate (SMPSO.py:143-185): x_gen (2*swarms*pop, d) float32, swarm-major, per swarm pop moved positions
- *   clip(x + v) then pop polynomial mutants of uniformly drawn particles of that swarm (Philox seed / stream_id).
+ *   clip(x + v) then pop polynomial mutants of uniformly drawn particles of that swarm (Philox seed / stream_id);
+ *   x_gen_f64 (optional, host or device) receives the same float32 values widened to float64 -- what MOEA.generate
+ *   hands on after its np.clip (MOEA.py:155).  Either output may be NULL.
  * dmo_smpso_update (SMPSO.py:187-238): consumes rows [0, swarms*pop) of x_gen (float32 when x_is_f32, else float64) and
  *   y_gen (float64) exactly as the reference slices them; scalars (swarms, 8) HOST doubles per swarm = w, c1, r1, c2, r2,
  *   chi, ind1, ind2 drawn by the caller in the reference's order (velocity_vector, SMPSO.py:316-335; ind < 0 = no draw);
@@ -284,7 +286,7 @@ int dmo_mutate_groups(dmo_ctx* ctx, const double* pop_x, int64_t group_size, int
  *   parm_f32 / obj_f32 (optional) receive the new state as float32 host arrays. */
 int dmo_smpso_generate(dmo_ctx* ctx, const double* parm, const double* vel, int swarms, int64_t pop, int d,
                        const double* di_mutation, const double* xlb, const double* xub, double mutation_rate,
-                       uint64_t seed, uint64_t stream_id, float* x_gen);
+                       uint64_t seed, uint64_t stream_id, float* x_gen, double* x_gen_f64);
 int dmo_smpso_update(dmo_ctx* ctx, double* parm, double* obj, double* vel, const void* x_gen, int x_is_f32,
                      const double* y_gen, int swarms, int64_t pop, int d, int M, int metric, const double* scalars,
                      const double* xlb, const double* xub, int32_t* ranks, int64_t* perm, float* parm_f32,
