@@ -66,6 +66,7 @@ _SIGNATURES = {
     ),
     "dmo_gp_create": (_c_int, [_vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "dmo_gp_destroy": (_c_int, [_vp, _vp]),
+    "dmo_gp_fit": (_c_int, [_vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp]),
     "dmo_gp_set_linear_mean": (_c_int, [_vp, _vp, _vp, _vp]),
     "dmo_gp_predict": (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _c_int]),
     "dmo_gp_auto_info": (_c_int, [_vp, _vp, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_dbl),
@@ -614,6 +615,28 @@ def nsga2_generate(pop_x, pool_idx, popsize, crossover_prob, mutation_prob, muta
         "u_genes": draws[5 * T :].reshape(T, 2, d),
     }
     return x_gen[:P], kind[:P], dd
+
+
+# --------------------------------------------------------------------------- N1: exact-GP fit for given hyper-parameters
+def gp_fit(X_train, y, constant, length_scale, noise, kernel=KERNEL_MATERN52, jitter=1e-10, want_L=True, want_alpha=True):
+    """(L (M,N,N) or None, alpha (M,N) or None, lml (M,)) of the exact GP with the given hyper-parameters, per objective:
+    K = c k(X, X) + (noise + jitter) I, L = chol(K), alpha = K^-1 y, lml = log marginal likelihood (dmo_gp_fit).
+    X_train (N,d) normalised inputs, y (M,N) normalised targets, length_scale (M,d)."""
+    X_train = _f64(X_train)
+    N, d = X_train.shape
+    y = _f64(y)
+    M = y.shape[0]
+    ls = np.empty((M, d), dtype=np.float64)
+    for m in range(M):
+        ls[m, :] = np.asarray(length_scale[m], dtype=np.float64)
+    cst, nz = _f64(constant), _f64(noise)
+    assert y.shape == (M, N) and cst.shape == (M,) and nz.shape == (M,)
+    L = np.empty((M, N, N), dtype=np.float64) if want_L else None
+    alpha = np.empty((M, N), dtype=np.float64) if want_alpha else None
+    lml = np.empty(M, dtype=np.float64)
+    _check(load_library().dmo_gp_fit(context(), N, d, M, int(kernel), _ptr(X_train), _ptr(y), _ptr(cst), _ptr(ls), _ptr(nz), float(jitter), _ptr(L), _ptr(alpha),
+                                     _ptr(lml)), "dmo_gp_fit")
+    return L, alpha, lml
 
 
 # --------------------------------------------------------------------------- A18

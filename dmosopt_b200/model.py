@@ -5,11 +5,13 @@ Reference: dmosopt/model.py:1182-1275 (GPR_Matern) and :1278-1364 (GPR_RBF); sel
 signature, ``predict`` / ``evaluate`` and the ``return_mean_variance`` switch are the reference's.
 
 Scope: the per-generation call -- ``predict`` -- runs on the GPU
-(dmo_gp_predict).  Hyper-parameter fitting happens once per epoch and is NOT part of this build: it is
-delegated to scikit-learn's ``GaussianProcessRegressor.fit`` on the host, with the reference's SCE-UA
-optimiser when dmosopt is importable (``optimizer="sceua"``), scikit-learn's L-BFGS-B otherwise, or no
-optimisation at all (``optimizer=None``: fixed initial theta, the BASELINE.md configuration).  After
-fitting, the posterior state (X_train, alpha, L, theta, y mean/std) is uploaded once.
+(dmo_gp_predict).  The once-per-epoch fit (section 8f row N1) runs on the GPU as well (``fit="gpu"``, the default): for
+given hyper-parameters the kernel matrix, its Cholesky factor, alpha and the log marginal likelihood come from
+dmo_gp_fit (csrc/gp_fit.cu); with ``optimizer="sceua"`` the reference's SCE-UA search (dmosopt/model.py:1419-1753, used
+when dmosopt is importable; a bounded derivative-free SciPy search otherwise) drives that evaluation instead of
+scikit-learn's host Cholesky; ``optimizer=None`` keeps the initial theta (the BASELINE.md configuration).
+``fit="sklearn"`` is the previous behaviour: scikit-learn's ``GaussianProcessRegressor.fit`` on the host.  Either way the
+result is a list of scikit-learn regressors (``smlist``, as the reference keeps) whose posterior state is uploaded once.
 """
 
 import numpy as np
@@ -64,6 +66,7 @@ class _GPRBase:
         top_k=None,
         logger=None,
         precision="auto",
+        fit="gpu",
         **kwargs,
     ):
         from sklearn.gaussian_process import GaussianProcessRegressor
@@ -107,16 +110,79 @@ class _GPRBase:
         kernel = ConstantKernel(1, constant_kernel_bounds) * stationary + WhiteKernel(
             noise_level=self._default_noise, noise_level_bounds=noise_level_bounds
         )
+        if fit not in ("gpu", "sklearn"):
+            raise ValueError(f"{self._name}: fit must be 'gpu' or 'sklearn' (got {fit!r})")
         optf = _host_optimizer(optimizer, seed, logger)
-        smlist = []
-        for i in range(nOutput):
-            if logger is not None:
-                logger.info(f"{self._name}: creating regressor for output {i + 1} of {nOutput}...")
-            gpr = GaussianProcessRegressor(kernel=kernel, optimizer=optf, normalize_y=True)
-            gpr.fit(x, y[:, i])
-            smlist.append(gpr)
-        self.smlist = smlist
+        if fit == "gpu":
+            self.smlist = self._fit_on_gpu(kernel, optf, x, y, logger)
+        else:
+            smlist = []
+            for i in range(nOutput):
+                if logger is not None:
+                    logger.info(f"{self._name}: creating regressor for output {i + 1} of {nOutput}...")
+                gpr = GaussianProcessRegressor(kernel=kernel, optimizer=optf, normalize_y=True)
+                gpr.fit(x, y[:, i])
+                smlist.append(gpr)
+            self.smlist = smlist
         self._upload()
+
+    def _fit_on_gpu(self, kernel, optf, x, y, logger):
+        """GaussianProcessRegressor.fit restated around dmo_gp_fit (sklearn/gaussian_process/_gpr.py:fit): targets are
+        normalised per output, theta = log(constant, length scale(s), noise) is either kept or searched by the optimiser
+        with -log marginal likelihood evaluated on the GPU, and the final Cholesky factor / alpha of every output come from
+        one batched call.  Returns scikit-learn regressors carrying that state (their own predict works on it)."""
+        from sklearn.gaussian_process import GaussianProcessRegressor
+
+        M, d = self.nOutput, self.nInput
+        y_mean = np.mean(y, axis=0)
+        y_std = np.std(y, axis=0)
+        y_std = np.where(y_std < 10 * np.finfo(np.float64).eps, 1.0, y_std)  # sklearn _handle_zeros_in_scale
+        yn = ((y - y_mean) / y_std).T.copy()  # (M, N)
+        jitter = 1e-10  # GaussianProcessRegressor(alpha=1e-10)
+
+        def unpack(theta):
+            v = np.exp(np.asarray(theta, dtype=np.float64))
+            return v[0], v[1:-1], v[-1]  # constant, length scale(s), noise
+
+        thetas = []
+        for i in range(M):
+            theta = np.array(kernel.theta, dtype=np.float64)
+            if optf is not None:
+                if logger is not None:
+                    logger.info(f"{self._name}: optimising the hyper-parameters of output {i + 1} of {M} (likelihood on the GPU)...")
+
+                def obj_func(th, eval_gradient=False, _i=i):
+                    c, ls, nz = unpack(th)
+                    try:
+                        _, _, lml = _lib.gp_fit(x, yn[_i : _i + 1], [c], [np.broadcast_to(ls, (d,))], [nz], kernel=self._kernel_code, jitter=jitter,
+                                                want_L=False, want_alpha=False)
+                        val = -float(lml[0])
+                    except _lib.DmoError:  # not positive definite at this theta: what sklearn maps to -inf likelihood
+                        val = np.inf
+                    return val, None
+
+                if callable(optf):
+                    theta, _ = optf(obj_func, theta, kernel.bounds)
+                else:  # "fmin_l_bfgs_b" has no gradient here: bounded derivative-free search instead
+                    from scipy.optimize import minimize
+
+                    res = minimize(lambda th: obj_func(th)[0], theta, method="Powell", bounds=kernel.bounds, options={"xtol": 1e-3, "ftol": 1e-6})
+                    theta = res.x
+            thetas.append(np.asarray(theta, dtype=np.float64))
+        cs, lss, nzs = zip(*[unpack(t) for t in thetas])
+        L, alpha, lml = _lib.gp_fit(x, yn, list(cs), [np.broadcast_to(ls, (d,)) for ls in lss], list(nzs), kernel=self._kernel_code, jitter=jitter)
+        smlist = []
+        for i in range(M):
+            gpr = GaussianProcessRegressor(kernel=kernel, optimizer=None, normalize_y=True)
+            gpr.kernel_ = kernel.clone_with_theta(thetas[i])
+            gpr.X_train_, gpr.y_train_ = x, yn[i]
+            gpr._y_train_mean, gpr._y_train_std = y_mean[i], y_std[i]
+            gpr.alpha_, gpr.L_ = alpha[i], L[i]
+            gpr.log_marginal_likelihood_value_ = float(lml[i])
+            gpr.n_features_in_ = d
+            gpr._rng = None
+            smlist.append(gpr)
+        return smlist
 
     def _upload(self):
         """Posterior state of every objective -> HBM (dmo_gp_create), once per epoch."""

@@ -184,6 +184,25 @@ def mutate_groups(pop_x, group_size, n_groups, per_group, di_mutation, xlb, xub,
     return (out, pi) if return_parents else out
 
 
+def gp_fit(X_train, y, constant, length_scale, noise, kernel=0, jitter=1e-10, want_L=True, want_alpha=True):
+    """dmo_gp_fit on the CPU: kernel matrix, Cholesky, alpha, log marginal likelihood per objective (oracle/gp.py)."""
+    from scipy.linalg import cho_solve, cholesky
+
+    X = np.asarray(X_train, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    M, N = y.shape
+    Ls, als, lml = [], [], np.empty(M)
+    for m in range(M):
+        K = constant[m] * gp.kernel_matrix(X, X, np.asarray(length_scale[m], dtype=np.float64), kernel)
+        K[np.diag_indices_from(K)] += noise[m] + jitter
+        Lm = cholesky(K, lower=True, check_finite=False)
+        a = cho_solve((Lm, True), y[m], check_finite=False)
+        lml[m] = -0.5 * y[m] @ a - np.log(np.diag(Lm)).sum() - 0.5 * N * np.log(2 * np.pi)
+        Ls.append(Lm)
+        als.append(a)
+    return (np.stack(Ls) if want_L else None), (np.stack(als) if want_alpha else None), lml
+
+
 class ResidentRows:
     """NumPy-backed stand-in for _lib.ResidentRows (same surface: shape, __array__, indexing, copy)."""
 
@@ -241,7 +260,7 @@ SmpsoSwarms = None  # the CPU seam exercises the per-swarm host path of the SMPS
 
 FUNCTIONS = ["rank_nd", "crowding_distance", "euclidean_distance", "order_mo", "remove_worst", "remove_worst_pair", "tournament", "mutation_u", "sbx_u",
              "nsga2_generate", "GPHandle", "hypervolume", "ehvi_select", "get_duplicates", "age_survival", "smpso_velocity", "mutate_groups",
-             "cmaes_sample", "cmaes_update_cholesky", "ResidentRows", "resident_rows", "gather_rows", "identity_rows", "SmpsoSwarms"]
+             "cmaes_sample", "cmaes_update_cholesky", "ResidentRows", "resident_rows", "gather_rows", "identity_rows", "SmpsoSwarms", "gp_fit"]
 
 
 def install(monkeypatch):

@@ -925,3 +925,87 @@ def test_benchmark_functions_on_gpu(L):
     np.testing.assert_allclose(bm.wfg4(X, 4), ob.wfg4(X, 4), rtol=1e-12)
     np.testing.assert_allclose(bm.dtlz7(X[:, :22], 5), ob.dtlz7(X[:, :22], 5), rtol=1e-12)
     np.testing.assert_allclose(bm.dtlz2(X[:, :12], 3), ob.dtlz2(X[:, :12], 3), rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ N1: exact-GP fit on the GPU
+@pytest.mark.parametrize("N,d,M,kind", [(50, 4, 2, "matern"), (64, 6, 1, "rbf"), (700, 12, 3, "matern"), (2048, 30, 3, "matern")])
+def test_gp_fit_vs_scipy_cholesky(L, N, d, M, kind):
+    """dmo_gp_fit (kernel matrix, blocked float64 Cholesky, alpha, log marginal likelihood) against the oracle's fit
+    (scipy cholesky / cho_solve, the arithmetic of GaussianProcessRegressor.fit) for the same hyper-parameters."""
+    rng = np.random.default_rng(N + d)
+    X = rng.random((N, d))
+    Y = np.column_stack([np.sin(3 * X[:, :3].sum(axis=1) + k) + X[:, (3 + k) % d] ** 2 for k in range(M)])
+    code = L.KERNEL_MATERN52 if kind == "matern" else L.KERNEL_RBF
+    cs, nz = np.linspace(0.7, 2.0, M), np.full(M, 1e-6 if kind == "matern" else 1e-5)
+    ls = [np.full(d, 0.5 + 0.3 * m) for m in range(M)]
+    st = gp.fit_fixed(X, Y, np.zeros(d), np.ones(d), list(cs), [float(v[0]) for v in ls], list(nz), kind=gp.MATERN52 if kind == "matern" else gp.RBF)
+    yn = np.stack([(Y[:, m] - o.y_mean) / o.y_std for m, o in enumerate(st.objectives)])
+    Lg, ag, lml = L.gp_fit(X, yn, cs, ls, nz, kernel=code)
+    for m, o in enumerate(st.objectives):
+        assert np.max(np.abs(Lg[m] - o.L)) <= 1e-9 * np.max(np.abs(o.L)), m
+        assert np.max(np.abs(ag[m] - o.alpha)) <= 1e-6 * np.max(np.abs(o.alpha)), m
+        lml_ref = -0.5 * yn[m] @ o.alpha - np.log(np.diag(o.L)).sum() - 0.5 * N * np.log(2 * np.pi)
+        assert abs(lml[m] - lml_ref) <= 1e-8 * abs(lml_ref), (m, lml[m], lml_ref)
+    # likelihood only (what a hyper-parameter search trial asks for)
+    _, _, lml2 = L.gp_fit(X, yn, cs, ls, nz, kernel=code, want_L=False, want_alpha=False)
+    assert np.array_equal(lml, lml2)
+
+
+def test_gp_fit_reports_a_matrix_that_is_not_positive_definite(L):
+    X = np.vstack([np.full((1, 3), 0.5)] * 5)  # five identical points, no noise: K is singular
+    with pytest.raises(L.DmoError, match="positive definite"):
+        L.gp_fit(X, np.zeros((1, 5)), [1.0], [np.full(3, 0.5)], [0.0], jitter=0.0)
+
+
+def test_gpr_plugin_fit_on_gpu_equals_sklearn_fit(L):
+    """GPR_Matern(fit="gpu") -- the default -- against fit="sklearn" (scikit-learn's own fit on the host): same theta (fixed),
+    same posterior to 1e-8, and scikit-learn's own predict on the GPU-fitted state agrees with the GPU predict."""
+    import dmosopt_b200 as b2
+
+    rng = np.random.default_rng(12)
+    N, d, M = 900, 10, 2
+    X = rng.random((N, d))
+    Y = np.column_stack((np.sin(4 * X[:, 0]) + X[:, 1:].sum(axis=1), np.cos(3 * X[:, 1]) * (1 + X[:, 2])))
+    xlb, xub = np.zeros(d), np.ones(d)
+    a = b2.GPR_Matern(X, Y, d, M, xlb, xub, optimizer=None)  # fit="gpu"
+    b = b2.GPR_Matern(X, Y, d, M, xlb, xub, optimizer=None, fit="sklearn")
+    Xt = rng.random((500, d))
+    ma, va = a.predict(Xt)
+    mb, vb = b.predict(Xt)
+    ystd = np.array([np.ravel(g_._y_train_std)[0] for g_ in b.smlist])
+    assert np.max(np.abs(ma - mb) / np.maximum(np.abs(mb), ystd)) < 1e-8
+    assert np.max(np.abs(va - vb) / (ystd**2)) < 1e-8
+    sk = np.column_stack([g_.predict(Xt) for g_ in a.smlist])  # scikit-learn's predict on the state fitted by dmo_gp_fit
+    assert np.max(np.abs(sk - ma) / np.maximum(np.abs(sk), ystd)) < 1e-5
+    for ga, gb in zip(a.smlist, b.smlist):
+        assert abs(ga.log_marginal_likelihood_value_ - gb.log_marginal_likelihood_value_) <= 1e-8 * abs(gb.log_marginal_likelihood_value_)
+
+
+def test_gpr_plugin_hyperparameter_search_on_gpu(L):
+    """optimizer != None with fit="gpu": the search (the reference's SCE-UA when baseline/_ref is shipped, SciPy's bounded
+    Powell otherwise) evaluates -log marginal likelihood through dmo_gp_fit and must not end below the initial theta."""
+    import os
+    import sys
+
+    import dmosopt_b200 as b2
+
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    added = os.path.isdir(os.path.join(ref, "dmosopt")) and ref not in sys.path
+    if added:
+        sys.path.insert(0, ref)
+    try:
+        rng = np.random.default_rng(4)
+        N, d = 120, 3
+        X = rng.random((N, d))
+        Y = (np.sin(6 * X[:, 0]) + 0.5 * X[:, 1] + 0.01 * rng.standard_normal(N))[:, None]
+        fixed = b2.GPR_Matern(X, Y, d, 1, np.zeros(d), np.ones(d), optimizer=None)
+        tuned = b2.GPR_Matern(X, Y, d, 1, np.zeros(d), np.ones(d), optimizer="sceua", seed=3)
+        l0, l1 = fixed.smlist[0].log_marginal_likelihood_value_, tuned.smlist[0].log_marginal_likelihood_value_
+        print("lml fixed", l0, "tuned", l1, "theta", np.exp(tuned.smlist[0].kernel_.theta))
+        assert l1 >= l0 - 1e-9
+        Xt = rng.random((200, d))
+        truth = np.sin(6 * Xt[:, 0]) + 0.5 * Xt[:, 1]
+        assert np.sqrt(np.mean((tuned.evaluate(Xt)[:, 0] - truth) ** 2)) < 0.1
+    finally:
+        if added:
+            sys.path.remove(ref)
