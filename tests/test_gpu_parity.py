@@ -713,7 +713,7 @@ def test_hv3_tree_equals_the_sweep_kernel_and_the_oracle(L, n, kind):
         finally:
             del os.environ["DMO_HV3_TREE"]
     assert abs(vals["1"] - vals["0"]) <= 1e-12 * vals["0"], (vals, n, kind)
-    if n <= 5000:
+    if n <= 1100:  # the CPU oracle is O(n^2) Python
         exp = hv.hypervolume(F, ref)
         assert abs(vals["1"] - exp) <= 1e-11 * exp
     # the ranked entry point feeds dominated rows straight into the kernel: same value
