@@ -222,8 +222,10 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
   for (int x = 0; x < 8; ++x) vsum[x] = 0.0;
 
+  // row blocks of L^-1 are dealt round-robin over gridDim.z CTAs per candidate tile (small candidate sets -- AUTO's probe
+  // and refinement calls -- would otherwise run on a handful of SMs); partial sums are combined in a fixed order
   const int64_t ntile = Npad / VB;
-  for (int64_t it = 0; it < ntile; ++it) {
+  for (int64_t it = blockIdx.z; it < ntile; it += gridDim.z) {
     const int64_t i0 = it * VB;
     const int64_t nk = (i0 + VB) / VK;  // L^-1 is lower triangular: row block `it` only touches k < i0 + VB
     double acc[8][8];
@@ -306,18 +308,20 @@ __global__ void __launch_bounds__(256, 1)
     double s = 0.0;
 #pragma unroll
     for (int r = 0; r < 16; ++r) s += red[r * VB + tid];
-    vnorm[(int64_t)m * Pcpad + p0 + tid] = s;
+    vnorm[((int64_t)blockIdx.z * gridDim.y + m) * Pcpad + p0 + tid] = s;
   }
 }
 
-__global__ void var_finish_kernel(const double* __restrict__ vnorm, int64_t Pc, int64_t Pcpad, int M,
+__global__ void var_finish_kernel(const double* __restrict__ vnorm, int nplanes, int64_t Pc, int64_t Pcpad, int M,
                                   const double* __restrict__ constant, const double* __restrict__ noise,
                                   const double* __restrict__ ystd, int64_t p_base, double* __restrict__ var) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= Pc * M) return;
   int64_t pl = t / M;
   int m = (int)(t - pl * M);
-  double v = (constant[m] + noise[m]) - vnorm[(int64_t)m * Pcpad + pl];  // kernel_.diag(X) - einsum(V^2)
+  double vn = 0.0;
+  for (int z = 0; z < nplanes; ++z) vn += vnorm[((int64_t)z * M + m) * Pcpad + pl];  // row-block groups, fixed order
+  double v = (constant[m] + noise[m]) - vn;  // kernel_.diag(X) - einsum(V^2)
   if (v < 0.0) v = 0.0;                                                  // sklearn clamps negative variances
   double sd = sqrt(v * (ystd[m] * ystd[m]));                             // sklearn returns the std ...
   var[(p_base + pl) * M + m] = sd * sd;                                  // ... dmosopt squares it (model.py:1267)
@@ -334,9 +338,14 @@ int gp_predict_fp64(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, doub
   Pc_max = (Pc_max / VB) * VB;
   if (Pc_max < VB) Pc_max = VB;
   const int64_t Pc_alloc = P < Pc_max ? ceil_div(P, VB) * VB : Pc_max;
+  // split the row blocks of L^-1 over gridDim.z so that at least ~2 CTAs per SM exist even for a few hundred candidates
+  const int64_t ntile = Npad / VB;
+  int64_t nsplit = ceil_div((int64_t)2 * ctx->sm_count, (Pc_alloc / VB) * M);
+  if (nsplit > ntile) nsplit = ntile;
+  if (nsplit < 1) nsplit = 1;
   DevBuf<double> Ks, vnorm;
   DMO_TRY(Ks.alloc(ctx, (size_t)M * Pc_alloc * Npad));
-  DMO_TRY(vnorm.alloc(ctx, (size_t)M * Pc_alloc));
+  DMO_TRY(vnorm.alloc(ctx, (size_t)nsplit * M * Pc_alloc));
   const int64_t kplane = Pc_alloc * Npad;
   for (int64_t p_base = 0; p_base < P; p_base += Pc_alloc) {
     const int64_t Pc = (P - p_base) < Pc_alloc ? (P - p_base) : Pc_alloc;
@@ -359,11 +368,11 @@ int gp_predict_fp64(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, doub
     }
     if (d_var) {
       ProfileScope ps(ctx, "gp_var");
-      dim3 gv((unsigned)(Pcpad / VB), (unsigned)M);
+      dim3 gv((unsigned)(Pcpad / VB), (unsigned)M, (unsigned)nsplit);
       DMO_CUDA(cudaFuncSetAttribute(var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VAR_SMEM));
       DMO_LAUNCH(var_kernel, gv, 256, VAR_SMEM, gp->Linv.p, Npad, Npad * Npad, Ks.p, Npad, kplane, Npad, vnorm.p, Pc_alloc);
-      DMO_LAUNCH(var_finish_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, Pc, Pc_alloc, M, gp->constant.p,
-                 gp->noise.p, gp->ystd.p, p_base, d_var);
+      DMO_LAUNCH(var_finish_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, (int)nsplit, Pc, Pc_alloc, M,
+                 gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
     }
   }
   DMO_CHECK_LAUNCH();
