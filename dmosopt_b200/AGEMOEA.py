@@ -171,7 +171,7 @@ class AGEMOEA(MOEA):
         logger=None,
         **kwargs,
     ):
-        super().__init__(name="AGEMOEA", popsize=popsize, nInput=nInput, nOutput=nOutput, **kwargs)
+        super().__init__(name="AGEMOEA", popsize=popsize, nInput=nInput, nOutput=nOutput, optimize_mean_variance=optimize_mean_variance, **kwargs)
         self.model = model
         self.logger = logger
         self.feasibility_model = feasibility_model

@@ -47,7 +47,7 @@ class CMAES(MOEA):
         optimize_mean_variance: bool = False,
         **kwargs,
     ):
-        super().__init__(name="CMAES", popsize=popsize, nInput=nInput, nOutput=nOutput, **kwargs)
+        super().__init__(name="CMAES", popsize=popsize, nInput=nInput, nOutput=nOutput, optimize_mean_variance=optimize_mean_variance, **kwargs)
         self.model = model
         self.x_distance_metrics = None
         if getattr(self.model, "feasibility", None) is not None:

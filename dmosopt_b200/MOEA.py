@@ -32,6 +32,8 @@ def euclidean_distance_metric(Y):
     return _lib.euclidean_distance(Y)
 
 
+MAX_OBJECTIVES = 8  # dmo_rank_nd / dmo_crowding_distance (exact hypervolume: 5, _lib.HV_MAX_OBJECTIVES)
+
 _METRIC_CODES = {None: _lib.METRIC_NONE, "crowding": _lib.METRIC_CROWDING, "euclidean": _lib.METRIC_EUCLIDEAN}
 
 
@@ -83,6 +85,7 @@ class MOEA(object):
     """Base class of the B200 optimizer plugins; same contract as dmosopt.MOEA.MOEA (MOEA.py:55-188)."""
 
     def __init__(self, name: str, popsize: int, nInput: int, nOutput: int, **kwargs):
+        doubled = bool(kwargs.pop("optimize_mean_variance", False))  # not an optimizer parameter: only sizes the check below
         self.name = name
         self.popsize = popsize
         self.nInput = nInput
@@ -103,6 +106,12 @@ class MOEA(object):
                 self.opt_params[k] = v
         self.local_random = None
         self.state = None
+        # limits of the kernels, checked before an epoch starts rather than at the first sortMO (csrc/rank.cu, sortmo.cu:
+        # records and per-objective tables are sized for at most 8 objectives; optimize_mean_variance doubles the count)
+        n_sorted = nOutput * (2 if doubled else 1)
+        if n_sorted > MAX_OBJECTIVES:
+            raise ValueError(f"dmosopt_b200.{name}: {n_sorted} objectives to sort (nOutput={nOutput}"
+                             f"{', doubled by optimize_mean_variance' if n_sorted != nOutput else ''}); the rank / crowding kernels take at most {MAX_OBJECTIVES}")
 
     @property
     def default_parameters(self) -> Dict[str, Any]:

@@ -45,7 +45,7 @@ class NSGA2(MOEA):
         optimize_mean_variance: bool = False,
         **kwargs,
     ):
-        super().__init__(name="NSGA2", popsize=popsize, nInput=nInput, nOutput=nOutput, **kwargs)
+        super().__init__(name="NSGA2", popsize=popsize, nInput=nInput, nOutput=nOutput, optimize_mean_variance=optimize_mean_variance, **kwargs)
         self.model = model
         self.distance_metric = distance_metric
         self.optimize_mean_variance = optimize_mean_variance

@@ -62,7 +62,7 @@ class SMPSO(MOEA):
     ):
         swarm_size = kwargs.get("swarm_size", self.default_parameters["swarm_size"])
         kwargs["initial_size"] = popsize * swarm_size  # SMPSO.py:36
-        super().__init__(name="SMPSO", popsize=popsize, nInput=nInput, nOutput=nOutput, **kwargs)
+        super().__init__(name="SMPSO", popsize=popsize, nInput=nInput, nOutput=nOutput, optimize_mean_variance=optimize_mean_variance, **kwargs)
         self.pop_slices = [range(p * popsize, (p + 1) * popsize) for p in range(swarm_size)]
         self.model = model
         self.distance_metric = distance_metric

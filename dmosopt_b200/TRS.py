@@ -71,7 +71,7 @@ class TrState:
 class TRS(MOEA):
     def __init__(self, popsize: int, nInput: int, nOutput: int, model: Optional[Any], optimize_mean_variance: bool = False, **kwargs):
         kwargs.pop("distance_metric", None)  # MOASMO.epoch passes distance_metric=None to every optimizer (MOASMO.py:365-373)
-        super().__init__(name="TRS", popsize=popsize, nInput=nInput, nOutput=nOutput, **kwargs)
+        super().__init__(name="TRS", popsize=popsize, nInput=nInput, nOutput=nOutput, optimize_mean_variance=optimize_mean_variance, **kwargs)
         self.model = model
         self.x_distance_metrics = None
         if getattr(self.model, "feasibility", None) is not None:
