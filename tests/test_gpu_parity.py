@@ -1009,3 +1009,83 @@ def test_gpr_plugin_hyperparameter_search_on_gpu(L):
     finally:
         if added:
             sys.path.remove(ref)
+
+
+# ------------------------------------------------------------------------------------------ round-2 regressions
+@pytest.mark.parametrize("pc,pm", [(0.0, 0.1), (0.05, 0.02), (0.0, 1.0), (0.9, 0.1)])
+def test_variation_loop_terminates_for_any_rates(L, pc, pm):
+    """The reference loops until enough children exist whatever the probabilities (NSGA2.py:142); the parallel plan is sized
+    from them (dmo_nsga2_plan_length), so mutation-only and low-rate configurations finish too."""
+    rng = np.random.default_rng(3)
+    pop, d = 1500, 6
+    x = rng.random((pop, d))
+    pool = rng.permutation(pop)[: pop // 2]
+    T = int(L.load_library().dmo_nsga2_plan_length(pop, pc, pm))
+    assert T >= 2 * pop + 64
+    x_gen, kind, draws = L.nsga2_generate(x, pool, pop, pc, pm, 1.0 / d, np.ones(d), np.full(d, 20.0), np.zeros(d), np.ones(d), 7, 1, return_draws=True)
+    assert pop - 1 <= x_gen.shape[0] <= pop + 1 and draws["u_cross"].shape == (T,)
+    if pc == 0.0:
+        assert np.all(kind == 2)
+    # replay of the kernel's own draws on the oracle: same offspring
+    xo, cidx, midx = nsga2.generate_given_draws(x[pool], draws["u_cross"], draws["u_mut"], draws["pair"], draws["single"], draws["u_genes"], pop, np.ones(d),
+                                                np.full(d, 20.0), np.zeros(d), np.ones(d), 1.0 / d, crossover_prob=pc, mutation_prob=pm)
+    assert xo.shape == x_gen.shape and np.max(np.abs(xo - np.asarray(x_gen))) < 1e-13
+    assert np.array_equal(np.flatnonzero(kind < 2), cidx) and np.array_equal(np.flatnonzero(kind == 2), midx)
+
+
+def test_offspring_mirror_is_released_after_update(L):
+    """Each generate() hands out a page-locked offspring matrix with a device mirror; update() consumes it and drops the HBM
+    copy, so a caller that keeps every x_gen of an epoch (MOASMO.optimize's history) does not pin one device buffer per
+    generation."""
+    import dmosopt_b200 as b2
+
+    rng = np.random.default_rng(1)
+    d, M, pop = 5, 2, 512
+    opt = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=b2.Model(), distance_metric=None)
+    x0 = rng.random((pop, d))
+    f = lambda x: np.column_stack((x[:, 0], 1 + x[:, 1:].sum(axis=1) - x[:, 0]))  # noqa: E731
+    opt.initialize_strategy(x0, f(x0).astype(np.float32), np.column_stack((np.zeros(d), np.ones(d))), rng)
+    kept = []
+    for _ in range(4):
+        x_gen, st = opt.generate()
+        assert L.mirror_ptr(x_gen) is not None
+        opt.update(x_gen, f(np.asarray(x_gen)), st)
+        assert L.mirror_ptr(x_gen) is None  # released
+        kept.append(x_gen)
+    assert all(np.all(np.isfinite(k)) for k in kept)  # the host arrays stay valid
+
+
+def test_two_set_duplicates_edge_cases(L):
+    rng = np.random.default_rng(2)
+    X = rng.random((40, 3))
+    assert not L.get_duplicates(X, Y=np.zeros((0, 3))).any()
+    Y = X.copy()  # identical sets: row i is a duplicate iff some EARLIER row j < i equals it -> none (rows are distinct)
+    assert not L.get_duplicates(X, Y=Y).any()
+    Y[0] = X[5]
+    assert np.array_equal(np.flatnonzero(L.get_duplicates(X, Y=Y)), [5])
+
+
+def test_smpso_resident_small_swarm_and_f64_offspring(L):
+    """Resident SMPSO against the per-swarm host path of the same plugin (the CPU seam's path): same state after an update
+    fed with the float64 offspring MOASMO hands over (np.clip of the float32 x_gen, MOEA.py:155)."""
+    import dmosopt_b200 as b2
+
+    d, M, pop = 4, 3, 37
+    bounds = np.column_stack((np.zeros(d), np.ones(d)))
+    f = lambda x: np.column_stack((x[:, 0] + 0.1 * x[:, 3], (1 - x[:, 0]) * (1 + x[:, 1]), x[:, 2] ** 2 + 0.3 * x[:, 1]))  # noqa: E731
+    x0 = np.random.default_rng(5).random((5 * pop, d))
+    states = []
+    for resident in (True, False):
+        opt = b2.SMPSO(popsize=pop, nInput=d, nOutput=M, model=b2.Model(), distance_metric=None)
+        opt.initialize_strategy(x0.copy(), f(x0).astype(np.float32), bounds, np.random.default_rng(9))
+        if not resident:
+            opt._resident = lambda: None
+        for g in range(2):
+            x_gen, st = opt.generate()
+            assert x_gen.dtype == np.float64 and x_gen.shape == (10 * pop, d)
+            opt.local_random = np.random.default_rng(100 + g)
+            opt.update(x_gen, f(np.asarray(x_gen)), st)
+        states.append((opt.state.population_parm.copy(), opt.state.population_obj.copy(), opt.state.velocity.copy(), np.stack(opt.state.ranks),
+                       opt.state.successful_children))
+    for a, b in zip(*states):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
