@@ -26,27 +26,48 @@ __device__ __forceinline__ double stationary_fit(double s2, int kind) {
   return exp(-0.5 * s2);
 }
 
-// lower triangle (and diagonal) of K, row-major with leading dimension ld; the strict upper triangle is zeroed
-__global__ void kernel_matrix_kernel(const double* __restrict__ X, int64_t N, int d, int kind, const double* __restrict__ inv_ls,
-                                     double constant, double diag_add, int64_t ld, double* __restrict__ K) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= ld || j >= ld) return;
-  double v = 0.0;
-  if (i < N && j < N) {
-    if (j <= i) {
-      double s = 0.0;
-      for (int c = 0; c < d; ++c) {
-        const double t = (X[i * d + c] - X[j * d + c]) * inv_ls[c];
-        s += t * t;
-      }
-      v = constant * stationary_fit(s, kind);
-      if (i == j) v += diag_add;
+// lower triangle (and diagonal) of K, row-major with leading dimension ld; the strict upper triangle is zeroed.
+// One CTA per 32 x 32 tile of K: the 64 rows of X it needs are staged in shared memory once (scaled by 1 / l), tiles
+// strictly above the diagonal only write zeros.
+__global__ void __launch_bounds__(256) kernel_matrix_kernel(const double* __restrict__ X, int64_t N, int d, int kind,
+                                                            const double* __restrict__ inv_ls, double constant, double diag_add,
+                                                            int64_t ld, double* __restrict__ K) {
+  extern __shared__ double xs[];  // [64][d + 1]: rows i0 .. i0+31 then j0 .. j0+31 of X, scaled
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+  const int dp = d + 1;
+  const bool upper = j0 > i0 + 31;
+  if (!upper) {
+    for (int t = threadIdx.x; t < 64 * d; t += 256) {
+      const int r = t / d, c = t - r * d;
+      const int64_t g = (r < 32 ? i0 + r : j0 + (r - 32));
+      xs[r * dp + c] = g < N ? X[g * d + c] * inv_ls[c] : 0.0;
     }
-  } else if (i == j) {
-    v = 1.0;  // identity tail of the padded matrix
   }
-  K[i * ld + j] = v;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int li = ty + 8 * u;
+    const int64_t i = i0 + li, j = j0 + tx;
+    if (i >= ld || j >= ld) continue;
+    double v = 0.0;
+    if (i < N && j < N) {
+      if (j <= i) {
+        const double* a = xs + li * dp;
+        const double* b = xs + (32 + tx) * dp;
+        double s = 0.0;
+        for (int c = 0; c < d; ++c) {
+          const double t = a[c] - b[c];
+          s += t * t;
+        }
+        v = constant * stationary_fit(s, kind);
+        if (i == j) v += diag_add;
+      }
+    } else if (i == j) {
+      v = 1.0;  // identity tail of the padded matrix
+    }
+    K[i * ld + j] = v;
+  }
 }
 
 // ---- Cholesky steps (A: lower triangle, in place, leading dimension ld, ld % CB == 0) ----------------------------------
@@ -266,7 +287,7 @@ int dmo_gp_fit(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const double* 
                const double* length_scale, const double* noise, double jitter, double* L_out, double* alpha_out, double* lml_out) {
   if (!ctx) return DMO_ERR_ARG;
   DMO_CUDA(cudaSetDevice(ctx->device));
-  DMO_REQUIRE(N >= 1 && d >= 1 && M >= 1 && X_train && y && constant && length_scale && noise, "gp_fit: bad arguments");
+  DMO_REQUIRE(N >= 1 && d >= 1 && d <= 90 && M >= 1 && X_train && y && constant && length_scale && noise, "gp_fit: bad arguments");
   DMO_REQUIRE(kernel == DMO_KERNEL_MATERN52 || kernel == DMO_KERNEL_RBF, "gp_fit: unknown kernel %d", kernel);
   DMO_REQUIRE(alpha_out || lml_out || L_out, "gp_fit: nothing to compute");
   std::vector<double> h_c(M), h_n(M), h_ls((size_t)M * d), h_inv((size_t)M * d);
@@ -296,8 +317,9 @@ int dmo_gp_fit(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const double* 
   DMO_CUDA(cudaFuncSetAttribute(syrk_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
   ProfileScope ps(ctx, "gp_fit");
   for (int m = 0; m < M; ++m) {
-    dim3 kb(32, 8), kg((unsigned)ceil_div(ld, 32), (unsigned)ceil_div(ld, 8));
-    DMO_LAUNCH(kernel_matrix_kernel, kg, kb, 0, ix.d, N, d, kernel, inv_ls.p + (size_t)m * d, h_c[m], h_n[m] + jitter, ld, A.p);
+    dim3 kg((unsigned)ceil_div(ld, 32), (unsigned)ceil_div(ld, 32));
+    DMO_LAUNCH(kernel_matrix_kernel, kg, 256, (size_t)64 * (d + 1) * sizeof(double), ix.d, N, d, kernel, inv_ls.p + (size_t)m * d, h_c[m],
+               h_n[m] + jitter, ld, A.p);
     for (int64_t k = 0; k < nb; ++k) {
       const int64_t k0 = k * CB;
       DMO_LAUNCH(potrf_diag_kernel, 1, 256, 0, A.p, ld, k0, info.p);

@@ -17,6 +17,19 @@ timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2g_benc
 timeout 600 python bench.py > gpurun_out/r2g_bench_default.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2g_smoke.log 2>&1
 tail -2 gpurun_out/r2g_smoke.log
+cat > /tmp/fit_probe.py <<'PY'
+import time, numpy as np, bench
+from dmosopt_b200 import _lib as L
+w = bench.workload(1024, 30, 3, 4096)
+x = (w["Xtr"] - w["xlb"]) / (w["xub"] - w["xlb"])
+yn = ((w["Ytr"] - w["Ytr"].mean(0)) / w["Ytr"].std(0)).T.copy()
+for _ in range(3):
+    t0 = time.time(); L.gp_fit(x, yn[:1], [1.0], [np.full(30, 0.5)], [1e-6], want_L=False, want_alpha=False); print("lml-only, 1 objective, N=4096: s", time.time() - t0, flush=True)
+PY
+timeout 300 python /tmp/fit_probe.py > gpurun_out/r2g_fit.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2g_fit_launches.csv python /tmp/fit_probe.py > /dev/null 2>&1
+python scripts/summarize_launches.py gpurun_out/r2g_fit_launches.csv > gpurun_out/r2g_fit_launches_summary.txt 2>&1
+cat gpurun_out/r2g_fit.log | tail -3; head -12 gpurun_out/r2g_fit_launches_summary.txt
 timeout 600 python scripts/config_sweep.py C2 C3 C4 C5 > gpurun_out/r2g_config_sweep.log 2>&1
 cat gpurun_out/r2g_config_sweep.log | tail -8
 for f in gpurun_out/r2g_bench.log gpurun_out/r2g_bench_default.log; do tail -1 $f | cut -c1-900; done
