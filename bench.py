@@ -161,14 +161,19 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arms
 def use_all_host_threads():
-    """BLAS / OpenMP pools to every host core (torchrun exports OMP_NUM_THREADS=1); returns the thread count in use."""
+    """BLAS / OpenMP pools to every host core (torchrun exports OMP_NUM_THREADS=1).  Returns the thread count of the BLAS
+    pool NumPy / SciPy compute with (the only multi-threaded part of the reference path; the OpenBLAS build in this image
+    stops at 64 threads) -- the same number whether or not torch's own pools are loaded in the process."""
     n = os.cpu_count() or 1
     try:
         import threadpoolctl
 
         threadpoolctl.threadpool_limits(limits=n)
-        got = [p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()]
-        return int(max(got)) if got else n
+        info = threadpoolctl.threadpool_info()
+        blas = [p.get("num_threads", 1) for p in info if p.get("user_api") == "blas" and "numpy" in str(p.get("filepath", "")) + str(p.get("prefix", ""))]
+        if not blas:
+            blas = [p.get("num_threads", 1) for p in info if p.get("user_api") == "blas"]
+        return int(min(blas)) if blas else n
     except Exception:
         return n
 

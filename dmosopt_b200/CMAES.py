@@ -109,8 +109,10 @@ class CMAES(MOEA):
         mid_front = None
         full = False
         chosen_count = 0
+        by_rank = np.argsort(rank, kind="stable")  # indices grouped by rank, ascending inside a front: np.argwhere(rank == r)
+        bounds_r = np.searchsorted(rank[by_rank], np.arange(int(np.max(rank)) + 2))
         for r in range(int(np.max(rank)) + 1):
-            front_r = order_inv[np.argwhere(rank == r).ravel()]  # (sic) the reference maps fronts through order_inv (:190)
+            front_r = order_inv[by_rank[bounds_r[r] : bounds_r[r + 1]]]  # (sic) the reference maps fronts through order_inv (:190)
             if chosen_count + len(front_r) <= popsize and not full:
                 chosen[front_r] = True
                 chosen_count += len(front_r)
@@ -142,14 +144,9 @@ class CMAES(MOEA):
         dim, mu, lambda_ = self.nInput, self.opt_params.mu, self.opt_params.lambda_
         arz = rng.normal(size=(lambda_ * mu, dim))
         order, rank = sortMO(st.parents_x, st.parents_y, self.x_distance_metrics)
-        parent_selection, count = [], 0
-        for r in range(int(np.max(rank)) + 1):
-            front_r = np.argwhere(rank == r).ravel()
-            parent_selection.append(front_r)
-            count += len(front_r)
-            if count >= mu:
-                break
-        parent_selection = np.concatenate(parent_selection)[:mu]
+        # fronts in rank order until at least mu parents are collected (CMAES.py:249-258) == the first mu indices of a
+        # stable sort by rank
+        parent_selection = np.argsort(rank, kind="stable")[:mu]
         js = rng.choice(len(parent_selection), size=lambda_ * mu)
         p_idx = parent_selection[js]
         individuals = _lib.cmaes_sample(st.parents_x, st.sigmas, st.A, p_idx, arz)

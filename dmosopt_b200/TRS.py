@@ -158,8 +158,9 @@ class TRS(MOEA):
         mid_front = None
         full = False
         chosen_count = 0
+        bounds_r = np.searchsorted(rank, np.arange(int(np.max(rank)) + 2))  # rank is ascending here (orderMO returns rank[perm])
         for r in range(int(np.max(rank)) + 1):
-            front_r = order_inv[np.argwhere(rank == r).ravel()]
+            front_r = order_inv[bounds_r[r] : bounds_r[r + 1]]  # order_inv[np.argwhere(rank == r)], TRS.py:226 (sic)
             if chosen_count + len(front_r) <= popsize and not full:
                 chosen[front_r] = True
                 chosen_count += len(front_r)
