@@ -33,6 +33,8 @@ def sortMO(x, y, x_distance_metrics=None):
                 idx = rank == front
                 dist[idx] = fn(x[idx, :])
             keys.append(-dist)
+    if not keys:  # np.lexsort((rank,)) is a stable sort by rank
+        return np.argsort(rank, kind="stable"), rank
     return np.lexsort(keys + [rank]), rank
 
 
@@ -103,7 +105,8 @@ class CMAES(MOEA):
         if n <= popsize:
             return np.ones(n, dtype=bool), np.zeros(n, dtype=bool), _lib.rank_nd(candidates_y)
         order, rank = sortMO(candidates_x, candidates_y, self.x_distance_metrics)
-        order_inv = np.argsort(order)
+        order_inv = np.empty(n, dtype=np.intp)  # np.argsort(order): the inverse permutation
+        order_inv[order] = np.arange(n)
         chosen = np.zeros(n, dtype=bool)
         not_chosen = np.zeros(n, dtype=bool)
         mid_front = None

@@ -152,7 +152,8 @@ class TRS(MOEA):
             return np.ones(n, dtype=bool), np.zeros(n, dtype=bool), full_rank
         # NB orderMO returns rank[perm] (ranks in sorted order) and the reference indexes candidates with the positions of
         # ``rank == r`` in that array mapped through argsort(order) (TRS.py:213, 226): reproduced as written
-        order_inv = np.argsort(order)
+        order_inv = np.empty(n, dtype=np.intp)  # np.argsort(order): the inverse permutation
+        order_inv[order] = np.arange(n)
         chosen = np.zeros(n, dtype=bool)
         not_chosen = np.zeros(n, dtype=bool)
         mid_front = None

@@ -445,25 +445,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             mbar_wait(&full[stage], phase, abort_flag);
             tc_fence_after();
             const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES2);
-            // diagonal block of the lower-triangular L^-1 (the last 8 k-chunks of a row block): chunk c only meets rows
-            // >= 32 c of the block, the rows above hold exact zeros -- issue the MMA on the lower N = 256 - 32 c rows only
-            // (B descriptor advanced by 32 c rows = 4 c eight-row groups of 512 B, accumulator columns from 32 c on)
-            const int cdiag = kc - jt * (TN2 / TK2);
-            const uint32_t r0 = cdiag > 0 ? 32u * (uint32_t)cdiag : 0u;
-            const uint32_t idesc = (1u << 4) | (((uint32_t)(TN2 - r0) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            const uint64_t b_adv = (uint64_t)(((r0 >> 3) * 512u) >> 4);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const uint32_t d_tmem = tmem_base + h * TN2 + r0;
+              const uint32_t d_tmem = tmem_base + h * TN2;
               const uint32_t a_off = h * (128 * TK2 * 2);
               const uint64_t a_hi = make_sdesc64(sa + a_off), a_lo = make_sdesc64(sa + TILE_BYTES2 + a_off);
-              const uint64_t b_hi = make_sdesc64(sa + 2 * TILE_BYTES2) + b_adv, b_lo = make_sdesc64(sa + 3 * TILE_BYTES2) + b_adv;
+              const uint64_t b_hi = make_sdesc64(sa + 2 * TILE_BYTES2), b_lo = make_sdesc64(sa + 3 * TILE_BYTES2);
 #pragma unroll
               for (int ks = 0; ks < TK2 / UK; ++ks) {
                 const uint64_t adv = (uint64_t)((ks * UK * 2) >> 4);
-                tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (kc | ks) ? 1u : 0u);
-                tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kc | ks) ? 1u : 0u);
+                tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+                tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1u);
               }
             }
             tc_commit(&empty[stage]);

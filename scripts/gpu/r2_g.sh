@@ -18,7 +18,9 @@ timeout 600 python bench.py > gpurun_out/r2g_bench_default.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2g_smoke.log 2>&1
 tail -2 gpurun_out/r2g_smoke.log
 cat > /tmp/fit_probe.py <<'PY'
-import time, numpy as np, bench
+import sys, time, numpy as np
+sys.path.insert(0, '/root/repo')
+import bench
 from dmosopt_b200 import _lib as L
 w = bench.workload(1024, 30, 3, 4096)
 x = (w["Xtr"] - w["xlb"]) / (w["xub"] - w["xlb"])
