@@ -23,9 +23,15 @@ struct dmo_gp {
   DevBuf<uint16_t> Lhi, Llo;  // (M, Npad, Npad) fp16 split of the row-scaled L^-1
   DevBuf<float> Lscale;       // (M, Npad) 1 / (row scale * K_* scale), powers of two
   DevBuf<int> Kexp;           // (M,) K_* scaling exponents
+  // whitened targets z = L^-1 y_n = L' alpha (float), zero padded to Npad: with D = K_* L^-T the posterior mean is D z, so
+  // the variance contraction's epilogue delivers it from the accumulator it already reads (gp_tensor.cu)
+  DevBuf<float> Zf;           // (M, Npad); empty when the model was created from L^-1 (factor_is_inverse)
+  bool z_ready = false;
+  bool mean_from_d = false;   // chosen by the AUTO calibration: mean from the contraction instead of the K_* alpha pass
   // DMO_GP_AUTO: per-model calibration of the tensor path against the float64 path on probe candidates (gp.cu)
   bool calibrated = false;
-  bool auto_mean_tensor = false;  // fp32-K_* mean holds 1e-5 on the probes (with margin)
+  bool auto_mean_tensor = false;  // a tensor-path mean (K_* alpha pass or D z) holds 1e-5 on the probes (with margin)
+  double cal_mean_err_d = 0.0;    // probe error of the mean taken from the contraction (D z)
   bool auto_var_tensor = false;   // split-fp16 variance holds 1e-5 * prior on the probes (with margin)
   double cal_mean_err = 0.0;      // max |mean_t - mean_64| / max(|mean_64|, y_std) over the probes
   double cal_var_err = 0.0;       // max |var_t - var_64| / prior over the probes
@@ -34,4 +40,5 @@ struct dmo_gp {
 };
 
 int gp_predict_fp64(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var);
-int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var);
+// mean_from_d: take the mean from the variance contraction (needs d_var and gp->z_ready), else from the K_* alpha pass
+int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var, bool mean_from_d = false);

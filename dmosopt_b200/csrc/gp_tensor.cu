@@ -338,6 +338,8 @@ struct GemmParams3 {
   double* vnorm;  // [n_q][M][vn_ld]
   int64_t vn_ld;
   int* abort_flag;
+  const float* zf;        // [M][l_rows] whitened targets (nullptr: the mean is not taken from this contraction)
+  double* mnorm;          // [n_q][M][vn_ld] partial sums of D z
   const unsigned* ready;  // [n_pb] completion counters of the K_* producer (nullptr: K_* is complete at launch)
   unsigned ready_target;
   int dbg;  // DMO_GP_DBG bits (diagnostics): 1 = no proxy fence, 2 = no nanosleep in the wait loop
@@ -477,8 +479,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const int m = w / per_m, r = w - m * per_m;
       const int pb = r / prm.n_q, q = r - pb * prm.n_q;
       const float* isc = prm.inv_scale + (int64_t)m * prm.l_rows;
+      const float* zf = prm.zf ? prm.zf + (int64_t)m * prm.l_rows : nullptr;
       const int jhi = prm.n_jt - 1 - q;
-      double total0 = 0.0, total1 = 0.0;
+      double total0 = 0.0, total1 = 0.0, mtot0 = 0.0, mtot1 = 0.0;
       for (int s = 0; s < 2; ++s) {
         const int jt = s ? jhi : q;
         if (s && q == jhi) break;
@@ -495,12 +498,28 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           // four independent fp32 partial sums per sub-tile over 8 squares each, folded into float64 every 32 columns:
           // the rounding of the sum of squares stays at the 2^-24 * sqrt(8) level instead of growing with N
           float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f};
+          if (zf) {  // posterior mean = D z out of the same accumulator (z = L^-1 y_n): one more FMA per element
+            const float* zc = zf + jt * TN2 + c0;
+            float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float sv = __ldg(sc + e);
-            const float t0 = __uint_as_float(r0[e]) * sv, t1 = __uint_as_float(r1[e]) * sv;
-            p0[e & 3] = fmaf(t0, t0, p0[e & 3]);
-            p1[e & 3] = fmaf(t1, t1, p1[e & 3]);
+            for (int e = 0; e < 32; ++e) {
+              const float sv = __ldg(sc + e), zv = __ldg(zc + e);
+              const float t0 = __uint_as_float(r0[e]) * sv, t1 = __uint_as_float(r1[e]) * sv;
+              p0[e & 3] = fmaf(t0, t0, p0[e & 3]);
+              p1[e & 3] = fmaf(t1, t1, p1[e & 3]);
+              q0[e & 3] = fmaf(t0, zv, q0[e & 3]);
+              q1[e & 3] = fmaf(t1, zv, q1[e & 3]);
+            }
+            mtot0 += ((double)q0[0] + (double)q0[1]) + ((double)q0[2] + (double)q0[3]);
+            mtot1 += ((double)q1[0] + (double)q1[1]) + ((double)q1[2] + (double)q1[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float sv = __ldg(sc + e);
+              const float t0 = __uint_as_float(r0[e]) * sv, t1 = __uint_as_float(r1[e]) * sv;
+              p0[e & 3] = fmaf(t0, t0, p0[e & 3]);
+              p1[e & 3] = fmaf(t1, t1, p1[e & 3]);
+            }
           }
           total0 += ((double)p0[0] + (double)p0[1]) + ((double)p0[2] + (double)p0[3]);
           total1 += ((double)p1[0] + (double)p1[1]) + ((double)p1[2] + (double)p1[3]);
@@ -509,6 +528,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);
         acc_phase ^= 1u;
+      }
+      if (zf) {
+        double* mo = prm.mnorm + ((int64_t)q * prm.M + m) * prm.vn_ld + (int64_t)pb * TM2 + quarter * 32 + lane;
+        mo[0] = mtot0;
+        mo[128] = mtot1;
       }
       double* out = prm.vnorm + ((int64_t)q * prm.M + m) * prm.vn_ld + (int64_t)pb * TM2 + quarter * 32 + lane;
       out[0] = total0;
@@ -727,6 +751,19 @@ __global__ void mean_split_kernel(const uint16_t* __restrict__ Kh, const uint16_
   if (lane == 0) mean[(p_base + pl) * M + m] = ystd[m] * scalbn(s, -k_exp[m]) + ymean[m];
 }
 
+// mean[p][m] = y_std * sum over the work items' partial sums of D z + y_mean (fixed order)
+__global__ void mean_finish_tc_kernel(const double* __restrict__ mnorm, int nplanes, int64_t Pc, int64_t ld, int M,
+                                      const double* __restrict__ ymean, const double* __restrict__ ystd, int64_t p_base,
+                                      double* __restrict__ mean) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Pc * M) return;
+  int64_t pl = t / M;
+  int m = (int)(t - pl * M);
+  double s = 0.0;
+  for (int q = 0; q < nplanes; ++q) s += mnorm[((int64_t)q * M + m) * ld + pl];
+  mean[(p_base + pl) * M + m] = ystd[m] * s + ymean[m];
+}
+
 __global__ void var_finish_tc_kernel(const double* __restrict__ vnorm, int nplanes, int64_t Pc, int64_t ld, int M,
                                      const double* __restrict__ constant, const double* __restrict__ noise,
                                      const double* __restrict__ ystd, int64_t p_base, double* __restrict__ var) {
@@ -795,7 +832,7 @@ int prepare_tensor_state(dmo_ctx* ctx, dmo_gp* gp) {
 
 }  // namespace
 
-int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var) {
+int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var, bool mean_from_d) {
   const int64_t N = gp->N, Npad = gp->Npad;
   const int M = gp->M, d = gp->d;
   DMO_REQUIRE(M <= 16, "gp_predict(tensor): at most 16 objectives per model (got %d)", M);
@@ -814,6 +851,8 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   const bool overlap = version == 3 && getenv("DMO_GP_OVERLAP") && atoi(getenv("DMO_GP_OVERLAP"));
   const int dbg = getenv("DMO_GP_DBG") ? atoi(getenv("DMO_GP_DBG")) : 0;  // 4: event instead of flags, 8: mean after var
   const bool use_flags = overlap && !(dbg & 4);
+  // mean from the contraction (D z) instead of the K_* alpha pass: only with the variance, version 3 and a model created from L
+  mean_from_d = mean_from_d && d_var != nullptr && version == 3 && gp->z_ready;
   constexpr int64_t TMv = v2::TM2;
   // candidate chunk: K_* hi/lo (2 x M x Pc x Npad fp16) within ~6 GiB
   int64_t Pc_max = ((int64_t)6 << 30) / ((int64_t)M * Npad * 4);
@@ -831,6 +870,8 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   DMO_TRY(Kh.alloc(ctx, (size_t)M * Pc_alloc * Npad));
   DMO_TRY(Kl.alloc(ctx, (size_t)M * Pc_alloc * Npad));
   DMO_TRY(vnorm.alloc(ctx, (size_t)n_q * M * Pc_alloc));
+  DevBuf<double> mnorm;
+  if (mean_from_d) DMO_TRY(mnorm.alloc(ctx, (size_t)n_q * M * Pc_alloc));
   DMO_TRY(abort_flag.alloc(ctx, 1));
   DMO_TRY(ready.alloc(ctx, (size_t)n_chunks * n_pb_alloc));
   DMO_CUDA(cudaMemsetAsync(abort_flag.p, 0, sizeof(int), ctx->stream));
@@ -884,7 +925,7 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       DMO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->aux));
       DMO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0));
     }
-    if (!(dbg & 8)) {
+    if (!(dbg & 8) && !mean_from_d) {
       ProfileScope ps_(ctx, "gp_mean", ps);
       DMO_LAUNCH_ON(ps, mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane,
                     M, gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
@@ -902,6 +943,8 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       prm.vnorm = vnorm.p;
       prm.vn_ld = Pc_alloc;
       prm.abort_flag = abort_flag.p;
+      prm.zf = mean_from_d ? gp->Zf.p : nullptr;
+      prm.mnorm = mean_from_d ? mnorm.p : nullptr;
       prm.ready = use_flags ? rdy : nullptr;
       prm.dbg = dbg;
       prm.ready_target = 8u * gk.x;  // KT_TP = 32 candidates per producer block: 8 tile rows x gk.x column blocks per 256
@@ -913,6 +956,9 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       }
       DMO_LAUNCH(var_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, vnorm.p, n_q, Pc, Pc_alloc, M,
                  gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
+      if (mean_from_d)
+        DMO_LAUNCH(mean_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, mnorm.p, n_q, Pc, Pc_alloc, M, gp->ymean.p,
+                   gp->ystd.p, p_base, d_mean);
     } else if (d_var) {
       v2::GemmParams2 prm;
       prm.M = M;
@@ -948,7 +994,7 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
                  gp->constant.p, gp->noise.p, gp->ystd.p, p_base, d_var);
     }
     if (overlap) DMO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // mean (and K_*) of this chunk done
-    if (dbg & 8) {
+    if ((dbg & 8) && !mean_from_d) {
       ProfileScope ps_(ctx, "gp_mean");
       DMO_LAUNCH(mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane, M,
                  gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);

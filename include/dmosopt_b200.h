@@ -215,9 +215,10 @@ int dmo_gp_set_linear_mean(dmo_ctx* ctx, dmo_gp* gp, const double* weight, const
 int dmo_gp_predict(dmo_ctx* ctx, dmo_gp* gp, const double* X, int64_t P, double* mean,
                    double* var, int precision);
 /* What DMO_GP_AUTO decided for this model (runs the one-off calibration if it has not run yet):
- * both arithmetic paths predict 512 probe candidates; mean_tensor / var_tensor = 1 when the fp32-K_*
- * mean (error relative to max(|mean|, y_std)) / the tcgen05 variance (error relative to the prior
- * variance) stay within the margins documented in csrc/gp.cu; theta: rows whose tensor variance is
+ * both arithmetic paths predict 512 probe candidates; mean_tensor bit 0 = the fp32-K_* alpha pass is
+ * admitted (mean-only predicts), bit 1 = the mean is taken from the variance contraction (D z, predicts with
+ * variance); var_tensor = 1 when the tcgen05 variance is admitted; errors relative to max(|mean|, y_std) and to
+ * the prior variance, margins documented in csrc/gp.cu; theta: rows whose tensor variance is
  * below theta * prior are recomputed in float64; last_refined: rows the last AUTO predict recomputed
  * (= P when the whole call ran in float64).  Any output pointer may be NULL. */
 int dmo_gp_auto_info(dmo_ctx* ctx, dmo_gp* gp, int* mean_tensor, int* var_tensor, double* mean_err,
