@@ -112,7 +112,9 @@ class CMAES(MOEA):
         mid_front = None
         full = False
         chosen_count = 0
-        by_rank = np.argsort(rank, kind="stable")  # indices grouped by rank, ascending inside a front: np.argwhere(rank == r)
+        # indices grouped by rank, ascending inside a front (= np.argwhere(rank == r) front by front); without extra sort keys
+        # that is the order sortMO has just computed
+        by_rank = order if not self.x_distance_metrics else np.argsort(rank, kind="stable")
         bounds_r = np.searchsorted(rank[by_rank], np.arange(int(np.max(rank)) + 2))
         for r in range(int(np.max(rank)) + 1):
             front_r = order_inv[by_rank[bounds_r[r] : bounds_r[r + 1]]]  # (sic) the reference maps fronts through order_inv (:190)

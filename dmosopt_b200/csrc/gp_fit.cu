@@ -8,8 +8,9 @@
 // Float64 throughout (this is the parity anchor of the posterior: alpha and L feed dmo_gp_create).  Right-looking blocked
 // Cholesky with 64 x 64 blocks: per block column one diagonal factorisation (one CTA, shared memory), one panel solve
 // X L_kk' = A_ik (one CTA per block row, forward substitution per row) and one trailing update A_ij -= A_ik A_jk' over
-// the lower triangle (one CTA per 64 x 64 tile, 4 x 4 register blocking).  The triangular solves for alpha run as one CTA
-// sweeping the block columns (N^2 flops, latency bound, ~1 ms at N = 4096).
+// the lower triangle (one CTA per 64 x 64 tile, 4 x 4 register blocking).  The targets ride along as one extra ROW of the
+// matrix ([K y; y' big]): the factorisation then leaves z = L^-1 y in that row, so y' K^-1 y = z' z and the log marginal
+// likelihood need no separate forward solve; alpha = L^-T z is one backward sweep (one CTA, only when alpha is wanted).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -31,7 +32,7 @@ __device__ __forceinline__ double stationary_fit(double s2, int kind) {
 // strictly above the diagonal only write zeros.
 __global__ void __launch_bounds__(256) kernel_matrix_kernel(const double* __restrict__ X, int64_t N, int d, int kind,
                                                             const double* __restrict__ inv_ls, double constant, double diag_add,
-                                                            int64_t ld, double* __restrict__ K) {
+                                                            const double* __restrict__ y, int64_t ld, double* __restrict__ K) {
   extern __shared__ double xs[];  // [64][d + 1]: rows i0 .. i0+31 then j0 .. j0+31 of X, scaled
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
@@ -63,8 +64,10 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const double* __rest
         v = constant * stationary_fit(s, kind);
         if (i == j) v += diag_add;
       }
+    } else if (i == N && j < N) {
+      v = y[j];  // the augmented row: the factorisation turns it into z = L^-1 y
     } else if (i == j) {
-      v = 1.0;  // identity tail of the padded matrix
+      v = i == N ? 1e300 : 1.0;  // its diagonal only has to stay positive; identity tail of the padded matrix
     }
     K[i * ld + j] = v;
   }
@@ -80,19 +83,21 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
   }
   __syncthreads();
   for (int j = 0; j < CB; ++j) {
-    const double djj = a[j][j];
+    const double djj = a[j][j];  // every thread reads the pivot (written before the barrier that ended the previous column)
     if (!(djj > 0.0)) {
       if (tid == 0) atomicExch(info, (int)(k0 + j) + 1);  // not positive definite (numpy raises LinAlgError here)
       return;
     }
-    const double s = sqrt(djj);
-    __syncthreads();
-    if (tid == 0) a[j][j] = s;
-    if (tid > j && tid < CB) a[tid][j] = a[tid][j] / s;
+    const double s = sqrt(djj), rs = 1.0 / s;
+    double mine = 0.0;
+    if (tid > j && tid < CB) mine = a[tid][j] * rs;
+    __syncthreads();  // all pivot reads done
+    if (tid == j) a[j][j] = s;
+    if (tid > j && tid < CB) a[tid][j] = mine;
     __syncthreads();
     // trailing update of the block: a[r][c] -= a[r][j] a[c][j], j < c <= r
     for (int t = tid; t < CB * CB; t += 256) {
-      const int r = t / CB, c = t % CB;
+      const int r = t >> 6, c = t & 63;
       if (c > j && c <= r) a[r][c] -= a[r][j] * a[c][j];
     }
     __syncthreads();
@@ -110,6 +115,7 @@ __global__ void __launch_bounds__(CB) trsm_panel_kernel(double* __restrict__ A, 
   extern __shared__ double dyn_sm[];
   double (*l)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(dyn_sm);
   double (*x)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(dyn_sm + CB * (CB + 1));
+  __shared__ double linv[CB];
   const int r = threadIdx.x;
   const int64_t i0 = k0 + (int64_t)(blockIdx.x + 1) * CB;
   for (int c = 0; c < CB; ++c) {
@@ -117,12 +123,26 @@ __global__ void __launch_bounds__(CB) trsm_panel_kernel(double* __restrict__ A, 
     x[c][r] = A[(i0 + c) * ld + k0 + r];                  // x[row c][col r]
   }
   __syncthreads();
-  // row r: x_rj = (a_rj - sum_{t<j} x_rt L_jt) / L_jj
+  linv[r] = 1.0 / l[r][r];
+  // row r in registers (fully unrolled: static indices): x_rj = (a_rj - sum_{t<j} x_rt L_jt) / L_jj, L_kk broadcast from
+  // shared memory, two independent accumulation chains
+  double xr[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) xr[c] = x[r][c];
+  __syncthreads();
+#pragma unroll
   for (int j = 0; j < CB; ++j) {
-    double s = x[r][j];
-    for (int t = 0; t < j; ++t) s -= x[r][t] * l[j][t];
-    x[r][j] = s / l[j][j];
+    double s0 = xr[j], s1 = 0.0;
+#pragma unroll
+    for (int t = 0; t + 1 < j; t += 2) {
+      s0 = fma(-xr[t], l[j][t], s0);
+      s1 = fma(-xr[t + 1], l[j][t + 1], s1);
+    }
+    if (j & 1) s0 = fma(-xr[j - 1], l[j][j - 1], s0);
+    xr[j] = (s0 + s1) * linv[j];
   }
+#pragma unroll
+  for (int c = 0; c < CB; ++c) x[r][c] = xr[c];
   __syncthreads();
   for (int c = 0; c < CB; ++c) A[(i0 + c) * ld + k0 + r] = x[c][r];
 }
@@ -170,52 +190,20 @@ __global__ void __launch_bounds__(256) syrk_tile_kernel(double* __restrict__ A, 
     }
 }
 
-// ---- alpha = L^-T L^-1 y and the log marginal likelihood: one CTA ------------------------------------------------------
+// ---- log marginal likelihood from the augmented row, alpha = L^-T z by one backward sweep: one CTA ----------------------------
 constexpr int SV_T = 1024;
-__global__ void __launch_bounds__(SV_T) solve_alpha_kernel(const double* __restrict__ L, int64_t ld, int64_t N, const double* __restrict__ y,
-                                                           double* __restrict__ work, double* __restrict__ alpha, double* __restrict__ lml) {
+__global__ void __launch_bounds__(SV_T) finish_fit_kernel(const double* __restrict__ L, int64_t ld, int64_t N, double* __restrict__ work,
+                                                          double* __restrict__ alpha, double* __restrict__ lml, int want_alpha) {
   __shared__ double xs[CB];
   __shared__ double red[SV_T / 32];
   __shared__ double dl[CB][CB + 1];  // the current diagonal block of L
   const int tid = threadIdx.x;
-  const int64_t nb = (N + CB - 1) / CB;
-  for (int64_t i = tid; i < nb * CB; i += SV_T) work[i] = i < N ? y[i] : 0.0;
-  __syncthreads();
-  // forward: L z = y, block column by block column
-  for (int64_t b = 0; b < nb; ++b) {
-    const int64_t k0 = b * CB;
-    for (int e = tid; e < CB * CB; e += SV_T) dl[e / CB][e % CB] = L[(k0 + e / CB) * ld + k0 + e % CB];
-    __syncthreads();
-    if (tid < 32) {  // the diagonal block: one warp, column-oriented substitution (lane owns rows lane and lane + 32)
-      double z0 = work[k0 + tid], z1 = work[k0 + tid + 32];
-      for (int j = 0; j < CB; ++j) {
-        const double ljj = dl[j][j];
-        double zj = __shfl_sync(0xffffffffu, j < 32 ? z0 : z1, j & 31) / ljj;
-        if (tid == (j & 31)) {
-          if (j < 32) z0 = zj; else z1 = zj;
-        }
-        if (tid > j) z0 -= dl[tid][j] * zj;
-        if (tid + 32 > j) z1 -= dl[tid + 32][j] * zj;
-      }
-      xs[tid] = z0;
-      xs[tid + 32] = z1;
-      work[k0 + tid] = z0;
-      work[k0 + tid + 32] = z1;
-    }
-    __syncthreads();
-    for (int64_t i = k0 + CB + tid; i < nb * CB; i += SV_T) {  // rows below: subtract the block's contribution
-      const double* row = L + i * ld + k0;
-      double s = 0.0;
-#pragma unroll 8
-      for (int j = 0; j < CB; ++j) s += row[j] * xs[j];
-      work[i] -= s;
-    }
-    __syncthreads();
-  }
-  // y' K^-1 y = z' z ; sum log L_ii
+  const int64_t nb = ld / CB;
+  // z = row N of the factor; y' K^-1 y = z' z ; sum log L_ii over the N real rows
   double q = 0.0, ld_sum = 0.0;
   for (int64_t i = tid; i < N; i += SV_T) {
-    q += work[i] * work[i];
+    const double z = L[N * ld + i];
+    q += z * z;
     ld_sum += log(L[i * ld + i]);
   }
   q = warp_sum(q);
@@ -237,8 +225,11 @@ __global__ void __launch_bounds__(SV_T) solve_alpha_kernel(const double* __restr
     for (int w = 0; w < SV_T / 32; ++w) s += red[w];
     lml[0] = -0.5 * quad - s - 0.5 * (double)N * 1.8378770664093453;  // log(2 pi)
   }
+  if (!want_alpha) return;
+  // backward: L' alpha = z over the whole padded matrix with right-hand side (z, 0, 0, ...): the augmented row and the identity
+  // tail get alpha = 0 and drop out, the leading N x N block is solved exactly.  Block columns from the last to the first.
+  for (int64_t i = tid; i < ld; i += SV_T) work[i] = i < N ? L[N * ld + i] : 0.0;
   __syncthreads();
-  // backward: L' alpha = z, block columns from the last to the first (row i of L' is column i of L)
   for (int64_t b = nb - 1; b >= 0; --b) {
     const int64_t k0 = b * CB;
     for (int e = tid; e < CB * CB; e += SV_T) dl[e / CB][e % CB] = L[(k0 + e / CB) * ld + k0 + e % CB];
@@ -260,7 +251,7 @@ __global__ void __launch_bounds__(SV_T) solve_alpha_kernel(const double* __restr
       work[k0 + tid + 32] = a1;
     }
     __syncthreads();
-    // rows above: work[i] -= sum_j L[k0 + j][i] * x_j   (column i of the block row k0..k0+63: strided, but read once)
+    // rows above: work[i] -= sum_j L[k0 + j][i] * x_j   (column i of the block row k0..k0+63: coalesced over i)
     for (int64_t i = tid; i < k0; i += SV_T) {
       double s = 0.0;
 #pragma unroll 8
@@ -295,7 +286,7 @@ int dmo_gp_fit(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const double* 
   DMO_CUDA(cudaMemcpy(h_n.data(), noise, M * sizeof(double), cudaMemcpyDefault));
   DMO_CUDA(cudaMemcpy(h_ls.data(), length_scale, (size_t)M * d * sizeof(double), cudaMemcpyDefault));
   for (size_t t = 0; t < h_ls.size(); ++t) h_inv[t] = 1.0 / h_ls[t];
-  const int64_t nb = ceil_div(N, CB), ld = nb * CB;
+  const int64_t nb = ceil_div(N + 1, CB), ld = nb * CB;  // N rows of K + the row that carries the targets
   In<double> ix, iy;
   DMO_TRY(ix.init(ctx, X_train, (size_t)N * d));
   DMO_TRY(iy.init(ctx, y, (size_t)M * N));
@@ -319,7 +310,7 @@ int dmo_gp_fit(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const double* 
   for (int m = 0; m < M; ++m) {
     dim3 kg((unsigned)ceil_div(ld, 32), (unsigned)ceil_div(ld, 32));
     DMO_LAUNCH(kernel_matrix_kernel, kg, 256, (size_t)64 * (d + 1) * sizeof(double), ix.d, N, d, kernel, inv_ls.p + (size_t)m * d, h_c[m],
-               h_n[m] + jitter, ld, A.p);
+               h_n[m] + jitter, iy.d + (size_t)m * N, ld, A.p);
     for (int64_t k = 0; k < nb; ++k) {
       const int64_t k0 = k * CB;
       DMO_LAUNCH(potrf_diag_kernel, 1, 256, 0, A.p, ld, k0, info.p);
@@ -330,7 +321,7 @@ int dmo_gp_fit(dmo_ctx* ctx, int64_t N, int d, int M, int kernel, const double* 
       }
     }
     if (oa.d || ol.d) {
-      DMO_LAUNCH(solve_alpha_kernel, 1, SV_T, 0, A.p, ld, N, iy.d + (size_t)m * N, work.p, alpha_d.p, lml_d.p);
+      DMO_LAUNCH(finish_fit_kernel, 1, SV_T, 0, A.p, ld, N, work.p, alpha_d.p, lml_d.p, oa.d ? 1 : 0);
       if (oa.d) DMO_CUDA(cudaMemcpyAsync(oa.d + (size_t)m * N, alpha_d.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       if (ol.d) DMO_CUDA(cudaMemcpyAsync(ol.d + m, lml_d.p, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     }
