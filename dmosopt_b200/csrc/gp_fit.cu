@@ -75,36 +75,50 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const double* __rest
 
 // ---- Cholesky steps (A: lower triangle, in place, leading dimension ld, ld % CB == 0) ----------------------------------
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int64_t ld, int64_t k0, int* __restrict__ info) {
-  __shared__ double a[CB][CB + 1];
-  const int tid = threadIdx.x;
-  for (int t = tid; t < CB * CB; t += 256) {
-    const int r = t / CB, c = t % CB;
-    a[r][c] = c <= r ? A[(k0 + r) * ld + k0 + c] : 0.0;
+  // Thread (w, c) = (tid >> 6, tid & 63) keeps the 16 elements (r = w + 4 u, c) of the block in registers for the whole
+  // factorisation.  Column j: its four owner threads publish the (unscaled) column to shared memory, one barrier, then every
+  // thread scales what it needs itself (L_rj = a_rj / sqrt(a_jj)) and updates its own elements -- 16 independent FMAs per
+  // thread and step, one barrier per column (the published column is double buffered).
+  __shared__ double col[2][CB];
+  const int tid = threadIdx.x, c = tid & 63, w = tid >> 6;
+  double a[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int r = w + 4 * u;
+    a[u] = c <= r ? A[(k0 + r) * ld + k0 + c] : 0.0;
   }
-  __syncthreads();
   for (int j = 0; j < CB; ++j) {
-    const double djj = a[j][j];  // every thread reads the pivot (written before the barrier that ended the previous column)
-    if (!(djj > 0.0)) {
-      if (tid == 0) atomicExch(info, (int)(k0 + j) + 1);  // not positive definite (numpy raises LinAlgError here)
+    double* cb = col[j & 1];
+    if (c == j) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) cb[w + 4 * u] = a[u];
+    }
+    __syncthreads();
+    const double djj = cb[j];
+    if (!(djj > 0.0)) {  // uniform over the block: not positive definite (numpy raises LinAlgError here)
+      if (tid == 0) atomicExch(info, (int)(k0 + j) + 1);
       return;
     }
     const double s = sqrt(djj), rs = 1.0 / s;
-    double mine = 0.0;
-    if (tid > j && tid < CB) mine = a[tid][j] * rs;
-    __syncthreads();  // all pivot reads done
-    if (tid == j) a[j][j] = s;
-    if (tid > j && tid < CB) a[tid][j] = mine;
-    __syncthreads();
-    // trailing update of the block: a[r][c] -= a[r][j] a[c][j], j < c <= r
-    for (int t = tid; t < CB * CB; t += 256) {
-      const int r = t >> 6, c = t & 63;
-      if (c > j && c <= r) a[r][c] -= a[r][j] * a[c][j];
+    if (c == j) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int r = w + 4 * u;
+        a[u] = r == j ? s : (r > j ? a[u] * rs : a[u]);
+      }
+    } else if (c > j) {
+      const double lc = cb[c] * rs;  // L_cj
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int r = w + 4 * u;
+        if (r >= c) a[u] = fma(-(cb[r] * rs), lc, a[u]);
+      }
     }
-    __syncthreads();
   }
-  for (int t = tid; t < CB * CB; t += 256) {
-    const int r = t / CB, c = t % CB;
-    if (c <= r) A[(k0 + r) * ld + k0 + c] = a[r][c];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int r = w + 4 * u;
+    if (c <= r) A[(k0 + r) * ld + k0 + c] = a[u];
   }
 }
 

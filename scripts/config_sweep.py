@@ -53,7 +53,14 @@ def run(name, cls, d, M, pop, N, kind, gens=2, keep_last=None, **okw):
     y0 = sm.evaluate(x0).astype(np.float32)
     opt.initialize_strategy(x0, y0, bounds, rng)
     times, parts = [], []
+    prof = None
+    if os.environ.get("DMO_PROFILE"):  # where does the host side of a generation go (cProfile over the timed generations)
+        import cProfile
+
+        prof = cProfile.Profile()
     for g in range(gens + 1):
+        if prof is not None and g == 1:
+            prof.enable()
         if g == gens and keep_last is not None:  # the state the last update starts from (for exact re-computation by the tests)
             keep_last["before"] = {k: np.array(v) for k, v in opt.state.items() if isinstance(v, np.ndarray)}
         L.synchronize()
@@ -67,6 +74,11 @@ def run(name, cls, d, M, pop, N, kind, gens=2, keep_last=None, **okw):
         t3 = time.perf_counter()
         times.append(t3 - t0)
         parts.append((t1 - t0, t2 - t1, t3 - t2))
+    if prof is not None:
+        import pstats
+
+        prof.disable()
+        pstats.Stats(prof).sort_stats("cumulative").print_stats(28)
     if keep_last is not None:
         keep_last.update(x_gen=np.array(x_gen), y_gen=np.array(y_gen), state_gen=st, ms=np.mean(times[1:]) * 1e3, surrogate=sm)
     px, py = opt.population_objectives
