@@ -34,8 +34,15 @@ def sortMO(x, y, x_distance_metrics=None):
                 dist[idx] = fn(x[idx, :])
             keys.append(-dist)
     if not keys:  # np.lexsort((rank,)) is a stable sort by rank
-        return np.argsort(rank, kind="stable"), rank
+        return _stable_order(rank), rank
     return np.lexsort(keys + [rank]), rank
+
+
+def _stable_order(rank):
+    """np.argsort(rank, kind="stable"); 16-bit keys take NumPy's radix sort (ranks are small non-negative integers)."""
+    if rank.size and 0 <= int(rank.min()) and int(rank.max()) < 65536:
+        return np.argsort(rank.astype(np.uint16), kind="stable")
+    return np.argsort(rank, kind="stable")
 
 
 class CMAES(MOEA):
@@ -95,13 +102,14 @@ class CMAES(MOEA):
         psucc = np.asarray([p.ptarg] * n)
         order, rank = sortMO(x, y, self.x_distance_metrics)
         idx = order[:n]
-        return Struct(bounds=bounds, parents_x=x[idx].copy(), parents_y=y[idx].copy(), sigmas=sigmas, A=A, Ainv=Ainv, pc=pc,
-                      psucc=psucc, rank=rank[idx].copy())
+        # parents_x and sigmas are (n, dim) per-parent rows as well: resident, read by NumPy on demand
+        return Struct(bounds=bounds, parents_x=_lib.resident_rows(x[idx]), parents_y=y[idx].copy(), sigmas=_lib.resident_rows(sigmas), A=A, Ainv=Ainv,
+                      pc=pc, psucc=psucc, rank=rank[idx].copy())
 
     def _select(self, candidates_x, candidates_y, candidates_ps, candidates_inds):
         """CMAES.py:167-229."""
         popsize = self.opt_params.popsize
-        n = candidates_x.shape[0]
+        n = candidates_y.shape[0]  # candidates_x is only materialised on the host when x distance metrics need it
         if n <= popsize:
             return np.ones(n, dtype=bool), np.zeros(n, dtype=bool), _lib.rank_nd(candidates_y)
         order, rank = sortMO(candidates_x, candidates_y, self.x_distance_metrics)
@@ -148,27 +156,29 @@ class CMAES(MOEA):
         st = self.state
         dim, mu, lambda_ = self.nInput, self.opt_params.mu, self.opt_params.lambda_
         arz = rng.normal(size=(lambda_ * mu, dim))
-        order, rank = sortMO(st.parents_x, st.parents_y, self.x_distance_metrics)
+        order, rank = sortMO(np.asarray(st.parents_x) if self.x_distance_metrics else None, st.parents_y, self.x_distance_metrics)
         # fronts in rank order until at least mu parents are collected (CMAES.py:249-258) == the first mu indices of a
         # stable sort by rank
-        parent_selection = np.argsort(rank, kind="stable")[:mu]
+        parent_selection = (order if not self.x_distance_metrics else _stable_order(rank))[:mu]
         js = rng.choice(len(parent_selection), size=lambda_ * mu)
         p_idx = parent_selection[js]
-        individuals = _lib.cmaes_sample(st.parents_x, st.sigmas, st.A, p_idx, arz)
-        xrng = self.bounds[:, 1] - self.bounds[:, 0]
-        x_new = (individuals / np.max(np.abs(individuals))) * xrng + self.bounds[:, 0]  # (sic) global rescale, CMAES.py:269-270
+        # sample, the reference's global rescale (sic, CMAES.py:269-270) and MOEA.generate's clip on the device; the
+        # offspring matrix comes back read-only with its device copy kept for the surrogate and the update
+        x_new = _lib.cmaes_generate(st.parents_x, st.sigmas, st.A, p_idx, arz, self.bounds[:, 0], self.bounds[:, 1])
         return x_new, {"p_idx": p_idx}
 
     def update_strategy(self, x_gen, y_gen, state, **params):
-        """CMAES.py:273-414."""
+        """CMAES.py:273-414.  Scalars per individual (success rates, step-size factors, selection masks) are computed on
+        the host; every (n, dim) / (n, dim, dim) array (positions, step sizes, factors, paths) stays in HBM and is
+        re-assembled there."""
         st, p = self.state, self.opt_params
-        dim = self.nInput
         p_idxs = np.asarray(state["p_idx"])
         xlb, xub = self.bounds[:, 0], self.bounds[:, 1]
-        parents_x = st.parents_x
-        P, C = parents_x.shape[0], x_gen.shape[0]
-        candidates_x = np.vstack((x_gen, parents_x))
+        P, C = st.parents_x.shape[0], x_gen.shape[0]
+        xg_d, px_d, sig_d = _lib.rows_of(x_gen), _lib.rows_of(st.parents_x), _lib.rows_of(st.sigmas)
+        A_d, Ainv_d, pc_d = _lib.resident_rows(st.A), _lib.resident_rows(st.Ainv), _lib.resident_rows(st.pc)
         candidates_y = np.vstack((y_gen, st.parents_y))
+        candidates_x = np.vstack((np.asarray(x_gen), np.asarray(px_d))) if self.x_distance_metrics else None
         is_off = np.concatenate((np.ones(C, dtype=bool), np.zeros(P, dtype=bool)))
         pidx = np.concatenate((p_idxs, np.arange(P, dtype=np.int_)))
         chosen, not_chosen, rank = self._select(candidates_x, candidates_y, is_off, pidx)
@@ -176,65 +186,69 @@ class CMAES(MOEA):
         fac = lambda ps: np.exp((ps - ptarg) / (d * (1.0 - ptarg)))  # noqa: E731
 
         # ---- chosen offspring: their own strategy parameters start from the parent's (copied before any update)
-        ch_off = np.flatnonzero(chosen & is_off)
+        ch_off = np.flatnonzero(chosen[:C])  # offspring are the first C candidates
         par = pidx[ch_off]
         off_psucc = (1.0 - cp) * st.psucc[par] + cp
-        last_steps = st.sigmas[par].copy()
-        off_sigmas = last_steps * fac(off_psucc)[:, None]
-        A_d, Ainv_d, pc_d = _lib.resident_rows(st.A), _lib.resident_rows(st.Ainv), _lib.resident_rows(st.pc)
+        last_steps = _lib.gather_rows(sig_d, par)
+        off_sigmas = _lib.scale_rows(_lib.gather_rows(sig_d, par), fac(off_psucc))
         off_A, off_Ainv, off_pc = _lib.gather_rows(A_d, par), _lib.gather_rows(Ainv_d, par), _lib.gather_rows(pc_d, par)
         if len(ch_off) > 0:
-            z = np.divide(candidates_x[ch_off] - parents_x[par], xub - xlb) / last_steps
+            z = _lib.cmaes_step_z(xg_d, ch_off, px_d, par, xlb, xub, last_steps)
             off_A, off_Ainv, off_pc = _lib.cmaes_update_cholesky(off_A, off_Ainv, off_pc, z, off_psucc, cc, ccov, pthresh)
 
         # ---- parents: one success event per chosen offspring (ascending candidate index), then one failure event per
-        # not-chosen offspring; the recurrences are sequential per parent, so they are applied event-rank by event-rank
-        new_psucc, new_sig = st.psucc.copy(), st.sigmas.copy()
-        nc_off = np.flatnonzero(not_chosen & is_off)
+        # not-chosen offspring; the recurrences are sequential per parent: the scalar success rates are advanced event
+        # rank by event rank here, the step-size rows take their factors in the same order on the device
+        new_psucc = st.psucc.copy()
+        nc_off = np.flatnonzero(not_chosen[:C])
         ev_parent = np.concatenate((par, pidx[nc_off]))
         ev_success = np.concatenate((np.ones(len(par), dtype=bool), np.zeros(len(nc_off), dtype=bool)))
         if len(ev_parent) > 0:
             order = np.argsort(ev_parent, kind="stable")
             ep, es = ev_parent[order], ev_success[order]
             first = np.r_[True, ep[1:] != ep[:-1]]
-            start = np.maximum.accumulate(np.where(first, np.arange(len(ep)), 0))
-            k_in_parent = np.arange(len(ep)) - start
+            seg_start = np.flatnonzero(first)
+            k_in_parent = np.arange(len(ep)) - np.repeat(seg_start, np.diff(np.r_[seg_start, len(ep)]))
+            f_ev = np.empty(len(ep))
             for k in range(int(k_in_parent.max()) + 1):
-                sel = k_in_parent == k
+                sel = np.flatnonzero(k_in_parent == k)
                 q = ep[sel]
                 new_psucc[q] = (1.0 - cp) * new_psucc[q] + np.where(es[sel], cp, 0.0)
-                new_sig[q] = new_sig[q] * fac(new_psucc[q])[:, None]
-        st.psucc, st.sigmas = new_psucc, new_sig
+                f_ev[sel] = fac(new_psucc[q])
+            _lib.scale_rows(sig_d, f_ev, seg_row=ep[seg_start], seg_start=np.r_[seg_start, len(ep)])  # in place: the old rows were copied above
+        st.psucc = new_psucc
 
         # ---- assemble the next parent set (CMAES.py:385-411)
         ch = np.flatnonzero(chosen)
-        ch_is_off = is_off[ch]
-        slot = np.full(candidates_x.shape[0], -1, dtype=int)
+        ch_is_off = ch < C
+        slot = np.full(C + P, -1, dtype=np.int64)
         slot[ch_off] = np.arange(len(ch_off))
         src_par = pidx[ch]
-        sigmas_n = st.sigmas[src_par].copy()
-        psucc_n = st.psucc[src_par].copy()
+        psucc_n = st.psucc[src_par]
         src_idx = src_par.astype(np.int64)
         if len(ch_off) > 0:
             o = slot[ch[ch_is_off]]
-            sigmas_n[ch_is_off] = off_sigmas[o]
             psucc_n[ch_is_off] = off_psucc[o]
             src_idx[ch_is_off] = o  # these rows come from the updated offspring arrays
-        # one device-side gather per state array: a surviving parent keeps its factors, a chosen offspring brings its own
+        # one device-side gather per state array: a surviving parent keeps its rows, a chosen offspring brings its own
         sel = ch_is_off if len(ch_off) > 0 else None
-        A_n = _lib.gather_rows(A_d, src_idx, alt=off_A if sel is not None else None, sel=sel)
-        Ainv_n = _lib.gather_rows(Ainv_d, src_idx, alt=off_Ainv if sel is not None else None, sel=sel)
-        pc_n = _lib.gather_rows(pc_d, src_idx, alt=off_pc if sel is not None else None, sel=sel)
-        st.parents_x = candidates_x[chosen]
-        st.parents_y = candidates_y[chosen]
-        st.rank = rank[chosen]
+        alt = (lambda a: a) if sel is not None else (lambda a: None)
+        sigmas_n = _lib.gather_rows(sig_d, src_idx, alt=alt(off_sigmas), sel=sel)
+        A_n = _lib.gather_rows(A_d, src_idx, alt=alt(off_A), sel=sel)
+        Ainv_n = _lib.gather_rows(Ainv_d, src_idx, alt=alt(off_Ainv), sel=sel)
+        pc_n = _lib.gather_rows(pc_d, src_idx, alt=alt(off_pc), sel=sel)
+        x_idx = np.where(ch_is_off, ch, ch - C)  # candidate row -> row of x_gen / of the old parents
+        st.parents_x = _lib.gather_rows(px_d, x_idx, alt=alt(xg_d), sel=sel)
+        st.parents_y = candidates_y[ch]
+        st.rank = rank[ch]
         st.sigmas, st.A, st.Ainv, st.pc, st.psucc = sigmas_n, A_n, Ainv_n, pc_n, psucc_n
+        _lib.mirror_drop(x_gen)  # the offspring matrix has been consumed: callers that keep it hold host memory only
         if p.adaptive_population_size:
             self.update_population_size()
 
     def get_population_strategy(self):
         """CMAES.py:416-430."""
-        x, y = remove_duplicates(self.state.parents_x.copy(), self.state.parents_y.copy())
+        x, y = remove_duplicates(np.asarray(self.state.parents_x), self.state.parents_y.copy())
         if len(x) > 0:
             x, y, _ = remove_worst(x, y, self.popsize)
         return x, y

@@ -84,6 +84,9 @@ _SIGNATURES = {
     "dmo_cmaes_sample": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp]),
     "dmo_cmaes_update_cholesky": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl]),
     "dmo_gather_rows": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp]),
+    "dmo_cmaes_generate": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp, _vp, _vp]),
+    "dmo_cmaes_step_z": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _vp]),
+    "dmo_scale_rows": (_c_int, [_vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _c_i64]),
     "dmo_benchmark_eval": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _c_int, _c_dbl, _vp]),
     "dmo_smpso_generate": (_c_int, [_vp, _vp, _vp, _c_int, _c_i64, _c_int, _vp, _vp, _vp, _c_dbl, _c_u64, _c_u64, _vp, _vp]),
     "dmo_smpso_update": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -893,6 +896,9 @@ class ResidentRows:
     def ptr(self):
         return self.dev.ptr
 
+    def data_ptr(self):
+        return self.dev.ptr
+
     @property
     def row_elems(self):
         return int(np.prod(self.shape[1:])) if len(self.shape) > 1 else 1
@@ -934,6 +940,40 @@ def gather_rows(src, idx, alt=None, sel=None):
     return out
 
 
+class _Borrowed:
+    """Device memory owned by someone else (the mirror of a read-only host array) behind the DeviceArray surface."""
+
+    def __init__(self, ptr, host):
+        self.ptr, self.host = ptr, host
+
+    def download(self, count=None):
+        return np.array(self.host, dtype=np.float64).reshape(-1)[: None if count is None else int(count)]
+
+
+def rows_of(a):
+    """ResidentRows over ``a``: itself, the device mirror the library already holds for a read-only host array (no
+    copy; valid while the mirror lives), or an upload."""
+    if isinstance(a, ResidentRows):
+        return a
+    if isinstance(a, np.ndarray) and a.dtype == np.float64:
+        m = mirror_ptr(a)
+        if m is not None:
+            return ResidentRows(_Borrowed(m, a), a.shape)
+    return resident_rows(a)
+
+
+def scale_rows(rows, factors, seg_row=None, seg_start=None):
+    """In place on a ResidentRows: ``rows[seg_row[s]] *= factors[e]`` for e in [seg_start[s], seg_start[s+1]), one rounded
+    multiplication after the other (dmo_scale_rows); without segments: ``rows[s] *= factors[s]``."""
+    f = _f64(factors)
+    sr = None if seg_row is None else np.ascontiguousarray(seg_row, dtype=np.int64)
+    ss = None if seg_start is None else np.ascontiguousarray(seg_start, dtype=np.int64)
+    n_seg = rows.shape[0] if sr is None else sr.shape[0]
+    assert (ss is None or ss.shape[0] == n_seg + 1) and (ss is not None or f.shape[0] == n_seg)
+    _check(load_library().dmo_scale_rows(context(), rows.ptr, rows.row_elems, n_seg, _ptr(sr), _ptr(ss), _ptr(f), f.shape[0]), "dmo_scale_rows")
+    return rows
+
+
 def identity_rows(n, d):
     """n copies of the d x d identity, resident (CMAES.py:137-141) -- built on the device from one uploaded matrix."""
     return gather_rows(resident_rows(np.identity(d)[None, :, :]), np.zeros(n, dtype=np.int64))
@@ -954,13 +994,44 @@ def cmaes_sample(parents_x, sigmas, A, p_idx, z):
     return out
 
 
+def cmaes_generate(parents_x, sigmas, A, p_idx, z, xlb, xub):
+    """Offspring of one MO-CMA-ES generation from the resident parent state: sample, global rescale, clip (CMAES.py:265-270,
+    MOEA.py:155) in one call; returns a read-only page-locked (n, d) array whose device copy the next calls reuse."""
+    z = _f64(z)
+    pi = np.ascontiguousarray(p_idx, dtype=np.int64)
+    n, d = z.shape
+    px, sg = rows_of(parents_x), rows_of(sigmas)
+    cols = 1 if sg.ndim == 1 else sg.shape[1]
+    lb, ub = _f64(xlb), _f64(xub)
+    x_dev = DeviceArray((n, d), np.float64)
+    _check(load_library().dmo_cmaes_generate(context(), px.ptr, sg.ptr, cols, A.ptr, px.shape[0], _ptr(pi), _ptr(z), n, d, _ptr(lb), _ptr(ub), x_dev.ptr),
+           "dmo_cmaes_generate")
+    out = pinned_empty((n, d), np.float64)
+    memcpy(out, x_dev.ptr, out.nbytes)
+    mirror_register(out, x_dev)
+    out.flags.writeable = False
+    return out
+
+
+def cmaes_step_z(x_gen, cand_idx, parents_x, par_idx, xlb, xub, steps):
+    """z = ((x_gen[cand_idx] - parents_x[par_idx]) / (xub - xlb)) / steps on resident rows (CMAES.py:359)."""
+    ci = np.ascontiguousarray(cand_idx, dtype=np.int64)
+    pi = np.ascontiguousarray(par_idx, dtype=np.int64)
+    n, d = ci.shape[0], parents_x.shape[1]
+    out = ResidentRows(DeviceArray((n, d), np.float64), (n, d))
+    if n:
+        lb, ub = _f64(xlb), _f64(xub)
+        _check(load_library().dmo_cmaes_step_z(context(), x_gen.ptr, _ptr(ci), parents_x.ptr, _ptr(pi), _ptr(lb), _ptr(ub), steps.ptr, n, d, out.ptr), "dmo_cmaes_step_z")
+    return out
+
+
 def cmaes_update_cholesky(A, Ainv, pc, z, psucc, cc, ccov, pthresh):
     """Batched CMAES.updateCholesky (dmosopt/CMAES.py:489-537); returns new (A, Ainv, pc).  ResidentRows are updated in
     place in HBM (no factor crosses the PCIe bus), host arrays are copied, staged and returned."""
     if isinstance(A, ResidentRows):
         n, d = pc.shape
         if n:
-            z, ps = _f64(z), _f64(psucc)
+            z, ps = (z if isinstance(z, ResidentRows) else _f64(z)), _f64(psucc)
             _check(load_library().dmo_cmaes_update_cholesky(context(), A.ptr, Ainv.ptr, pc.ptr, _ptr(z), _ptr(ps), n, d, float(cc), float(ccov), float(pthresh)),
                    "dmo_cmaes_update_cholesky")
         return A, Ainv, pc

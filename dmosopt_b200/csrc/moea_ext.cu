@@ -5,6 +5,8 @@
 //   SMPSO per-swarm polynomial mutation        dmosopt/SMPSO.py:163-182
 //   CMAES sampling x = x_p + sigma_p A_p z     dmosopt/CMAES.py:263-267
 //   CMAES updateCholesky (batched)             dmosopt/CMAES.py:489-537
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -272,6 +274,62 @@ __global__ void gather_rows_kernel(const double* __restrict__ src, const double*
   dst[t] = s[idx[i] * row + c];
 }
 
+// max |x| over a device array as the bit pattern of a non-negative double (which orders like the value); exact, the
+// maximum does not depend on the order of the reduction
+__global__ void absmax_kernel(const double* __restrict__ x, int64_t n, unsigned long long* __restrict__ out_bits) {
+  unsigned long long m = 0ull;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x[t]));
+    m = b > m ? b : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, m, o);
+    m = v > m ? v : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out_bits, m);
+}
+
+// x = clip((individual / max|individuals|) * (xub - xlb) + xlb, xlb, xub): the reference's global rescale (CMAES.py:269-270)
+// followed by MOEA.generate's clip (MOEA.py:155); every operation rounded separately, as NumPy evaluates it
+__global__ void cmaes_rescale_kernel(double* __restrict__ x, int64_t n, int d, const unsigned long long* __restrict__ mx_bits,
+                                     const double* __restrict__ xlb, const double* __restrict__ xub) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * d) return;
+  const int j = (int)(t % d);
+  const double mx = __longlong_as_double((long long)*mx_bits);
+  const double lb = xlb[j], ub = xub[j];
+  const double v = __dadd_rn(__dmul_rn(__ddiv_rn(x[t], mx), __dsub_rn(ub, lb)), lb);
+  x[t] = fmin(fmax(v, lb), ub);
+}
+
+// z[i] = ((x_gen[ci[i]] - parents_x[pi[i]]) / (xub - xlb)) / step[i]: the offspring's move in its parent's coordinates
+// (CMAES.py:316-318), operations rounded one by one
+__global__ void cmaes_z_kernel(const double* __restrict__ xg, const int64_t* __restrict__ ci, const double* __restrict__ px,
+                               const int64_t* __restrict__ pi, const double* __restrict__ xlb, const double* __restrict__ xub,
+                               const double* __restrict__ steps, int64_t n, int d, double* __restrict__ z) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * d) return;
+  const int64_t i = t / d;
+  const int j = (int)(t - i * d);
+  const double diff = __dsub_rn(xg[ci[i] * d + j], px[pi[i] * d + j]);
+  z[t] = __ddiv_rn(__ddiv_rn(diff, __dsub_rn(xub[j], xlb[j])), steps[t]);
+}
+
+// rows[seg_row[s], :] *= factors[e] for e = seg_start[s] .. seg_start[s + 1] - 1, one multiplication after the other (the
+// step-size recurrences of one parent are sequential, CMAES.py:330-383); seg_row == nullptr: row s, seg_start == nullptr:
+// one factor per row
+__global__ void scale_rows_kernel(double* __restrict__ rows, int64_t row, int64_t n_seg, const int64_t* __restrict__ seg_row,
+                                  const int64_t* __restrict__ seg_start, const double* __restrict__ factors) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_seg * row) return;
+  const int64_t s = t / row, c = t - s * row;
+  const int64_t r = seg_row ? seg_row[s] : s;
+  const int64_t e0 = seg_start ? seg_start[s] : s, e1 = seg_start ? seg_start[s + 1] : s + 1;
+  double v = rows[r * row + c];
+  for (int64_t e = e0; e < e1; ++e) v = __dmul_rn(v, factors[e]);
+  rows[r * row + c] = v;
+}
+
 }  // namespace
 
 extern "C" {
@@ -394,6 +452,77 @@ int dmo_cmaes_sample(dmo_ctx* ctx, const double* parents_x, const double* sigmas
              oo.d);
   DMO_CHECK_LAUNCH();
   DMO_TRY(oo.finish(ctx));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
+
+int dmo_cmaes_generate(dmo_ctx* ctx, const double* parents_x, const double* sigmas, int sigma_cols, const double* A,
+                       int64_t n_parents, const int64_t* p_idx, const double* z, int64_t n, int d, const double* xlb,
+                       const double* xub, double* x_out) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  DMO_REQUIRE(parents_x && sigmas && A && p_idx && z && xlb && xub && x_out && n > 0 && n_parents > 0 && d >= 1 &&
+                  (sigma_cols == 1 || sigma_cols == d),
+              "cmaes_generate: bad arguments");
+  In<double> ipx, isg, iA, iz, ilb, iub;
+  In<int64_t> ipi;
+  Out<double> oo;
+  DevBuf<unsigned long long> mx;
+  DMO_TRY(ipx.init(ctx, parents_x, (size_t)n_parents * d));
+  DMO_TRY(isg.init(ctx, sigmas, (size_t)n_parents * sigma_cols));
+  DMO_TRY(iA.init(ctx, A, (size_t)n_parents * d * d));
+  DMO_TRY(ipi.init(ctx, p_idx, (size_t)n));
+  DMO_TRY(iz.init(ctx, z, (size_t)n * d));
+  DMO_TRY(ilb.init(ctx, xlb, (size_t)d));
+  DMO_TRY(iub.init(ctx, xub, (size_t)d));
+  DMO_TRY(oo.init(ctx, x_out, (size_t)n * d));
+  DMO_TRY(mx.alloc(ctx, 1));
+  DMO_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(unsigned long long), ctx->stream));
+  DMO_LAUNCH(cmaes_sample_kernel, (unsigned)ceil_div(n * d, 256), 256, 0, ipx.d, isg.d, sigma_cols, iA.d, ipi.d, iz.d, n, d,
+             oo.d);
+  DMO_LAUNCH(absmax_kernel, (unsigned)std::min<int64_t>(ceil_div(n * d, 256), 4 * (int64_t)ctx->sm_count), 256, 0, oo.d, n * d, mx.p);
+  DMO_LAUNCH(cmaes_rescale_kernel, (unsigned)ceil_div(n * d, 256), 256, 0, oo.d, n, d, mx.p, ilb.d, iub.d);
+  DMO_CHECK_LAUNCH();
+  DMO_TRY(oo.finish(ctx));
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
+
+int dmo_cmaes_step_z(dmo_ctx* ctx, const double* x_gen, const int64_t* cand_idx, const double* parents_x,
+                     const int64_t* par_idx, const double* xlb, const double* xub, const double* steps, int64_t n, int d,
+                     double* z_out) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return DMO_OK;
+  DMO_REQUIRE(x_gen && cand_idx && parents_x && par_idx && xlb && xub && steps && z_out && n > 0 && d >= 1, "cmaes_step_z: bad arguments");
+  DMO_REQUIRE(dmo_is_device_ptr(x_gen) && dmo_is_device_ptr(parents_x) && dmo_is_device_ptr(steps) && dmo_is_device_ptr(z_out),
+              "cmaes_step_z: x_gen / parents_x / steps / z_out are device-resident arrays");
+  In<int64_t> ici, ipi;
+  In<double> ilb, iub;
+  DMO_TRY(ici.init(ctx, cand_idx, (size_t)n));
+  DMO_TRY(ipi.init(ctx, par_idx, (size_t)n));
+  DMO_TRY(ilb.init(ctx, xlb, (size_t)d));
+  DMO_TRY(iub.init(ctx, xub, (size_t)d));
+  DMO_LAUNCH(cmaes_z_kernel, (unsigned)ceil_div(n * d, 256), 256, 0, x_gen, ici.d, parents_x, ipi.d, ilb.d, iub.d, steps, n, d, z_out);
+  DMO_CHECK_LAUNCH();
+  DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DMO_OK;
+}
+
+int dmo_scale_rows(dmo_ctx* ctx, double* rows, int64_t row_elems, int64_t n_seg, const int64_t* seg_row,
+                   const int64_t* seg_start, const double* factors, int64_t n_factors) {
+  if (!ctx) return DMO_ERR_ARG;
+  DMO_CUDA(cudaSetDevice(ctx->device));
+  if (n_seg == 0) return DMO_OK;
+  DMO_REQUIRE(rows && factors && n_seg > 0 && row_elems >= 1 && n_factors >= (seg_start ? 0 : n_seg), "scale_rows: bad arguments");
+  DMO_REQUIRE(dmo_is_device_ptr(rows), "scale_rows: rows is a device-resident array");
+  In<int64_t> isr, iss;
+  In<double> ifa;
+  DMO_TRY(isr.init(ctx, seg_row, (size_t)n_seg));
+  DMO_TRY(iss.init(ctx, seg_start, (size_t)n_seg + 1));
+  DMO_TRY(ifa.init(ctx, factors, (size_t)n_factors));
+  DMO_LAUNCH(scale_rows_kernel, (unsigned)ceil_div(n_seg * row_elems, 256), 256, 0, rows, row_elems, n_seg, isr.d, iss.d, ifa.d);
+  DMO_CHECK_LAUNCH();
   DMO_CUDA(cudaStreamSynchronize(ctx->stream));
   return DMO_OK;
 }

@@ -241,6 +241,32 @@ def identity_rows(n, d):
     return ResidentRows(np.broadcast_to(np.identity(d), (n, d, d)))
 
 
+def rows_of(a):
+    return resident_rows(a)
+
+
+def scale_rows(rows, factors, seg_row=None, seg_start=None):
+    f = np.asarray(factors, dtype=np.float64)
+    if seg_row is None:
+        rows.a *= f.reshape((-1,) + (1,) * (rows.a.ndim - 1))
+        return rows
+    for s, r in enumerate(np.asarray(seg_row)):
+        for e in range(int(seg_start[s]), int(seg_start[s + 1])):
+            rows.a[r] = rows.a[r] * f[e]
+    return rows
+
+
+def cmaes_generate(parents_x, sigmas, A, p_idx, z, xlb, xub):
+    ind = cmaes_sample(parents_x, sigmas, A, p_idx, z)
+    xlb, xub = np.asarray(xlb, dtype=np.float64), np.asarray(xub, dtype=np.float64)
+    return np.clip((ind / np.max(np.abs(ind))) * (xub - xlb) + xlb, xlb, xub)
+
+
+def cmaes_step_z(x_gen, cand_idx, parents_x, par_idx, xlb, xub, steps):
+    z = np.divide(np.asarray(x_gen)[np.asarray(cand_idx)] - np.asarray(parents_x)[np.asarray(par_idx)], np.asarray(xub) - np.asarray(xlb)) / np.asarray(steps)
+    return ResidentRows(z)
+
+
 def cmaes_sample(parents_x, sigmas, A, p_idx, z):
     p_idx = np.asarray(p_idx)
     return np.asarray(parents_x)[p_idx] + np.asarray(sigmas)[p_idx] * np.einsum("ijk,ik->ij", np.asarray(A)[p_idx], np.asarray(z))
@@ -260,7 +286,8 @@ SmpsoSwarms = None  # the CPU seam exercises the per-swarm host path of the SMPS
 
 FUNCTIONS = ["rank_nd", "crowding_distance", "euclidean_distance", "order_mo", "remove_worst", "remove_worst_pair", "tournament", "mutation_u", "sbx_u",
              "nsga2_generate", "GPHandle", "hypervolume", "ehvi_select", "get_duplicates", "age_survival", "smpso_velocity", "mutate_groups",
-             "cmaes_sample", "cmaes_update_cholesky", "ResidentRows", "resident_rows", "gather_rows", "identity_rows", "SmpsoSwarms", "gp_fit"]
+             "cmaes_sample", "cmaes_update_cholesky", "ResidentRows", "resident_rows", "gather_rows", "identity_rows", "rows_of", "scale_rows",
+             "cmaes_generate", "cmaes_step_z", "SmpsoSwarms", "gp_fit"]
 
 
 def install(monkeypatch):

@@ -889,6 +889,44 @@ def test_cmaes_kernels(L):
         np.testing.assert_allclose(pc2[i], c, rtol=1e-13, atol=1e-15)
 
 
+def test_cmaes_resident_steps_are_bit_exact(L):
+    """The device-resident MO-CMA-ES steps against the NumPy expressions of the reference, operation by operation:
+    rescale + clip (CMAES.py:269-270, MOEA.py:155), z (CMAES.py:359), sequential step-size factors (CMAES.py:330-383)."""
+    rng = np.random.default_rng(5)
+    npar, n, d = 300, 1000, 24
+    px, sig = rng.random((npar, d)) - 0.5, rng.random((npar, d)) * 0.01
+    A = L.resident_rows(np.eye(d)[None] + 0.1 * rng.standard_normal((npar, d, d)))
+    pidx = rng.integers(0, npar, size=n)
+    zn = rng.standard_normal((n, d))
+    xlb, xub = -rng.random(d), 1.0 + rng.random(d)
+    ind = L.cmaes_sample(px, sig, A, pidx, zn)
+    x = L.cmaes_generate(L.resident_rows(px), L.resident_rows(sig), A, pidx, zn, xlb, xub)
+    want = np.clip((ind / np.max(np.abs(ind))) * (xub - xlb) + xlb, xlb, xub)
+    assert not x.flags.writeable and L.mirror_ptr(x) is not None and np.array_equal(x, want)
+    assert (want == xlb).any() and not np.array_equal(want, (ind / np.max(np.abs(ind))) * (xub - xlb) + xlb)  # the clip acts
+    # z of chosen offspring
+    ci = np.sort(rng.choice(n, size=400, replace=False))
+    par = pidx[ci]
+    xg_d, px_d, sig_d = L.rows_of(x), L.resident_rows(px), L.resident_rows(sig)
+    assert isinstance(xg_d.dev, L._Borrowed)  # the offspring matrix is not uploaded again
+    steps = L.gather_rows(sig_d, par)
+    z = L.cmaes_step_z(xg_d, ci, px_d, par, xlb, xub, steps)
+    assert np.array_equal(np.asarray(z), np.divide(want[ci] - px[par], xub - xlb) / sig[par])
+    # one factor per row, then per-parent event lists
+    f = np.exp(rng.standard_normal(len(par)) * 0.1)
+    assert np.array_equal(np.asarray(L.scale_rows(steps, f)), sig[par] * f[:, None])
+    ev = np.sort(rng.integers(0, npar, size=700))
+    fe = np.exp(rng.standard_normal(700) * 0.1)
+    first = np.r_[True, ev[1:] != ev[:-1]]
+    ss = np.flatnonzero(first)
+    L.scale_rows(sig_d, fe, seg_row=ev[ss], seg_start=np.r_[ss, len(ev)])
+    ref = sig.copy()
+    for e, q in enumerate(ev):
+        ref[q] = ref[q] * fe[e]
+    assert np.array_equal(np.asarray(sig_d), ref)
+    L.mirror_drop(x)
+
+
 def test_age_smpso_cmaes_plugins_golden_on_gpu(L):
     import dmosopt_b200 as b2
     from test_host_plugins import _run_plugin_goldens
