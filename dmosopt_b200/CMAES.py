@@ -11,6 +11,7 @@ Drop-in for ``dmosopt.CMAES.CMAES`` (dmosopt/CMAES.py:26-537), selected by ``opt
                       CMAES.py:273-414, 489-537)
 """
 
+from concurrent.futures import ThreadPoolExecutor
 from typing import Any, Dict, Optional
 
 import numpy as np
@@ -36,6 +37,11 @@ def sortMO(x, y, x_distance_metrics=None):
     if not keys:  # np.lexsort((rank,)) is a stable sort by rank
         return _stable_order(rank), rank
     return np.lexsort(keys + [rank]), rank
+
+
+# one worker thread: generate_strategy ranks the parents on the GPU while the calling thread draws the normal variates
+# (both release the GIL; the library is not re-entrant, so the caller makes no library call until it has joined)
+_worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="dmosopt_b200_cmaes")
 
 
 def _stable_order(rank):
@@ -155,8 +161,13 @@ class CMAES(MOEA):
         rng = self.local_random
         st = self.state
         dim, mu, lambda_ = self.nInput, self.opt_params.mu, self.opt_params.lambda_
-        arz = rng.normal(size=(lambda_ * mu, dim))
-        order, rank = sortMO(np.asarray(st.parents_x) if self.x_distance_metrics else None, st.parents_y, self.x_distance_metrics)
+        if self.x_distance_metrics:  # host callables: keep everything on the calling thread
+            arz = rng.normal(size=(lambda_ * mu, dim))
+            order, rank = sortMO(np.asarray(st.parents_x), st.parents_y, self.x_distance_metrics)
+        else:  # same draws in the same order (sortMO consumes no random numbers), the device rank overlaps them
+            pending = _worker.submit(sortMO, None, st.parents_y, None)
+            arz = rng.normal(size=(lambda_ * mu, dim))
+            order, rank = pending.result()
         # fronts in rank order until at least mu parents are collected (CMAES.py:249-258) == the first mu indices of a
         # stable sort by rank
         parent_selection = (order if not self.x_distance_metrics else _stable_order(rank))[:mu]

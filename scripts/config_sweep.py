@@ -39,7 +39,7 @@ def targets(X, M, kind):
     return Y
 
 
-def run(name, cls, d, M, pop, N, kind, gens=2, keep_last=None, **okw):
+def run(name, cls, d, M, pop, N, kind, gens=4, keep_last=None, **okw):
     rng = np.random.default_rng(20260921 + len(name))
     xlb, xub = np.zeros(d), np.ones(d)
     Xtr = rng.random((N, d))
@@ -80,13 +80,18 @@ def run(name, cls, d, M, pop, N, kind, gens=2, keep_last=None, **okw):
         prof.disable()
         pstats.Stats(prof).sort_stats("cumulative").print_stats(28)
     if keep_last is not None:
-        keep_last.update(x_gen=np.array(x_gen), y_gen=np.array(y_gen), state_gen=st, ms=np.mean(times[1:]) * 1e3, surrogate=sm)
+        keep_last.update(x_gen=np.array(x_gen), y_gen=np.array(y_gen), state_gen=st, ms=np.median(times[1:]) * 1e3, surrogate=sm)
     px, py = opt.population_objectives
     assert px.shape[1] == d and py.shape[1] == M and np.all(np.isfinite(py)), name
     assert np.all(px >= xlb - 1e-12) and np.all(px <= xub + 1e-12), name
-    ms = np.mean(times[1:]) * 1e3
+    # median over the generations after the first: the stream-ordered memory pool still grows during the first few
+    # (a multi-GB cudaMallocAsync from the driver costs hundreds of milliseconds once)
+    ms = np.median(times[1:]) * 1e3
     P = x_gen.shape[0]
-    gm, em, um = (np.mean([p[i] for p in parts[1:]]) * 1e3 for i in range(3))
+    gm, em, um = (np.median([p[i] for p in parts[1:]]) * 1e3 for i in range(3))
+    if os.environ.get("DMO_VERBOSE_GENS"):
+        for g, (t, p3) in enumerate(zip(times, parts)):
+            print(f"   generation {g}: {t * 1e3:.1f} ms (generate {p3[0] * 1e3:.1f} + surrogate {p3[1] * 1e3:.1f} + update {p3[2] * 1e3:.1f})", flush=True)
     print(f"{name}: pop={pop} d={d} M={M} N_train={N} offspring/generation={P}: {ms:.1f} ms/generation (generate {gm:.1f} + surrogate {em:.1f} + update {um:.1f}) "
           f"-> {P / ms * 1e3:,.0f} candidates/s; population {px.shape[0]} rows", flush=True)
     return opt, px, py

@@ -152,4 +152,4 @@ def test_c5_cmaes_pop131072_m4(L):
     A, Ainv = np.asarray(st.A[idx]), np.asarray(st.Ainv[idx])
     err = np.abs(np.einsum("nij,njk->nik", A, Ainv) - np.eye(24)).max()
     assert err < 1e-9, err
-    assert last["ms"] < 400.0, last["ms"]  # was 1600 ms with the factors on the host
+    assert last["ms"] < 200.0, last["ms"]  # median generation; 1600 ms with the factors on the host, 150 ms with host-side positions / step sizes
