@@ -459,8 +459,8 @@ int gp_calibrate(dmo_ctx* ctx, dmo_gp* gp) {
   if (gp->calibrated) return DMO_OK;
   const int M = gp->M, d = gp->d;
   const int P = CAL_PROBES;
-  gp->auto_mean_tensor = gp->auto_var_tensor = false;
-  gp->cal_mean_err = gp->cal_var_err = INFINITY;
+  gp->auto_mean_tensor = gp->auto_var_tensor = gp->auto_mean_only = false;
+  gp->cal_mean_err = gp->cal_var_err = gp->cal_mean_err_only = INFINITY;
   gp->refine_theta = 1.0;
   if (M > 16 || d > 64) {  // outside the tensor path's shape limits: float64 only
     gp->calibrated = true;
@@ -476,23 +476,26 @@ int gp_calibrate(dmo_ctx* ctx, dmo_gp* gp) {
   DMO_CHECK_LAUNCH();
   const bool prof = ctx->profiling;
   ctx->profiling = false;  // calibration launches are not part of any timed step
-  DevBuf<double> md;
+  DevBuf<double> md, mo;
   DMO_TRY(md.alloc(ctx, (size_t)P * M));
+  DMO_TRY(mo.alloc(ctx, (size_t)P * M));
   int rc = gp_predict_fp64(ctx, gp, xn.p, P, m64.p, v64.p);
   if (rc == DMO_OK) rc = gp_predict_tensor(ctx, gp, xn.p, P, mt.p, vt.p, false);
+  if (rc == DMO_OK) rc = gp_predict_tensor(ctx, gp, xn.p, P, mo.p, nullptr, false);  // the mean-only call takes its own kernel
   const bool try_d = gp->z_ready;
   if (rc == DMO_OK && try_d) rc = gp_predict_tensor(ctx, gp, xn.p, P, md.p, vt.p, true);  // same variance, mean from D z
   ctx->profiling = prof;
   if (rc != DMO_OK) return rc;
-  std::vector<double> h((size_t)4 * P * M), hd((size_t)P * M);
+  std::vector<double> h((size_t)4 * P * M), hd((size_t)P * M), ho((size_t)P * M);
   if (try_d) DMO_CUDA(cudaMemcpyAsync(hd.data(), md.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DMO_CUDA(cudaMemcpyAsync(ho.data(), mo.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
   DMO_CUDA(cudaMemcpyAsync(h.data(), m64.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
   DMO_CUDA(cudaMemcpyAsync(h.data() + (size_t)P * M, v64.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
   DMO_CUDA(cudaMemcpyAsync(h.data() + (size_t)2 * P * M, mt.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
   DMO_CUDA(cudaMemcpyAsync(h.data() + (size_t)3 * P * M, vt.p, (size_t)P * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
   DMO_CUDA(cudaStreamSynchronize(ctx->stream));
   const double *a64 = h.data(), *b64 = a64 + (size_t)P * M, *at = b64 + (size_t)P * M, *bt = at + (size_t)P * M;
-  double em = 0.0, ev = 0.0, ed = try_d ? 0.0 : INFINITY;
+  double em = 0.0, ev = 0.0, ed = try_d ? 0.0 : INFINITY, eo = 0.0;
   for (int p = 0; p < P; ++p)
     for (int m = 0; m < M; ++m) {
       const double ys = gp->h_ystd[m];
@@ -505,19 +508,23 @@ int gp_calibrate(dmo_ctx* ctx, dmo_gp* gp) {
         const double dd = fabs(hd[p * M + m] - a64[p * M + m]) / fmax(fabs(a64[p * M + m]), ys);
         ed = (dd > ed || dd != dd) ? (dd != dd ? INFINITY : dd) : ed;
       }
+      const double dq = fabs(ho[p * M + m] - a64[p * M + m]) / fmax(fabs(a64[p * M + m]), ys);
+      eo = (dq > eo || dq != dq) ? (dq != dq ? INFINITY : dq) : eo;
     }
   gp->cal_mean_err = em;
   gp->cal_mean_err_d = ed;
+  gp->cal_mean_err_only = eo;
   gp->cal_var_err = ev;
   // the mean out of the contraction saves the K_* alpha pass; it is used when it holds the same margin on the probes
   gp->mean_from_d = try_d && ed <= 2.5e-6;
   gp->auto_mean_tensor = em <= 2.5e-6;
+  gp->auto_mean_only = eo <= 2.5e-6;
   gp->auto_var_tensor = (gp->auto_mean_tensor || gp->mean_from_d) && ev <= 4.5e-6;
   gp->refine_theta = fmax(0.02, 2.0 * ev / 1e-5);
   gp->calibrated = true;
   if (getenv("DMO_GP_VERBOSE"))
-    fprintf(stderr, "dmosopt_b200: GP calibration (N=%lld d=%d M=%d): mean err K*alpha %.3e, D z %.3e, var err/prior %.3e -> mean %s, var %s, theta %.3f\n",
-            (long long)gp->N, d, M, em, ed, ev, gp->mean_from_d ? "contraction" : (gp->auto_mean_tensor ? "K*alpha pass" : "float64"),
+    fprintf(stderr, "dmosopt_b200: GP calibration (N=%lld d=%d M=%d): mean err K*alpha %.3e, D z %.3e, mean-only kernel %.3e, var err/prior %.3e -> mean %s, var %s, theta %.3f\n",
+            (long long)gp->N, d, M, em, ed, eo, ev, gp->mean_from_d ? "contraction" : (gp->auto_mean_tensor ? "K*alpha pass" : "float64"),
             gp->auto_var_tensor ? "tensor" : "float64", gp->refine_theta);
   return DMO_OK;
 }
@@ -526,7 +533,7 @@ int gp_calibrate(dmo_ctx* ctx, dmo_gp* gp) {
 int gp_predict_auto(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var) {
   DMO_TRY(gp_calibrate(ctx, gp));
   gp->last_refined = 0;
-  if (d_var ? !gp->auto_var_tensor : !gp->auto_mean_tensor) {
+  if (d_var ? !gp->auto_var_tensor : !gp->auto_mean_only) {
     gp->last_refined = P;
     return gp_predict_fp64(ctx, gp, dXn, P, d_mean, d_var);
   }
@@ -742,7 +749,7 @@ int dmo_gp_auto_info(dmo_ctx* ctx, dmo_gp* gp, int* mean_tensor, int* var_tensor
   DMO_CUDA(cudaSetDevice(ctx->device));
   DMO_REQUIRE(gp, "gp_auto_info: null model");
   DMO_TRY(gp_calibrate(ctx, gp));
-  if (mean_tensor) *mean_tensor = (gp->auto_mean_tensor ? 1 : 0) | (gp->mean_from_d ? 2 : 0);
+  if (mean_tensor) *mean_tensor = (gp->auto_mean_tensor ? 1 : 0) | (gp->mean_from_d ? 2 : 0) | (gp->auto_mean_only ? 4 : 0);
   if (var_tensor) *var_tensor = gp->auto_var_tensor ? 1 : 0;
   if (mean_err) *mean_err = gp->mean_from_d ? fmax(gp->cal_mean_err_d, gp->auto_mean_tensor ? gp->cal_mean_err : 0.0) : gp->cal_mean_err;
   if (var_err) *var_err = gp->cal_var_err;

@@ -23,6 +23,7 @@ struct dmo_gp {
   DevBuf<uint16_t> Lhi, Llo;  // (M, Npad, Npad) fp16 split of the row-scaled L^-1
   DevBuf<float> Lscale;       // (M, Npad) 1 / (row scale * K_* scale), powers of two
   DevBuf<int> Kexp;           // (M,) K_* scaling exponents
+  DevBuf<float> Xtf;          // (Npad, 32) float copy of Xt, zero padded (mean-only direct kernel, d <= 32); built lazily
   // whitened targets z = L^-1 y_n = L' alpha (float), zero padded to Npad: with D = K_* L^-T the posterior mean is D z, so
   // the variance contraction's epilogue delivers it from the accumulator it already reads (gp_tensor.cu)
   DevBuf<float> Zf;           // (M, Npad); empty when the model was created from L^-1 (factor_is_inverse)
@@ -34,6 +35,8 @@ struct dmo_gp {
   double cal_mean_err_d = 0.0;    // probe error of the mean taken from the contraction (D z)
   bool auto_var_tensor = false;   // split-fp16 variance holds 1e-5 * prior on the probes (with margin)
   double cal_mean_err = 0.0;      // max |mean_t - mean_64| / max(|mean_64|, y_std) over the probes
+  bool auto_mean_only = false;    // the mean-only tensor-path call (direct kernel where it applies) holds 1e-5 on the probes
+  double cal_mean_err_only = 0.0; // its probe error
   double cal_var_err = 0.0;       // max |var_t - var_64| / prior over the probes
   double refine_theta = 1.0;      // rows with var_t < theta * prior are recomputed in float64
   int64_t last_refined = 0;       // rows recomputed by the last DMO_GP_AUTO predict

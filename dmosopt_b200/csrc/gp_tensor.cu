@@ -723,6 +723,138 @@ __global__ void __launch_bounds__(KT_TN)
   }
 }
 
+// Mean-only posterior (what MOASMO.optimize asks for every generation: model.evaluate -> mean, MOASMO.py:107-108): K_* is
+// never written.  A thread owns two candidates (coordinates in registers), the block walks its share of the training
+// points through a shared-memory tile (16-byte broadcast reads, packed fp32 distance loops as in kstar_tensor_kernel),
+// k(x, x_n) * (c alpha_n) is accumulated with packed FFMA over 32 training points and then folded into float64; the
+// partial sums of the blockIdx.x slices are added in a fixed order by mean_finish_tc_kernel (deterministic).
+constexpr int KM_T = 128, KM_Q = 256, KM_NS = 32, KM_D = 32;
+
+__global__ void pad_xt_f32_kernel(const double* __restrict__ Xt, int64_t N, int d, int64_t Npad, float* __restrict__ Xtf) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Npad * KM_D) return;
+  const int64_t n = t / KM_D;
+  const int j = (int)(t % KM_D);
+  Xtf[t] = (n < N && j < d) ? (float)Xt[n * d + j] : 0.f;
+}
+
+template <bool ISO, int MT>
+__global__ void __launch_bounds__(KM_T, 4)
+    gp_mean_direct_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, const float* __restrict__ Xtf, int64_t N,
+                          int64_t Npad, int64_t n_per_block, int d, int kind, const double* __restrict__ inv_ls,
+                          const double* __restrict__ constant, const double* __restrict__ alpha,
+                          double* __restrict__ mpart, int64_t mp_ld) {
+  __shared__ __align__(16) float s_x[KM_NS * KM_D];
+  __shared__ float s_al[MT * KM_NS];  // c_m * alpha_m[n] of the tile (zero beyond N)
+  __shared__ __align__(16) float s_il[MT * KM_D];
+  const int t = threadIdx.x;
+  const int64_t qa = (int64_t)blockIdx.y * KM_Q + t, qb = qa + KM_T;  // candidate rows inside this chunk
+  float2 ca[KM_D / 2], cb[KM_D / 2];
+  {
+    const int64_t pa = p_base + qa, pb = p_base + qb;
+#pragma unroll
+    for (int j = 0; j < KM_D / 2; ++j) {
+      const int j0 = 2 * j, j1 = 2 * j + 1;
+      ca[j] = make_float2((pa < P && j0 < d) ? (float)Xn[pa * d + j0] : 0.f, (pa < P && j1 < d) ? (float)Xn[pa * d + j1] : 0.f);
+      cb[j] = make_float2((pb < P && j0 < d) ? (float)Xn[pb * d + j0] : 0.f, (pb < P && j1 < d) ? (float)Xn[pb * d + j1] : 0.f);
+    }
+  }
+  for (int i = t; i < MT * KM_D; i += KM_T) {
+    const int m = i / KM_D, j = i % KM_D;
+    s_il[i] = j < d ? (float)inv_ls[m * d + j] : 0.f;
+  }
+  double sum_a[MT], sum_b[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) sum_a[m] = sum_b[m] = 0.0;
+  const int64_t n_begin = (int64_t)blockIdx.x * n_per_block;
+  const int64_t n_end = n_begin + n_per_block < Npad ? n_begin + n_per_block : Npad;
+  for (int64_t n0 = n_begin; n0 < n_end; n0 += KM_NS) {
+    __syncthreads();  // the previous tile has been consumed
+    {
+      const float4* src = reinterpret_cast<const float4*>(Xtf + n0 * KM_D);
+      float4* dst = reinterpret_cast<float4*>(s_x);
+      dst[t] = src[t];
+      dst[t + KM_T] = src[t + KM_T];
+    }
+    for (int i = t; i < MT * KM_NS; i += KM_T) {
+      const int m = i / KM_NS;
+      const int64_t n = n0 + i % KM_NS;
+      s_al[i] = n < N ? (float)(constant[m] * alpha[(int64_t)m * N + n]) : 0.f;
+    }
+    __syncthreads();
+    if (ISO) {  // one squared distance per (candidate, training point), scaled per objective
+      float2 acc[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) acc[m] = make_float2(0.f, 0.f);
+#pragma unroll 2
+      for (int i = 0; i < KM_NS; ++i) {
+        const float4* xr = reinterpret_cast<const float4*>(s_x + i * KM_D);
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;  // independent chains
+#pragma unroll
+        for (int j = 0; j < KM_D / 4; ++j) {
+          const float4 c = xr[j];
+          const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
+          const float2 da0 = __fadd2_rn(c01, make_float2(-ca[2 * j].x, -ca[2 * j].y));
+          const float2 db0 = __fadd2_rn(c01, make_float2(-cb[2 * j].x, -cb[2 * j].y));
+          const float2 da1 = __fadd2_rn(c23, make_float2(-ca[2 * j + 1].x, -ca[2 * j + 1].y));
+          const float2 db1 = __fadd2_rn(c23, make_float2(-cb[2 * j + 1].x, -cb[2 * j + 1].y));
+          a0 = __ffma2_rn(da0, da0, a0);
+          b0 = __ffma2_rn(db0, db0, b0);
+          a1 = __ffma2_rn(da1, da1, a1);
+          b1 = __ffma2_rn(db1, db1, b1);
+        }
+        const float2 r2 = make_float2((a0.x + a0.y) + (a1.x + a1.y), (b0.x + b0.y) + (b1.x + b1.y));
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const float il = s_il[m * KM_D];
+          const float il2 = il * il;
+          const float al = s_al[m * KM_NS + i];
+          acc[m] = __ffma2_rn(stationary2_f(__fmul2_rn(r2, make_float2(il2, il2)), kind), make_float2(al, al), acc[m]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        sum_a[m] += (double)acc[m].x;
+        sum_b[m] += (double)acc[m].y;
+      }
+    } else {  // one length scale per dimension and objective: a pass over the tile per objective
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float4* il4 = reinterpret_cast<const float4*>(s_il + m * KM_D);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int i = 0; i < KM_NS; ++i) {
+          const float4* xr = reinterpret_cast<const float4*>(s_x + i * KM_D);
+          float2 aa = make_float2(0.f, 0.f), bb = aa;
+#pragma unroll
+          for (int j = 0; j < KM_D / 4; ++j) {
+            const float4 c = xr[j], il = il4[j];
+            const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
+            const float2 i01 = make_float2(il.x, il.y), i23 = make_float2(il.z, il.w);
+            const float2 da0 = __fmul2_rn(__fadd2_rn(c01, make_float2(-ca[2 * j].x, -ca[2 * j].y)), i01);
+            const float2 db0 = __fmul2_rn(__fadd2_rn(c01, make_float2(-cb[2 * j].x, -cb[2 * j].y)), i01);
+            const float2 da1 = __fmul2_rn(__fadd2_rn(c23, make_float2(-ca[2 * j + 1].x, -ca[2 * j + 1].y)), i23);
+            const float2 db1 = __fmul2_rn(__fadd2_rn(c23, make_float2(-cb[2 * j + 1].x, -cb[2 * j + 1].y)), i23);
+            aa = __ffma2_rn(da0, da0, aa);
+            bb = __ffma2_rn(db0, db0, bb);
+            aa = __ffma2_rn(da1, da1, aa);
+            bb = __ffma2_rn(db1, db1, bb);
+          }
+          const float al = s_al[m * KM_NS + i];
+          acc = __ffma2_rn(stationary2_f(make_float2(aa.x + aa.y, bb.x + bb.y), kind), make_float2(al, al), acc);
+        }
+        sum_a[m] += (double)acc.x;
+        sum_b[m] += (double)acc.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    mpart[((int64_t)blockIdx.x * MT + m) * mp_ld + qa] = sum_a[m];
+    mpart[((int64_t)blockIdx.x * MT + m) * mp_ld + qb] = sum_b[m];
+  }
+}
+
 // mean[p][m] = y_std * sum_n K_*[p][n] alpha[n] + y_mean from the split K_* (hi + lo = 22 bits): HBM-bound pass,
 // one warp per (objective, candidate) row, float64 accumulation in a fixed order
 __global__ void mean_split_kernel(const uint16_t* __restrict__ Kh, const uint16_t* __restrict__ Kl, int64_t Pc, int64_t N,
@@ -830,6 +962,54 @@ int prepare_tensor_state(dmo_ctx* ctx, dmo_gp* gp) {
   return DMO_OK;
 }
 
+// mean-only predict without K_* in memory (d <= 32, M <= 6): see gp_mean_direct_kernel
+int gp_mean_direct(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean) {
+  const int64_t N = gp->N, Npad = gp->Npad;
+  const int M = gp->M, d = gp->d;
+  if (!gp->Xtf.p) {
+    DMO_TRY(gp->Xtf.alloc(ctx, (size_t)Npad * KM_D));
+    DMO_LAUNCH(pad_xt_f32_kernel, (unsigned)ceil_div(Npad * KM_D, 256), 256, 0, gp->Xt.p, N, d, Npad, gp->Xtf.p);
+  }
+  const int64_t n_qb = ceil_div(P, KM_Q);
+  // slices of the training set per candidate block: enough blocks for ~4 resident CTAs per SM, at least 256 points each
+  int64_t nsplit = ceil_div((int64_t)4 * ctx->sm_count, n_qb);
+  const int64_t max_split = Npad / 256;
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  const int64_t n_per_block = ceil_div(ceil_div(Npad, nsplit), KM_NS) * KM_NS;
+  nsplit = ceil_div(Npad, n_per_block);
+  const int64_t ld = n_qb * KM_Q;
+  DevBuf<double> mpart;
+  DMO_TRY(mpart.alloc(ctx, (size_t)nsplit * M * ld));
+  dim3 grid((unsigned)nsplit, (unsigned)n_qb);
+  {
+    ProfileScope ps_(ctx, "gp_mean_direct");
+#define KM_LAUNCH(ISO_, MT_)                                                                                            \
+  DMO_LAUNCH((gp_mean_direct_kernel<ISO_, MT_>), grid, KM_T, 0, dXn, P, (int64_t)0, gp->Xtf.p, N, Npad, n_per_block, d, \
+             gp->kernel, gp->inv_ls.p, gp->constant.p, gp->alpha.p, mpart.p, ld)
+#define KM_SWITCH(ISO_)        \
+  switch (M) {                 \
+    case 1: KM_LAUNCH(ISO_, 1); break; \
+    case 2: KM_LAUNCH(ISO_, 2); break; \
+    case 3: KM_LAUNCH(ISO_, 3); break; \
+    case 4: KM_LAUNCH(ISO_, 4); break; \
+    case 5: KM_LAUNCH(ISO_, 5); break; \
+    default: KM_LAUNCH(ISO_, 6); break; \
+  }
+    if (gp->isotropic) {
+      KM_SWITCH(true)
+    } else {
+      KM_SWITCH(false)
+    }
+#undef KM_SWITCH
+#undef KM_LAUNCH
+  }
+  DMO_LAUNCH(mean_finish_tc_kernel, (unsigned)ceil_div(P * M, 256), 256, 0, mpart.p, (int)nsplit, P, ld, M, gp->ymean.p,
+             gp->ystd.p, (int64_t)0, d_mean);
+  DMO_CHECK_LAUNCH();
+  return DMO_OK;  // mpart is released in stream order
+}
+
 }  // namespace
 
 int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean, double* d_var, bool mean_from_d) {
@@ -838,6 +1018,8 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   DMO_REQUIRE(M <= 16, "gp_predict(tensor): at most 16 objectives per model (got %d)", M);
   DMO_REQUIRE(d <= 64, "gp_predict(tensor): at most 64 input dimensions (got %d); use DMO_GP_FP64", d);
   DMO_REQUIRE(Npad % TN == 0, "gp_predict(tensor): internal padding error");
+  if (!d_var && d <= KM_D && M <= 6 && !(getenv("DMO_GP_MEAN_DIRECT") && atoi(getenv("DMO_GP_MEAN_DIRECT")) == 0))
+    return gp_mean_direct(ctx, gp, dXn, P, d_mean);  // nothing but the mean is wanted: K_* stays in registers
   DMO_TRY(prepare_tensor_state(ctx, gp));
   // kernel version: 3 (default) = equal-cost paired row blocks in L2-friendly order, overlapped with the K_* producer;
   // 2 = previous schedule, K_* / mean / variance back to back on one stream (DMO_GP_TC=2, kept for comparison)

@@ -343,6 +343,39 @@ def test_gp_predict_tensor_path(L, N, d, M, P):
     h.close()
 
 
+@pytest.mark.parametrize("N,d,M,P,ard,kind", [(300, 30, 3, 200, False, "matern"), (1000, 12, 2, 517, True, "matern"), (4096, 30, 3, 5000, False, "matern"),
+                                               (777, 22, 5, 1300, True, "rbf"), (513, 2, 1, 33, False, "rbf"), (2048, 24, 6, 4096, False, "matern")])
+def test_gp_mean_only_kernel(L, N, d, M, P, ard, kind):
+    """Predicts without variance (GPR_Matern.evaluate, once per generation in MOASMO.optimize) take gp_mean_direct_kernel:
+    K_* is never written, kernel values in fp32, float64 partial sums.  Against the oracle: 1e-5 of max(|mean|, y_std);
+    isotropic and per-dimension length scales, both kernels, ragged P and N, 1 .. 6 objectives."""
+    rng = np.random.default_rng(N + P)
+    xlb, xub = np.zeros(d), np.ones(d)
+    Xtr = rng.random((N, d))
+    Ytr = np.column_stack([np.sin(3 * Xtr[:, : min(4, d)].sum(axis=1) + k) + Xtr[:, (1 + k) % d] ** 2 for k in range(M)])
+    ls = [(0.3 + 0.5 * rng.random(d)) if ard else 0.4 + 0.05 * m for m in range(M)]
+    knd = gp.MATERN52 if kind == "matern" else gp.RBF
+    st = gp.fit_fixed(Xtr, Ytr, xlb, xub, [1.0 + 0.5 * m for m in range(M)], ls, 1e-5, kind=knd)
+    h = L.GPHandle(st.X_train, np.stack([o.alpha for o in st.objectives]), np.stack([o.L for o in st.objectives]), [o.constant for o in st.objectives],
+                   [np.broadcast_to(np.asarray(o.length_scale, dtype=np.float64), (d,)) for o in st.objectives], [o.noise for o in st.objectives],
+                   [o.y_mean for o in st.objectives], [o.y_std for o in st.objectives], xlb, xub, kernel=L.KERNEL_MATERN52 if kind == "matern" else L.KERNEL_RBF)
+    X = _candidates_with_near_training_rows(rng, Xtr, P, d)
+    mean_o, _ = gp.predict(st, X)
+    ystd, _ = _state_scales(st)
+    mean_t, none = h.predict(X, return_var=False, precision=L.GP_TENSOR)
+    assert none is None
+    em = np.max(np.abs(mean_t - mean_o) / np.maximum(np.abs(mean_o), ystd))
+    mean_a, _ = h.predict(X, return_var=False, precision=L.GP_AUTO)
+    ea = np.max(np.abs(mean_a - mean_o) / np.maximum(np.abs(mean_o), ystd))
+    info = h.auto_info()
+    print(f"mean-only N={N} d={d} M={M} ard={ard} {kind}: tensor-path err {em:.2e}, auto err {ea:.2e}, admitted {info['mean_only_tensor']}")
+    assert ea < 1e-5, ea  # whatever the calibration chose holds the bar
+    if info["mean_only_tensor"]:
+        assert em < 1e-5, em
+        assert np.array_equal(mean_a, mean_t)  # same kernel, deterministic order of the partial sums
+    h.close()
+
+
 def _assert_gp_bars(mean, var, mean_o, var_o, ystd, prior, what):
     """The north-star bar as the judge reads it: mean within 1e-5 relative (to max(|mean|, y_std)); variance within
     1e-5 of ITS OWN VALUE wherever it exceeds 1e-3 of the prior variance, within 1e-5 of the prior below that."""
