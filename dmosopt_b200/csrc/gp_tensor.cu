@@ -855,6 +855,169 @@ __global__ void __launch_bounds__(KM_T, 4)
   }
 }
 
+// K_* producer fused with the mean (predicts with variance): the layout of gp_mean_direct_kernel (a thread owns two
+// candidates) with 16-point tiles; besides accumulating k * (c alpha) the block stages the scaled hi / lo fp16 split of
+// its 256 x 16 tile per objective in shared memory (rows of 10 words: 8-byte stores of four consecutive training points
+// are conflict free) and writes it out as full 32-byte sectors.  Replaces kstar_tensor_kernel + mean_split_kernel
+// (1.46 + 0.72 ms at the BASELINE shape): K_* is written once and not read back for the mean.
+constexpr int KF_NS = 16, KF_LD = 10;
+
+template <bool ISO, int MT>
+__global__ void __launch_bounds__(KM_T, 3)
+    kstar_mean_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, const float* __restrict__ Xtf, int64_t N,
+                      int64_t Npad, int64_t n_per_block, int d, int kind, const double* __restrict__ inv_ls,
+                      const double* __restrict__ constant, const int* __restrict__ k_exp, const double* __restrict__ alpha,
+                      int64_t plane, uint16_t* __restrict__ Kh, uint16_t* __restrict__ Kl, double* __restrict__ mpart,
+                      int64_t mp_ld) {
+  extern __shared__ __align__(16) uint32_t kf_stage[];  // [MT][2][KM_Q][KF_LD] words: (objective, hi / lo, candidate row)
+  __shared__ __align__(16) float s_x[KF_NS * KM_D];
+  __shared__ float s_al[MT * KF_NS];  // c_m * alpha_m[n] of the tile (zero beyond N)
+  __shared__ float s_live[KF_NS];     // 1 for a training point, 0 for the padding columns (written as zeros)
+  __shared__ __align__(16) float s_il[MT * KM_D];
+  __shared__ float s_c[MT];           // c_m * 2^kexp_m: scale of the stored K_*
+  const int t = threadIdx.x;
+  const int64_t q_base = (int64_t)blockIdx.y * KM_Q;
+  const int64_t qa = q_base + t, qb = qa + KM_T;
+  float2 ca[KM_D / 2], cb[KM_D / 2];
+  {
+    const int64_t pa = p_base + qa, pb = p_base + qb;
+#pragma unroll
+    for (int j = 0; j < KM_D / 2; ++j) {
+      const int j0 = 2 * j, j1 = 2 * j + 1;
+      ca[j] = make_float2((pa < P && j0 < d) ? (float)Xn[pa * d + j0] : 0.f, (pa < P && j1 < d) ? (float)Xn[pa * d + j1] : 0.f);
+      cb[j] = make_float2((pb < P && j0 < d) ? (float)Xn[pb * d + j0] : 0.f, (pb < P && j1 < d) ? (float)Xn[pb * d + j1] : 0.f);
+    }
+  }
+  for (int i = t; i < MT * KM_D; i += KM_T) {
+    const int m = i / KM_D, j = i % KM_D;
+    s_il[i] = j < d ? (float)inv_ls[m * d + j] : 0.f;
+  }
+  if (t < MT) s_c[t] = scalbnf((float)constant[t], k_exp[t]);
+  double sum_a[MT], sum_b[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) sum_a[m] = sum_b[m] = 0.0;
+  const int64_t n_begin = (int64_t)blockIdx.x * n_per_block;
+  const int64_t n_end = n_begin + n_per_block < Npad ? n_begin + n_per_block : Npad;
+  uint32_t* row_a = kf_stage + (size_t)t * KF_LD;             // + (m * 2 + arr) * KM_Q * KF_LD
+  uint32_t* row_b = kf_stage + (size_t)(t + KM_T) * KF_LD;
+  for (int64_t n0 = n_begin; n0 < n_end; n0 += KF_NS) {
+    __syncthreads();  // the previous tile has been consumed and its stage flushed
+    if (t < KF_NS * KM_D / 4) reinterpret_cast<float4*>(s_x)[t] = reinterpret_cast<const float4*>(Xtf + n0 * KM_D)[t];
+    for (int i = t; i < MT * KF_NS; i += KM_T) {
+      const int m = i / KF_NS;
+      const int64_t n = n0 + i % KF_NS;
+      s_al[i] = n < N ? (float)(constant[m] * alpha[(int64_t)m * N + n]) : 0.f;
+    }
+    if (t < KF_NS) s_live[t] = (n0 + t < N) ? 1.f : 0.f;
+    __syncthreads();
+    float2 acc[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[m] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int i4 = 0; i4 < KF_NS; i4 += 4) {
+      uint32_t wh_a[MT][2], wl_a[MT][2], wh_b[MT][2], wl_b[MT][2];  // four training points -> two half2 words each
+#pragma unroll
+      for (int u2 = 0; u2 < 2; ++u2) {
+        float2 kv[2][MT];  // scaled kernel values of the pair of points (candidates a, b)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = i4 + 2 * u2 + u;
+          const float4* xr = reinterpret_cast<const float4*>(s_x + i * KM_D);
+          float2 r2 = make_float2(0.f, 0.f);
+          if (ISO) {
+            float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+            for (int j = 0; j < KM_D / 4; ++j) {
+              const float4 c = xr[j];
+              const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
+              const float2 da0 = __fadd2_rn(c01, make_float2(-ca[2 * j].x, -ca[2 * j].y));
+              const float2 db0 = __fadd2_rn(c01, make_float2(-cb[2 * j].x, -cb[2 * j].y));
+              const float2 da1 = __fadd2_rn(c23, make_float2(-ca[2 * j + 1].x, -ca[2 * j + 1].y));
+              const float2 db1 = __fadd2_rn(c23, make_float2(-cb[2 * j + 1].x, -cb[2 * j + 1].y));
+              a0 = __ffma2_rn(da0, da0, a0);
+              b0 = __ffma2_rn(db0, db0, b0);
+              a1 = __ffma2_rn(da1, da1, a1);
+              b1 = __ffma2_rn(db1, db1, b1);
+            }
+            r2 = make_float2((a0.x + a0.y) + (a1.x + a1.y), (b0.x + b0.y) + (b1.x + b1.y));
+          }
+          const float live = s_live[i];
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            float2 rr;
+            if (ISO) {
+              const float il = s_il[m * KM_D];
+              const float il2 = il * il;
+              rr = __fmul2_rn(r2, make_float2(il2, il2));
+            } else {
+              const float4* il4 = reinterpret_cast<const float4*>(s_il + m * KM_D);
+              float2 aa = make_float2(0.f, 0.f), bb = aa;
+#pragma unroll
+              for (int j = 0; j < KM_D / 4; ++j) {
+                const float4 c = xr[j], il = il4[j];
+                const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
+                const float2 i01 = make_float2(il.x, il.y), i23 = make_float2(il.z, il.w);
+                const float2 da0 = __fmul2_rn(__fadd2_rn(c01, make_float2(-ca[2 * j].x, -ca[2 * j].y)), i01);
+                const float2 db0 = __fmul2_rn(__fadd2_rn(c01, make_float2(-cb[2 * j].x, -cb[2 * j].y)), i01);
+                const float2 da1 = __fmul2_rn(__fadd2_rn(c23, make_float2(-ca[2 * j + 1].x, -ca[2 * j + 1].y)), i23);
+                const float2 db1 = __fmul2_rn(__fadd2_rn(c23, make_float2(-cb[2 * j + 1].x, -cb[2 * j + 1].y)), i23);
+                aa = __ffma2_rn(da0, da0, aa);
+                bb = __ffma2_rn(db0, db0, bb);
+                aa = __ffma2_rn(da1, da1, aa);
+                bb = __ffma2_rn(db1, db1, bb);
+              }
+              rr = make_float2(aa.x + aa.y, bb.x + bb.y);
+            }
+            const float2 k0 = stationary2_f(rr, kind);
+            const float al = s_al[m * KF_NS + i];
+            acc[m] = __ffma2_rn(k0, make_float2(al, al), acc[m]);
+            const float sc = s_c[m] * live;
+            kv[u][m] = __fmul2_rn(k0, make_float2(sc, sc));  // c * k(r), scaled by 2^kexp (exact); padding columns: 0
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {  // pack (n, n + 1) of one candidate into half2: hi, then lo = value - hi
+          const __half2 ha = __floats2half2_rn(kv[0][m].x, kv[1][m].x), hb = __floats2half2_rn(kv[0][m].y, kv[1][m].y);
+          const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+          const __half2 la = __floats2half2_rn(kv[0][m].x - fa.x, kv[1][m].x - fa.y);
+          const __half2 lb = __floats2half2_rn(kv[0][m].y - fb.x, kv[1][m].y - fb.y);
+          wh_a[m][u2] = *reinterpret_cast<const uint32_t*>(&ha);
+          wl_a[m][u2] = *reinterpret_cast<const uint32_t*>(&la);
+          wh_b[m][u2] = *reinterpret_cast<const uint32_t*>(&hb);
+          wl_b[m][u2] = *reinterpret_cast<const uint32_t*>(&lb);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const size_t oh = (size_t)(m * 2) * KM_Q * KF_LD + (i4 >> 1), ol = oh + (size_t)KM_Q * KF_LD;
+        *reinterpret_cast<uint2*>(row_a + oh) = make_uint2(wh_a[m][0], wh_a[m][1]);
+        *reinterpret_cast<uint2*>(row_a + ol) = make_uint2(wl_a[m][0], wl_a[m][1]);
+        *reinterpret_cast<uint2*>(row_b + oh) = make_uint2(wh_b[m][0], wh_b[m][1]);
+        *reinterpret_cast<uint2*>(row_b + ol) = make_uint2(wl_b[m][0], wl_b[m][1]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      sum_a[m] += (double)acc[m].x;
+      sum_b[m] += (double)acc[m].y;
+    }
+    __syncthreads();  // the tile is staged
+    // flush: 8-byte units, four per 32-byte row segment; a warp writes eight full sectors per instruction
+    for (int g = t; g < MT * 2 * KM_Q * 4; g += KM_T) {
+      const int r = g >> 2, c = g & 3;
+      const int ma = r / KM_Q, q = r - ma * KM_Q;
+      const uint2 v = *reinterpret_cast<const uint2*>(kf_stage + (size_t)r * KF_LD + 2 * c);
+      uint16_t* base = (ma & 1) ? Kl : Kh;
+      *reinterpret_cast<uint2*>(base + (int64_t)(ma >> 1) * plane + (q_base + q) * Npad + n0 + 4 * c) = v;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    mpart[((int64_t)blockIdx.x * MT + m) * mp_ld + qa] = sum_a[m];
+    mpart[((int64_t)blockIdx.x * MT + m) * mp_ld + qb] = sum_b[m];
+  }
+}
+
 // mean[p][m] = y_std * sum_n K_*[p][n] alpha[n] + y_mean from the split K_* (hi + lo = 22 bits): HBM-bound pass,
 // one warp per (objective, candidate) row, float64 accumulation in a fixed order
 __global__ void mean_split_kernel(const uint16_t* __restrict__ Kh, const uint16_t* __restrict__ Kl, int64_t Pc, int64_t N,
@@ -962,6 +1125,27 @@ int prepare_tensor_state(dmo_ctx* ctx, dmo_gp* gp) {
   return DMO_OK;
 }
 
+// Slices of the training set per candidate block for the two kernels above: the grid (slices x candidate blocks) should
+// fill whole waves of `slots` resident CTAs; a slice is a multiple of `tile` points and at least 256 of them.
+int64_t pick_slices(int64_t n_qb, int64_t Npad, int tile, int64_t slots, int64_t* n_per_block) {
+  int64_t best = 1;
+  double best_eff = -1.0;
+  *n_per_block = Npad;
+  const int64_t smax = Npad / 256 > 1 ? Npad / 256 : 1;
+  for (int64_t sp = 1; sp <= smax; ++sp) {
+    const int64_t npb = ceil_div(ceil_div(Npad, sp), (int64_t)tile) * tile;
+    const int64_t ns = ceil_div(Npad, npb);
+    const int64_t blocks = ns * n_qb;
+    const double eff = (double)blocks / (double)(ceil_div(blocks, slots) * slots);
+    if (eff > best_eff + 0.02) {  // fewer slices (fewer partial sums) unless more of them fill the waves visibly better
+      best_eff = eff;
+      best = ns;
+      *n_per_block = npb;
+    }
+  }
+  return best;
+}
+
 // mean-only predict without K_* in memory (d <= 32, M <= 6): see gp_mean_direct_kernel
 int gp_mean_direct(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean) {
   const int64_t N = gp->N, Npad = gp->Npad;
@@ -971,13 +1155,8 @@ int gp_mean_direct(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, doubl
     DMO_LAUNCH(pad_xt_f32_kernel, (unsigned)ceil_div(Npad * KM_D, 256), 256, 0, gp->Xt.p, N, d, Npad, gp->Xtf.p);
   }
   const int64_t n_qb = ceil_div(P, KM_Q);
-  // slices of the training set per candidate block: enough blocks for ~4 resident CTAs per SM, at least 256 points each
-  int64_t nsplit = ceil_div((int64_t)4 * ctx->sm_count, n_qb);
-  const int64_t max_split = Npad / 256;
-  if (nsplit > max_split) nsplit = max_split;
-  if (nsplit < 1) nsplit = 1;
-  const int64_t n_per_block = ceil_div(ceil_div(Npad, nsplit), KM_NS) * KM_NS;
-  nsplit = ceil_div(Npad, n_per_block);
+  int64_t n_per_block = Npad;
+  const int64_t nsplit = pick_slices(n_qb, Npad, KM_NS, (int64_t)4 * ctx->sm_count, &n_per_block);
   const int64_t ld = n_qb * KM_Q;
   DevBuf<double> mpart;
   DMO_TRY(mpart.alloc(ctx, (size_t)nsplit * M * ld));
@@ -1066,6 +1245,15 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   DMO_CUDA(cudaFuncSetAttribute(v2::gp_var_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::GEMM_SMEM2));
   DMO_CUDA(cudaFuncSetAttribute(v3::gp_var_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::GEMM_SMEM2));
   const int64_t kplane = Pc_alloc * Npad;
+  // K_* producer fused with the mean (d <= 32, M <= 6; DMO_GP_FUSED=0 keeps kstar_tensor_kernel + mean_split_kernel)
+  // (per-dimension length scales with more than two objectives spill in the fused kernel: they keep the two-kernel route)
+  const bool fused = !overlap && !mean_from_d && !(dbg & 8) && d <= KM_D && M <= 6 && (gp->isotropic || M <= 2) &&
+                     !(getenv("DMO_GP_FUSED") && atoi(getenv("DMO_GP_FUSED")) == 0);
+  DevBuf<double> mpart;
+  if (fused && !gp->Xtf.p) {
+    DMO_TRY(gp->Xtf.alloc(ctx, (size_t)Npad * KM_D));
+    DMO_LAUNCH(pad_xt_f32_kernel, (unsigned)ceil_div(Npad * KM_D, 256), 256, 0, gp->Xt.p, N, d, Npad, gp->Xtf.p);
+  }
   // producer side (K_* and the mean) on the second stream when overlapping, else in line
   cudaStream_t ps = overlap ? ctx->aux : ctx->stream;
   if (overlap) {
@@ -1082,36 +1270,73 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
       DMO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
       DMO_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
     }
-    {
-      ProfileScope ps_(ctx, "gp_kstar", ps);
-      const int dmax = d <= 32 ? 32 : 64;
-      size_t smem = (size_t)(KT_TP * dmax + M * dmax + M) * sizeof(float);
-#define KSTAR_LAUNCH(ISO_, DM_)                                                                                   \
-  DMO_LAUNCH_ON(ps, (kstar_tensor_kernel<ISO_, DM_>), gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M,    \
-                gp->kernel, gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p,                    \
-                (use_flags && d_var) ? rdy : nullptr)
-      if (gp->isotropic) {
-        if (d <= 32)
-          KSTAR_LAUNCH(true, 32);
-        else
-          KSTAR_LAUNCH(true, 64);
-      } else {
-        if (d <= 32)
-          KSTAR_LAUNCH(false, 32);
-        else
-          KSTAR_LAUNCH(false, 64);
+    if (fused) {
+      // K_* and the mean from one kernel (kstar_mean_kernel): K_* is written once and never read back for the mean
+      int64_t n_per_block = Npad;
+      const int64_t n_qb = Pcpad / KM_Q;
+      const int64_t nsplit = pick_slices(n_qb, Npad, KF_NS, (int64_t)3 * ctx->sm_count, &n_per_block);
+      DMO_TRY(mpart.alloc(ctx, (size_t)nsplit * M * Pcpad));
+      dim3 gf((unsigned)nsplit, (unsigned)n_qb);
+      const size_t smem = (size_t)M * 2 * KM_Q * KF_LD * sizeof(uint32_t);
+      {
+        ProfileScope ps_(ctx, "gp_kstar");
+#define KF_LAUNCH(ISO_, MT_)                                                                                               \
+  do {                                                                                                                     \
+    DMO_CUDA(cudaFuncSetAttribute(kstar_mean_kernel<ISO_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    DMO_LAUNCH((kstar_mean_kernel<ISO_, MT_>), gf, KM_T, smem, dXn, P, p_base, gp->Xtf.p, N, Npad, n_per_block, d,          \
+               gp->kernel, gp->inv_ls.p, gp->constant.p, gp->Kexp.p, gp->alpha.p, kplane, Kh.p, Kl.p, mpart.p, Pcpad);       \
+  } while (0)
+#define KF_SWITCH(ISO_)                  \
+  switch (M) {                           \
+    case 1: KF_LAUNCH(ISO_, 1); break;   \
+    case 2: KF_LAUNCH(ISO_, 2); break;   \
+    case 3: KF_LAUNCH(ISO_, 3); break;   \
+    case 4: KF_LAUNCH(ISO_, 4); break;   \
+    case 5: KF_LAUNCH(ISO_, 5); break;   \
+    default: KF_LAUNCH(ISO_, 6); break;  \
+  }
+        if (gp->isotropic) {
+          KF_SWITCH(true)
+        } else {
+          KF_SWITCH(false)
+        }
+#undef KF_SWITCH
+#undef KF_LAUNCH
       }
-#undef KSTAR_LAUNCH
-    }
-    if (overlap && (dbg & 4)) {  // diagnostics: the contraction waits for the whole K_* kernel by event, the mean still overlaps
-      DMO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->aux));
-      DMO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0));
-    }
-    if (!(dbg & 8) && !mean_from_d) {
-      ProfileScope ps_(ctx, "gp_mean", ps);
-      DMO_LAUNCH_ON(ps, mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane,
-                    M, gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
-    }
+      DMO_LAUNCH(mean_finish_tc_kernel, (unsigned)ceil_div(Pc * M, 256), 256, 0, mpart.p, (int)nsplit, Pc, Pcpad, M, gp->ymean.p,
+                 gp->ystd.p, p_base, d_mean);
+    } else {
+    {
+        ProfileScope ps_(ctx, "gp_kstar", ps);
+        const int dmax = d <= 32 ? 32 : 64;
+        size_t smem = (size_t)(KT_TP * dmax + M * dmax + M) * sizeof(float);
+  #define KSTAR_LAUNCH(ISO_, DM_)                                                                                   \
+    DMO_LAUNCH_ON(ps, (kstar_tensor_kernel<ISO_, DM_>), gk, KT_TN, smem, dXn, P, p_base, Pcpad, gp->Xt.p, N, d, M,    \
+                  gp->kernel, gp->inv_ls.p, gp->constant.p, gp->Kexp.p, Npad, kplane, Kh.p, Kl.p,                    \
+                  (use_flags && d_var) ? rdy : nullptr)
+        if (gp->isotropic) {
+          if (d <= 32)
+            KSTAR_LAUNCH(true, 32);
+          else
+            KSTAR_LAUNCH(true, 64);
+        } else {
+          if (d <= 32)
+            KSTAR_LAUNCH(false, 32);
+          else
+            KSTAR_LAUNCH(false, 64);
+        }
+  #undef KSTAR_LAUNCH
+      }
+      if (overlap && (dbg & 4)) {  // diagnostics: the contraction waits for the whole K_* kernel by event, the mean still overlaps
+        DMO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->aux));
+        DMO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0));
+      }
+      if (!(dbg & 8) && !mean_from_d) {
+        ProfileScope ps_(ctx, "gp_mean", ps);
+        DMO_LAUNCH_ON(ps, mean_split_kernel, (unsigned)ceil_div(Pc * M * 32, 256), 256, 0, Kh.p, Kl.p, Pc, N, Npad, kplane,
+                      M, gp->Kexp.p, gp->alpha.p, gp->ymean.p, gp->ystd.p, p_base, d_mean);
+      }
+}
     if (overlap) DMO_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
     if (d_var && version == 3) {
       v3::GemmParams3 prm;
