@@ -24,6 +24,7 @@ struct dmo_gp {
   DevBuf<float> Lscale;       // (M, Npad) 1 / (row scale * K_* scale), powers of two
   DevBuf<int> Kexp;           // (M,) K_* scaling exponents
   DevBuf<float> Xtf;          // (Npad, 32) float copy of Xt, zero padded (mean-only direct kernel, d <= 32); built lazily
+  DevBuf<float> CAf;          // (M, Npad) c_m * alpha_m as float, zero padded (fused K_* + mean kernel); built with Xtf
   // whitened targets z = L^-1 y_n = L' alpha (float), zero padded to Npad: with D = K_* L^-T the posterior mean is D z, so
   // the variance contraction's epilogue delivers it from the accumulator it already reads (gp_tensor.cu)
   DevBuf<float> Zf;           // (M, Npad); empty when the model was created from L^-1 (factor_is_inverse)

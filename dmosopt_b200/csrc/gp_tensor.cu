@@ -738,6 +738,15 @@ __global__ void pad_xt_f32_kernel(const double* __restrict__ Xt, int64_t N, int 
   Xtf[t] = (n < N && j < d) ? (float)Xt[n * d + j] : 0.f;
 }
 
+__global__ void pad_calpha_f32_kernel(const double* __restrict__ alpha, const double* __restrict__ constant, int64_t N, int M,
+                                      int64_t Npad, float* __restrict__ CAf) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)M * Npad) return;
+  const int m = (int)(t / Npad);
+  const int64_t n = t - (int64_t)m * Npad;
+  CAf[t] = n < N ? (float)(constant[m] * alpha[(int64_t)m * N + n]) : 0.f;
+}
+
 template <bool ISO, int MT>
 __global__ void __launch_bounds__(KM_T, 4)
     gp_mean_direct_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, const float* __restrict__ Xtf, int64_t N,
@@ -866,7 +875,7 @@ template <bool ISO, int MT>
 __global__ void __launch_bounds__(KM_T, 3)
     kstar_mean_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, const float* __restrict__ Xtf, int64_t N,
                       int64_t Npad, int64_t n_per_block, int d, int kind, const double* __restrict__ inv_ls,
-                      const double* __restrict__ constant, const int* __restrict__ k_exp, const double* __restrict__ alpha,
+                      const double* __restrict__ constant, const int* __restrict__ k_exp, const float* __restrict__ CAf,
                       int64_t plane, uint16_t* __restrict__ Kh, uint16_t* __restrict__ Kl, double* __restrict__ mpart,
                       int64_t mp_ld) {
   extern __shared__ __align__(16) uint32_t kf_stage[];  // [MT][2][KM_Q][KF_LD] words: (objective, hi / lo, candidate row)
@@ -900,16 +909,22 @@ __global__ void __launch_bounds__(KM_T, 3)
   const int64_t n_end = n_begin + n_per_block < Npad ? n_begin + n_per_block : Npad;
   uint32_t* row_a = kf_stage + (size_t)t * KF_LD;             // + (m * 2 + arr) * KM_Q * KF_LD
   uint32_t* row_b = kf_stage + (size_t)(t + KM_T) * KF_LD;
+  // the next tile's training coordinates (one float4 per thread: KF_NS * KM_D / 4 == KM_T) and c * alpha values travel
+  // through registers while the current tile is being worked on: no global-load latency between two barriers
+  static_assert(KF_NS * KM_D / 4 == KM_T && 6 * KF_NS <= KM_T, "tile prefetch mapping");
+  float4 px = reinterpret_cast<const float4*>(Xtf + n_begin * KM_D)[t];
+  float pal = t < MT * KF_NS ? CAf[(int64_t)(t / KF_NS) * Npad + n_begin + t % KF_NS] : 0.f;
+  __syncthreads();  // s_il, s_c
+  reinterpret_cast<float4*>(s_x)[t] = px;
+  if (t < MT * KF_NS) s_al[t] = pal;
+  if (t < KF_NS) s_live[t] = (n_begin + t < N) ? 1.f : 0.f;
+  __syncthreads();
   for (int64_t n0 = n_begin; n0 < n_end; n0 += KF_NS) {
-    __syncthreads();  // the previous tile has been consumed and its stage flushed
-    if (t < KF_NS * KM_D / 4) reinterpret_cast<float4*>(s_x)[t] = reinterpret_cast<const float4*>(Xtf + n0 * KM_D)[t];
-    for (int i = t; i < MT * KF_NS; i += KM_T) {
-      const int m = i / KF_NS;
-      const int64_t n = n0 + i % KF_NS;
-      s_al[i] = n < N ? (float)(constant[m] * alpha[(int64_t)m * N + n]) : 0.f;
+    const bool more = n0 + KF_NS < n_end;
+    if (more) {  // in flight during the tile's arithmetic
+      px = reinterpret_cast<const float4*>(Xtf + (n0 + KF_NS) * KM_D)[t];
+      if (t < MT * KF_NS) pal = CAf[(int64_t)(t / KF_NS) * Npad + n0 + KF_NS + t % KF_NS];
     }
-    if (t < KF_NS) s_live[t] = (n0 + t < N) ? 1.f : 0.f;
-    __syncthreads();
     float2 acc[MT];
 #pragma unroll
     for (int m = 0; m < MT; ++m) acc[m] = make_float2(0.f, 0.f);
@@ -1001,15 +1016,30 @@ __global__ void __launch_bounds__(KM_T, 3)
       sum_a[m] += (double)acc[m].x;
       sum_b[m] += (double)acc[m].y;
     }
-    __syncthreads();  // the tile is staged
-    // flush: 8-byte units, four per 32-byte row segment; a warp writes eight full sectors per instruction
-    for (int g = t; g < MT * 2 * KM_Q * 4; g += KM_T) {
-      const int r = g >> 2, c = g & 3;
-      const int ma = r / KM_Q, q = r - ma * KM_Q;
-      const uint2 v = *reinterpret_cast<const uint2*>(kf_stage + (size_t)r * KF_LD + 2 * c);
-      uint16_t* base = (ma & 1) ? Kl : Kh;
-      *reinterpret_cast<uint2*>(base + (int64_t)(ma >> 1) * plane + (q_base + q) * Npad + n0 + 4 * c) = v;
+    __syncthreads();  // the tile is staged, its inputs have been consumed
+    // flush: 8-byte units, four per 32-byte row segment (a warp writes eight full sectors per instruction); thread t
+    // always moves unit t & 3 of rows (t >> 2) + 32 k, so every offset below is a compile-time constant or one add
+    {
+      const uint32_t* src = kf_stage + (size_t)(t >> 2) * KF_LD + 2 * (t & 3);
+      const int64_t row0 = (q_base + (t >> 2)) * Npad + n0 + 4 * (t & 3);
+      const int64_t kstep = (int64_t)32 * Npad;
+#pragma unroll
+      for (int ma = 0; ma < 2 * MT; ++ma) {
+        uint16_t* dst = ((ma & 1) ? Kl : Kh) + (int64_t)(ma >> 1) * plane + row0;
+#pragma unroll
+        for (int k = 0; k < KM_Q / 32; ++k) {
+          const uint2 v = *reinterpret_cast<const uint2*>(src + (size_t)(ma * KM_Q + k * 32) * KF_LD);
+          *reinterpret_cast<uint2*>(dst) = v;
+          dst += kstep;
+        }
+      }
     }
+    if (more) {  // the next tile's inputs, from the registers filled above
+      reinterpret_cast<float4*>(s_x)[t] = px;
+      if (t < MT * KF_NS) s_al[t] = pal;
+      if (t < KF_NS) s_live[t] = (n0 + KF_NS + t < N) ? 1.f : 0.f;
+    }
+    __syncthreads();  // stage drained, next inputs in place
   }
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
@@ -1125,6 +1155,19 @@ int prepare_tensor_state(dmo_ctx* ctx, dmo_gp* gp) {
   return DMO_OK;
 }
 
+// float copies of the training inputs and of c * alpha, zero padded to Npad (once per model)
+int prepare_direct_state(dmo_ctx* ctx, dmo_gp* gp) {
+  if (gp->Xtf.p && gp->CAf.p) return DMO_OK;
+  const int64_t N = gp->N, Npad = gp->Npad;
+  DMO_TRY(gp->Xtf.alloc(ctx, (size_t)Npad * KM_D));
+  DMO_TRY(gp->CAf.alloc(ctx, (size_t)gp->M * Npad));
+  DMO_LAUNCH(pad_xt_f32_kernel, (unsigned)ceil_div(Npad * KM_D, 256), 256, 0, gp->Xt.p, N, gp->d, Npad, gp->Xtf.p);
+  DMO_LAUNCH(pad_calpha_f32_kernel, (unsigned)ceil_div((int64_t)gp->M * Npad, 256), 256, 0, gp->alpha.p, gp->constant.p, N, gp->M, Npad,
+             gp->CAf.p);
+  DMO_CHECK_LAUNCH();
+  return DMO_OK;
+}
+
 // Slices of the training set per candidate block for the two kernels above: the grid (slices x candidate blocks) should
 // fill whole waves of `slots` resident CTAs; a slice is a multiple of `tile` points and at least 256 of them.
 int64_t pick_slices(int64_t n_qb, int64_t Npad, int tile, int64_t slots, int64_t* n_per_block) {
@@ -1150,10 +1193,7 @@ int64_t pick_slices(int64_t n_qb, int64_t Npad, int tile, int64_t slots, int64_t
 int gp_mean_direct(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, double* d_mean) {
   const int64_t N = gp->N, Npad = gp->Npad;
   const int M = gp->M, d = gp->d;
-  if (!gp->Xtf.p) {
-    DMO_TRY(gp->Xtf.alloc(ctx, (size_t)Npad * KM_D));
-    DMO_LAUNCH(pad_xt_f32_kernel, (unsigned)ceil_div(Npad * KM_D, 256), 256, 0, gp->Xt.p, N, d, Npad, gp->Xtf.p);
-  }
+  DMO_TRY(prepare_direct_state(ctx, gp));
   const int64_t n_qb = ceil_div(P, KM_Q);
   int64_t n_per_block = Npad;
   const int64_t nsplit = pick_slices(n_qb, Npad, KM_NS, (int64_t)4 * ctx->sm_count, &n_per_block);
@@ -1250,10 +1290,7 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   const bool fused = !overlap && !mean_from_d && !(dbg & 8) && d <= KM_D && M <= 6 && (gp->isotropic || M <= 2) &&
                      !(getenv("DMO_GP_FUSED") && atoi(getenv("DMO_GP_FUSED")) == 0);
   DevBuf<double> mpart;
-  if (fused && !gp->Xtf.p) {
-    DMO_TRY(gp->Xtf.alloc(ctx, (size_t)Npad * KM_D));
-    DMO_LAUNCH(pad_xt_f32_kernel, (unsigned)ceil_div(Npad * KM_D, 256), 256, 0, gp->Xt.p, N, d, Npad, gp->Xtf.p);
-  }
+  if (fused) DMO_TRY(prepare_direct_state(ctx, gp));
   // producer side (K_* and the mean) on the second stream when overlapping, else in line
   cudaStream_t ps = overlap ? ctx->aux : ctx->stream;
   if (overlap) {
@@ -1284,7 +1321,7 @@ int gp_predict_tensor(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, do
   do {                                                                                                                     \
     DMO_CUDA(cudaFuncSetAttribute(kstar_mean_kernel<ISO_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
     DMO_LAUNCH((kstar_mean_kernel<ISO_, MT_>), gf, KM_T, smem, dXn, P, p_base, gp->Xtf.p, N, Npad, n_per_block, d,          \
-               gp->kernel, gp->inv_ls.p, gp->constant.p, gp->Kexp.p, gp->alpha.p, kplane, Kh.p, Kl.p, mpart.p, Pcpad);       \
+               gp->kernel, gp->inv_ls.p, gp->constant.p, gp->Kexp.p, gp->CAf.p, kplane, Kh.p, Kl.p, mpart.p, Pcpad);         \
   } while (0)
 #define KF_SWITCH(ISO_)                  \
   switch (M) {                           \
