@@ -148,10 +148,40 @@ def context(device=None):
         return _ctx
 
 
-def _check(st, what):
+def _check(st, what, ctx=None):
     if st != 0:
-        msg = _lib.dmo_last_error(_ctx)
+        msg = _lib.dmo_last_error(_ctx if ctx is None else ctx)
         raise DmoError(f"{what} failed (status {st}): {msg.decode() if msg else ''}")
+
+
+# Additional contexts on the same GPU (own stream, own scratch): independent sub-problems of one call -- the swarms of an
+# SMPSO update -- are issued from worker threads, one context each, so their latency-bound kernels (the rank chains)
+# overlap on the device.  The C library is not re-entrant per context; different contexts may run concurrently.
+_worker_ctx = []
+_worker_pool = None
+
+
+def worker_context(i):
+    """The i-th worker context on the main context's GPU (created on first use)."""
+    main = context()
+    with _lock:
+        while len(_worker_ctx) <= i:
+            h = _vp()
+            st = load_library().dmo_create(_ctx_device, ctypes.byref(h))
+            if st != 0 or not h.value:
+                raise DmoError(f"dmosopt_b200: dmo_create(device={_ctx_device}) failed for a worker context (status {st})")
+            _worker_ctx.append(h)
+    assert main is not None
+    return _worker_ctx[i]
+
+
+def worker_pool():
+    global _worker_pool
+    if _worker_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _worker_pool = ThreadPoolExecutor(max_workers=8, thread_name_prefix="dmosopt_b200_worker")
+    return _worker_pool
 
 
 def _ptr(a):
@@ -183,7 +213,8 @@ def stream_ptr():
 
 
 def launch_count():
-    return int(load_library().dmo_launch_count(context()))
+    lib = load_library()
+    return int(lib.dmo_launch_count(context())) + sum(int(lib.dmo_launch_count(c)) for c in _worker_ctx)
 
 
 def sm_count():
@@ -205,9 +236,12 @@ def flush_l2():
 
 
 def transfer_bytes():
-    a, b = _c_u64(0), _c_u64(0)
-    _check(load_library().dmo_transfer_bytes(context(), ctypes.byref(a), ctypes.byref(b)), "dmo_transfer_bytes")
-    return int(a.value), int(b.value)
+    h2d = d2h = 0
+    for c in [context()] + list(_worker_ctx):
+        a, b = _c_u64(0), _c_u64(0)
+        _check(load_library().dmo_transfer_bytes(c, ctypes.byref(a), ctypes.byref(b)), "dmo_transfer_bytes")
+        h2d, d2h = h2d + int(a.value), d2h + int(b.value)
+    return h2d, d2h
 
 
 def profile_enable(on=True):
@@ -865,8 +899,28 @@ class SmpsoSwarms:
         perm = np.empty(n, dtype=np.int64)
         po = parm_out if (parm_out.dtype == np.float32 and parm_out.flags.c_contiguous) else np.empty((n, self.d), np.float32)
         oo = obj_out if (obj_out.dtype == np.float32 and obj_out.flags.c_contiguous) else np.empty((n, self.M), np.float32)
-        _check(load_library().dmo_smpso_update(context(), self.parm.ptr, self.obj.ptr, self.vel.ptr, _in(xg), is32, _in(yg), self.swarms, self.pop, self.d,
-                                               self.M, int(metric), _ptr(sc), _ptr(lb), _ptr(ub), _ptr(ranks), _ptr(perm), _ptr(po), _ptr(oo)), "dmo_smpso_update")
+        lib = load_library()
+        if self.swarms > 1 and os.environ.get("DMOSOPT_B200_SMPSO_THREADS", "1") != "0":
+            # the swarms are independent (SMPSO.py:211-228): one worker context and thread per swarm, so the per-swarm
+            # rank chains (latency bound, a fraction of the SMs each) overlap on the device
+            synchronize()  # state and inputs produced on the main context's stream are complete
+            pxg, pyg, psc, prk, ppm, ppo, poo = _in(xg), _in(yg), _ptr(sc), _ptr(ranks), _ptr(perm), _ptr(po), _ptr(oo)
+            plb, pub = _ptr(lb), _ptr(ub)
+            xsz = 4 if is32 else 8
+            pop, d, M = self.pop, self.d, self.M
+
+            def one(p):
+                ctx, off = worker_context(p), p * pop
+                st = lib.dmo_smpso_update(ctx, self.parm.ptr + off * d * 8, self.obj.ptr + off * M * 8, self.vel.ptr + off * d * 8, pxg + off * d * xsz, is32,
+                                          pyg + off * M * 8, 1, pop, d, M, int(metric), psc + p * 64, plb, pub, prk + off * 4, ppm + off * 8,
+                                          ppo + off * d * 4, poo + off * M * 4)
+                return st, ctx
+
+            for st, ctx in list(worker_pool().map(one, range(self.swarms))):
+                _check(st, "dmo_smpso_update", ctx)
+        else:
+            _check(lib.dmo_smpso_update(context(), self.parm.ptr, self.obj.ptr, self.vel.ptr, _in(xg), is32, _in(yg), self.swarms, self.pop, self.d,
+                                        self.M, int(metric), _ptr(sc), _ptr(lb), _ptr(ub), _ptr(ranks), _ptr(perm), _ptr(po), _ptr(oo)), "dmo_smpso_update")
         if po is not parm_out:
             parm_out[...] = po
         if oo is not obj_out:
