@@ -122,7 +122,9 @@ def environmental_selection(local_random, population_parm, population_obj, pop, 
     crowd_dist = np.zeros_like(rank).astype(np.float32)
     selected = np.zeros_like(rank).astype(bool)
 
-    front_1 = np.argwhere(rank == 0).ravel()
+    # rank is sorted: front r is the contiguous index range [bounds[r], bounds[r + 1]) (= np.argwhere(rank == r))
+    bounds = np.searchsorted(rank, np.arange(rmax + 2))
+    front_1 = np.arange(bounds[1])
     ideal_point = np.min(ys[front_1, :], axis=0)
     normalization, p, crowd_dist[front_1] = survival_score(ys, front_1, ideal_point)
     yn[front_1, :] = ys[front_1] / normalization
@@ -130,15 +132,19 @@ def environmental_selection(local_random, population_parm, population_obj, pop, 
     count = len(front_1)
     if count < pop:
         selected[front_1] = True
+        # the reference walks the later fronts one by one (AGEMOEA.py:470-489); their scores are row-wise expressions, so
+        # they are evaluated for all later rows at once (rows past the cut keep a score nobody reads)
+        rest = slice(int(bounds[1]), len(rank))
+        yn[rest] = ys[rest] / normalization
+        with np.errstate(divide="ignore"):
+            crowd_dist[rest] = 1.0 / minkowski_to_point(yn[rest, :], ideal_point, p)
         for r in range(1, rmax + 1):
-            front_r = np.argwhere(rank == r).ravel()
-            yn[front_r] = ys[front_r] / normalization
-            with np.errstate(divide="ignore"):
-                crowd_dist[front_r] = 1.0 / minkowski_to_point(yn[front_r, :], ideal_point, p)
-            if (count + len(front_r)) < pop:
-                selected[front_r] = True
-                count += len(front_r)
+            b0, b1 = int(bounds[r]), int(bounds[r + 1])
+            if (count + (b1 - b0)) < pop:
+                selected[b0:b1] = True
+                count += b1 - b0
             else:
+                front_r = np.arange(b0, b1)
                 sort_keys = []
                 if feasibility_model is not None:
                     sort_keys.append(-feasibility_model.rank(xs[front_r]))

@@ -192,23 +192,39 @@ __global__ void gather_sorted_kernel(const int32_t* __restrict__ rank, const dou
   if (dist_out && dist) dist_out[p] = dist[i];
 }
 
-// ---- duplicates: rows sorted by their first coordinate, each row scans its +-eps window
+// ---- duplicates: rows sorted by a fixed linear projection s = sum_c w_c x_c (w_c in [1, 2)); a row scans the window of
+// rows whose projection can belong to a row within eps.  (A single coordinate is a poor key here: offspring are clipped to
+// the bounds, so thousands of rows share x_0 == lower bound exactly and every one of them would scan all the others.)
+// Rows within distance eps satisfy |s_i - s_j| <= ||w||_2 eps <= 2 sqrt(d) eps, plus the rounding of the two sums, which
+// is bounded through the absolute projection t = sum_c w_c |x_c|; identical rows have identical projections.
+__device__ __forceinline__ double dup_weight(int c) { return 1.0 + (double)(((uint32_t)c * 2654435761u >> 8) & 0xFFFFu) * (1.0 / 65536.0); }
+__device__ __forceinline__ double dup_projection(const double* __restrict__ x, int d) {
+  double s = 0.0;
+  for (int c = 0; c < d; ++c) s = fma(dup_weight(c), x[c], s);
+  return s;
+}
+__device__ __forceinline__ double dup_window(const double* __restrict__ x, int d, double eps) {
+  double t = 0.0;
+  for (int c = 0; c < d; ++c) t = fma(dup_weight(c), fabs(x[c]), t);
+  const double reach = 2.0 * sqrt((double)d) * eps;
+  return reach + 4.0 * d * 2.220446049250313e-16 * (t + reach);
+}
 __global__ void first_coord_keys_kernel(const double* __restrict__ X, int64_t n, int d, uint64_t* __restrict__ keys,
                                         uint32_t* __restrict__ idx) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    keys[i] = f64_to_ordered(X[i * d]);
+    keys[i] = f64_to_ordered(dup_projection(X + i * d, d));
     idx[i] = (uint32_t)i;
   }
 }
 // two-set form, MOEA.get_duplicates(X, Y) (MOEA.py:426-437 as MOASMO.py:442 calls it): row i of X is a duplicate when
 // some row j < i of Y lies within eps (cdist(X, Y) with the upper triangle INCLUDING the diagonal masked).  X and Y
-// rows share one sorted order on the first coordinate; ids >= n are rows of Y.
+// rows share one sorted order on the projection; ids >= n are rows of Y.
 __global__ void pair_keys_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Y, int64_t ny, int d,
                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n + ny) return;
-  keys[i] = f64_to_ordered(i < n ? X[i * d] : Y[(i - n) * d]);
+  keys[i] = f64_to_ordered(dup_projection(i < n ? X + i * d : Y + (i - n) * d, d));
   idx[i] = (uint32_t)i;
 }
 
@@ -221,10 +237,11 @@ __global__ void duplicates_pair_kernel(const double* __restrict__ X, int64_t n, 
   if (i >= n) return;  // a row of Y: only probed, never flagged
   const double x0 = ordered_to_f64(skeys[p]);
   const double* xi = X + (int64_t)i * d;
+  const double win = dup_window(xi, d, eps);
   bool dup = false;
   for (int dir = -1; dir <= 1 && !dup; dir += 2) {
     for (int64_t q = p + dir; q >= 0 && q < n + ny; q += dir) {
-      if (fabs(ordered_to_f64(skeys[q]) - x0) > eps) break;
+      if (fabs(ordered_to_f64(skeys[q]) - x0) > win) break;
       const uint32_t jx = sidx[q];
       if (jx < n) continue;              // another row of X
       const uint32_t j = jx - (uint32_t)n;
@@ -252,11 +269,12 @@ __global__ void duplicates_kernel(const double* __restrict__ X, const uint64_t* 
   const uint32_t i = sidx[p];
   const double x0 = ordered_to_f64(skeys[p]);
   const double* xi = X + (int64_t)i * d;
+  const double win = dup_window(xi, d, eps);
   bool dup = false;
   for (int dir = -1; dir <= 1 && !dup; dir += 2) {
     for (int64_t q = p + dir; q >= 0 && q < n; q += dir) {
       double dx0 = ordered_to_f64(skeys[q]) - x0;
-      if (fabs(dx0) > eps) break;
+      if (fabs(dx0) > win) break;
       const uint32_t jx = sidx[q];
       if (jx >= i) continue;  // only earlier rows make a row a duplicate (lower triangle, MOEA.py:430)
       const double* xj = X + (int64_t)jx * d;

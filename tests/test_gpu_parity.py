@@ -786,6 +786,28 @@ def test_duplicates(L):
     Y[:50] = X[1000:1050]   # j < i: duplicates
     Y[2900:2950] = X[10:60]  # j > i: masked
     assert np.array_equal(L.get_duplicates(X, Y=Y), moea.get_duplicates(X, Y=Y))
+    # a finite eps with rows just inside / just outside, mixed signs, and half of the rows sharing their first coordinate
+    # exactly (offspring clipped to a bound): the sort key is a projection of the whole row, not one coordinate
+    Z = rng.standard_normal((4000, 10))
+    Z[:, 0] = np.where(rng.random(4000) < 0.5, 0.0, Z[:, 0])
+    u = rng.standard_normal((200, 10))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    Z[3000:3100] = Z[100:200] + 0.9e-6 * u[:100]
+    Z[3100:3200] = Z[200:300] + 1.1e-6 * u[100:]
+    want = moea.get_duplicates(Z, eps=1e-6)
+    assert want[3000:3100].all() and not want[3100:3200].any()
+    assert np.array_equal(L.get_duplicates(Z, eps=1e-6), want)
+    assert np.array_equal(L.get_duplicates(Z[2000:], eps=1e-6, Y=Z[:2000]), moea.get_duplicates(Z[2000:], eps=1e-6, Y=Z[:2000]))
+    # 65 536 rows clipped to the lower bound in one coordinate: still milliseconds
+    import time
+
+    B = rng.random((65536, 30))
+    B[:, 0] = 0.0
+    L.get_duplicates(B[:1024])
+    t0 = time.perf_counter()
+    dupB = L.get_duplicates(B)
+    dt = time.perf_counter() - t0
+    assert not dupB.any() and dt < 0.05, dt
 
 
 # ------------------------------------------------------------------------------------------ plugins on the real library
