@@ -22,7 +22,7 @@ def main():
     pop, d, M, N = 65536, 30, 3, 4096
     L.context()
     w = bench.workload(pop, d, M, N)
-    sm = b2.GPR_Matern(w["Xtr"], w["Ytr"], d, M, w["xlb"], w["xub"], optimizer=None, precision="tensor")
+    sm = b2.GPR_Matern(w["Xtr"], w["Ytr"], d, M, w["xlb"], w["xub"], optimizer=None)  # precision = auto (the plugin default)
     mdl = b2.Model(objective=sm)
     y0 = sm.evaluate(w["X0"]).astype(np.float32)
     ref = y0.max(axis=0).astype(np.float64) + 0.1 * (y0.max(axis=0) - y0.min(axis=0))

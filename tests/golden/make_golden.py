@@ -630,6 +630,92 @@ def gen_plugins(rng):
     save("plugins", **out)
 
 
+def gen_adaptive(rng):
+    """The adaptive helpers of the optimizers (host control logic, off the hot path, but part of the plugin contract):
+    update_population_size of NSGA2 / AGEMOEA / SMPSO / CMAES / TRS and update_operator_rates of NSGA2 / SMPSO on crafted
+    states that reach every branch (few / many first-front members, small / large crowding spread, low / high success)."""
+    from dmosopt import TRS
+
+    out = {}
+    d, M, pop = 6, 2, 60
+    bounds = np.column_stack((np.zeros(d), np.ones(d)))
+
+    def states():
+        """(rank, objectives) pairs: every point on one front / a tiny first front / clustered first front / generic."""
+        t = np.sort(rng.random(pop))
+        yield np.zeros(pop, dtype=int), np.column_stack((t, 1.0 - t))
+        r = np.ones(pop, dtype=int)
+        r[:3] = 0
+        yield r, rng.random((pop, M))
+        r = (np.arange(pop) % 2).astype(int)
+        y = rng.random((pop, M))
+        y[r == 0] = 0.5 + 1e-3 * rng.random((int((r == 0).sum()), M))
+        yield r, y
+        yield rng.integers(0, 4, size=pop), rng.random((pop, M))
+        r = np.zeros(pop, dtype=int)
+        r[pop // 3:] = 1
+        y = rng.random((pop, M)) ** 3
+        yield r, y
+
+    cases = list(states())
+    out["n_cases"] = np.array(len(cases))
+    for k, (r, y) in enumerate(cases):
+        out[f"c{k}_rank"], out[f"c{k}_obj"] = r, y
+    x0 = rng.random((pop, d))
+    y0 = zdt1(x0)
+    for name, cls, kw in (("nsga2", NSGA2.NSGA2, {}), ("age", AGEMOEA.AGEMOEA, {}), ("cma", CMAES.CMAES, {"distance_metric": None}),
+                          ("trs", TRS.TRS, {})):
+        for k, (r, y) in enumerate(cases):
+            opt = cls(popsize=pop, nInput=d, nOutput=M, model=model_mod.Model(), **kw)
+            opt.initialize_strategy(x0.copy(), y0.copy(), bounds, np.random.default_rng(1))
+            st = opt.state
+            st.rank = r.copy()
+            if name == "cma":
+                st.parents_y = y.copy()
+            else:
+                st.population_obj = y.copy()
+            opt.opt_params.max_population_size, opt.opt_params.min_population_size = 90, 20
+            opt.update_population_size()
+            out[f"{name}_c{k}_popsize"] = np.array(opt.opt_params.popsize)
+    # SMPSO keeps one rank array per swarm
+    for k, (r, y) in enumerate(cases):
+        opt = SMPSO.SMPSO(popsize=pop // 5, nInput=d, nOutput=M, model=model_mod.Model(), distance_metric=None)
+        opt.initialize_strategy(x0.copy(), y0.astype(np.float32), bounds, np.random.default_rng(1))
+        opt.state.ranks = [r[s * (pop // 5):(s + 1) * (pop // 5)].copy() for s in range(5)]
+        opt.state.population_obj = y.copy()
+        opt.opt_params.max_population_size, opt.opt_params.min_population_size = 30, 4
+        opt.update_population_size()
+        out[f"smpso_c{k}_popsize"] = np.array(opt.opt_params.popsize)
+    # operator rates: (successful, total) counters below / inside / above the success band, twice in a row
+    rates = [(0, 50, 1, 40), (10, 50, 8, 40), (40, 50, 30, 40), (0, 0, 0, 0), (50, 50, 0, 40)]
+    out["n_rates"] = np.array(len(rates))
+    for k, (sc, tc, smu, tmu) in enumerate(rates):
+        opt = NSGA2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=model_mod.Model())
+        opt.initialize_strategy(x0.copy(), y0.copy(), bounds, np.random.default_rng(1))
+        rec = []
+        for _ in range(2):
+            st = opt.state
+            st.successful_crossovers, st.total_crossovers, st.successful_mutations, st.total_mutations = sc, tc, smu, tmu
+            opt.update_operator_rates()
+            p = opt.opt_params
+            rec.append(np.concatenate((np.atleast_1d(np.asarray(p.di_crossover, dtype=float)).ravel()[:1], [float(p.crossover_prob)],
+                                       np.atleast_1d(np.asarray(p.di_mutation, dtype=float)).ravel()[:1], [float(p.mutation_prob), float(p.mutation_rate)],
+                                       [st.successful_crossovers, st.total_crossovers, st.successful_mutations, st.total_mutations])))
+        out[f"nsga2_rates{k}"] = np.stack(rec)
+        out[f"nsga2_rates{k}_in"] = np.array([sc, tc, smu, tmu])
+        opt = SMPSO.SMPSO(popsize=pop // 5, nInput=d, nOutput=M, model=model_mod.Model(), distance_metric=None)
+        opt.initialize_strategy(x0.copy(), y0.astype(np.float32), bounds, np.random.default_rng(1))
+        rec = []
+        for _ in range(2):
+            opt.state.successful_children = sc
+            opt.update_operator_rates()
+            p = opt.opt_params
+            rec.append([float(np.atleast_1d(np.asarray(p.di_mutation, dtype=float)).ravel()[0]), float(p.mutation_rate), float(opt.state.successful_children)])
+        out[f"smpso_rates{k}"] = np.array(rec)
+    out["x0"], out["y0"] = x0, y0
+    save("adaptive", **out)
+
+
 def gen_trs(rng):
     """Trust-region search (dmosopt/TRS.py): initialize, then three generate / update rounds driven by one NumPy generator
     (Sobol perturbations come from scipy's sampler seeded by that generator, so the plugin reproduces them exactly), and
@@ -688,7 +774,7 @@ def gen_trs(rng):
 
 
 def main():
-    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes", "plugins", "trs"]
+    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes", "plugins", "trs", "adaptive"]
     gens = {
         "dda": gen_dda,
         "distance": gen_distance,
@@ -705,6 +791,7 @@ def main():
         "cmaes": gen_cmaes,
         "plugins": gen_plugins,
         "trs": gen_trs,
+        "adaptive": gen_adaptive,
     }
     for i, name in enumerate(which):
         gens[name](np.random.default_rng(20260921 + i * 0 + sum(map(ord, name))))

@@ -187,6 +187,60 @@ def test_age_smpso_cmaes_plugins_reproduce_reference(fake):
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "dmosopt")), reason="reference checkout not present")
+def test_adaptive_helpers_reproduce_reference(fake):
+    """update_population_size (NSGA2 / AGEMOEA / SMPSO / CMAES / TRS) and update_operator_rates (NSGA2 / SMPSO) against
+    the reference's own results on crafted states (tests/golden/adaptive.npz): host control logic of the plugin contract."""
+    import dmosopt_b200 as b2
+
+    g = load_golden("adaptive")
+    x0, y0 = g["x0"], g["y0"]
+    pop, d, M = x0.shape[0], x0.shape[1], y0.shape[1]
+    bounds = np.column_stack((np.zeros(d), np.ones(d)))
+    n = int(g["n_cases"])
+    for name, cls, kw in (("nsga2", b2.NSGA2, {}), ("age", b2.AGEMOEA, {}), ("cma", b2.CMAES, {"distance_metric": None}), ("trs", b2.TRS, {})):
+        for k in range(n):
+            opt = cls(popsize=pop, nInput=d, nOutput=M, model=b2.Model(), **kw)
+            opt.initialize_strategy(x0.copy(), y0.copy(), bounds, np.random.default_rng(1))
+            opt.state.rank = g[f"c{k}_rank"].copy()
+            if name == "cma":
+                opt.state.parents_y = g[f"c{k}_obj"].copy()
+            else:
+                opt.state.population_obj = g[f"c{k}_obj"].copy()
+            opt.opt_params.max_population_size, opt.opt_params.min_population_size = 90, 20
+            opt.update_population_size()
+            assert opt.opt_params.popsize == int(g[f"{name}_c{k}_popsize"]), (name, k)
+            if name == "nsga2":
+                assert opt.opt_params.poolsize == int(round(opt.opt_params.popsize / 2.0))
+    for k in range(n):
+        opt = b2.SMPSO(popsize=pop // 5, nInput=d, nOutput=M, model=b2.Model(), distance_metric=None)
+        opt.initialize_strategy(x0.copy(), y0.astype(np.float32), bounds, np.random.default_rng(1))
+        r = g[f"c{k}_rank"]
+        opt.state.ranks = [r[s * (pop // 5) : (s + 1) * (pop // 5)].copy() for s in range(5)]
+        opt.state.population_obj = g[f"c{k}_obj"].copy()
+        opt.opt_params.max_population_size, opt.opt_params.min_population_size = 30, 4
+        opt.update_population_size()
+        assert opt.opt_params.popsize == int(g[f"smpso_c{k}_popsize"]), k
+    first = lambda v: float(np.atleast_1d(np.asarray(v, dtype=float)).ravel()[0])  # noqa: E731
+    for k in range(int(g["n_rates"])):
+        sc, tc, smu, tmu = (int(v) for v in g[f"nsga2_rates{k}_in"])
+        opt = b2.NSGA2(popsize=pop, nInput=d, nOutput=M, model=b2.Model())
+        opt.initialize_strategy(x0.copy(), y0.copy(), bounds, np.random.default_rng(1))
+        for rnd in range(2):
+            st, p = opt.state, opt.opt_params
+            st.successful_crossovers, st.total_crossovers, st.successful_mutations, st.total_mutations = sc, tc, smu, tmu
+            opt.update_operator_rates()
+            got = [first(p.di_crossover), float(p.crossover_prob), first(p.di_mutation), float(p.mutation_prob), float(p.mutation_rate),
+                   st.successful_crossovers, st.total_crossovers, st.successful_mutations, st.total_mutations]
+            np.testing.assert_allclose(got, g[f"nsga2_rates{k}"][rnd], rtol=1e-15, atol=0, err_msg=str((k, rnd)))
+        opt = b2.SMPSO(popsize=pop // 5, nInput=d, nOutput=M, model=b2.Model(), distance_metric=None)
+        opt.initialize_strategy(x0.copy(), y0.astype(np.float32), bounds, np.random.default_rng(1))
+        for rnd in range(2):
+            opt.state.successful_children = sc
+            opt.update_operator_rates()
+            got = [first(opt.opt_params.di_mutation), float(opt.opt_params.mutation_rate), float(opt.state.successful_children)]
+            np.testing.assert_allclose(got, g[f"smpso_rates{k}"][rnd], rtol=1e-15, atol=0, err_msg=str((k, rnd)))
+
+
 def test_plugins_drop_into_unmodified_moasmo_epoch(fake):
     """The reference's own MOASMO.epoch (dmosopt/MOASMO.py:196-470) drives the plugins by import path."""
     sys.path.insert(0, REFERENCE)
