@@ -32,7 +32,7 @@ def euclidean_distance_metric(Y):
     return _lib.euclidean_distance(Y)
 
 
-MAX_OBJECTIVES = 8  # dmo_rank_nd / dmo_crowding_distance (exact hypervolume: 5, _lib.HV_MAX_OBJECTIVES)
+MAX_OBJECTIVES = 8  # dmo_rank_nd / dmo_crowding_distance (exact hypervolume: the same limit, _lib.HV_MAX_OBJECTIVES)
 
 _METRIC_CODES = {None: _lib.METRIC_NONE, "crowding": _lib.METRIC_CROWDING, "euclidean": _lib.METRIC_EUCLIDEAN}
 

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libdmosopt_b200.so")
 METRIC_NONE, METRIC_CROWDING, METRIC_EUCLIDEAN = 0, 1, 2
 KERNEL_MATERN52, KERNEL_RBF = 0, 1
 GP_FP64, GP_TENSOR, GP_AUTO = 0, 1, 2
-HV_MAX_OBJECTIVES = 5  # dmo_hypervolume: exact slicing for M <= 5 (csrc/hv.cu)
+HV_MAX_OBJECTIVES = 8  # dmo_hypervolume: exact, chain sums for M <= 5 (csrc/hv.cu), limit-set recursion for 6 .. 8 (csrc/hv_many.cu)
 
 _c_i64 = ctypes.c_int64
 _c_u64 = ctypes.c_uint64

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libdmosopt_b200.so")
 
-SOURCES = ["ctx.cu", "prims.cu", "rank.cu", "sortmo.cu", "variation.cu", "gp.cu", "gp_fit.cu", "gp_tensor.cu", "hv.cu", "hv3_tree.cu", "moea_ext.cu", "smpso.cu", "benchmarks.cu", "step.cu"]
+SOURCES = ["ctx.cu", "prims.cu", "rank.cu", "sortmo.cu", "variation.cu", "gp.cu", "gp_fit.cu", "gp_tensor.cu", "hv.cu", "hv3_tree.cu", "hv_many.cu", "moea_ext.cu", "smpso.cu", "benchmarks.cu", "step.cu"]
 
 NVCC_FLAGS = [
     "-gencode",

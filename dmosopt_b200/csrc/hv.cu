@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 // hv3_tree.cu: O(n log^2 n) evaluation of the M = 3 slicing identity for large fronts
+int hv_many_device(dmo_ctx* ctx, const double* Fnd, const uint32_t* sidx, int64_t n, int M, const double* dref, double* h_out);
 int hv3_tree_device(dmo_ctx* ctx, const double* xs, const double* ys, const double* zs, const uint32_t* zo, int64_t n, double rx,
                     double ry, double rz, double* partial, int64_t* n_partial);
 
@@ -521,7 +522,7 @@ int hypervolume_device_ranked(dmo_ctx* ctx, const double* dF, int64_t n, int M, 
                               double* h_out) {
   *h_out = 0.0;
   if (n <= 0) return DMO_OK;
-  DMO_REQUIRE(M >= 1 && M <= 5, "hypervolume: M=%d not supported (1..5; >= 10 objectives use Monte-Carlo in the reference)", M);
+  DMO_REQUIRE(M >= 1 && M <= 8, "hypervolume: M=%d not supported (1..8; >= 10 objectives use Monte-Carlo in the reference)", M);
   DevBuf<double> dref;
   DMO_TRY(dref.alloc(ctx, M));
   DMO_CUDA(cudaMemcpyAsync(dref.p, h_ref, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -554,6 +555,12 @@ int hypervolume_device_ranked(dmo_ctx* ctx, const double* dF, int64_t n, int M, 
     if (n2 == 0) return DMO_OK;
   }
   DevBuf<double>& Fnd = d_rank ? Fin : Fnd_own;
+  if (M >= 6 || (M >= 4 && getenv("DMO_HV_WFG") && atoi(getenv("DMO_HV_WFG")))) {
+    // 6 .. 8 objectives: limit-set recursion (hv_many.cu); DMO_HV_WFG=1 sends M = 4, 5 there too (cross-check of the chain sums)
+    DevBuf<uint32_t> sl;
+    DMO_TRY(sort_by_column(ctx, Fnd.p, n2, M, M - 1, sl));
+    return hv_many_device(ctx, Fnd.p, sl.p, n2, M, dref.p, h_out);
+  }
   DevBuf<uint32_t> sx;
   DMO_TRY(sort_by_column(ctx, Fnd.p, n2, M, 0, sx));
   if (M == 2) {

@@ -230,7 +230,9 @@ int dmo_gp_auto_info(dmo_ctx* ctx, dmo_gp* gp, int* mean_tensor, int* var_tensor
  * -> HyperVolumeBoxDecomposition.compute_hypervolume (dmosopt/hv_box_decomposition.py:86-304)
  * and indicators.Hypervolume._do (dmosopt/indicators.py:244-256).  Minimisation; points not
  * strictly inside ref are ignored (hv.py:159).  True hypervolume (see DESIGN.md for the
- * reference's <=0-coordinate defect).  1 <= M <= 5 (M >= 4 is O(n^(M-1))). */
+ * reference's <=0-coordinate defect).  1 <= M <= 8: chain sums for M <= 5 (M >= 4 is
+ * O(n^(M-1))), limit-set recursion for 6 .. 8 objectives (fronts of up to 2048 points; exponential in the worst case, as
+ * every exact algorithm, cheap on the mostly non-dominated fronts an optimizer produces). */
 int dmo_hypervolume(dmo_ctx* ctx, const double* F, int64_t n, int M, const double* ref, double* out);
 /* The same for a set that carries its non-dominated ranks within the superset it was selected from by rank
  * (the survivors of dmo_remove_worst / MOEA.remove_worst, dmosopt/MOEA.py:398-423): rows with rank > 0 are dominated

@@ -391,6 +391,31 @@ def gen_hv(rng):
     save("hv", **out)
 
 
+def gen_hv_many(rng):
+    """Exact hypervolume for 6 .. 8 objectives from the reference's box decomposition (the branch hv.py:160-170 takes for
+    every M < 10): random clouds and DTLZ2-shaped (mostly non-dominated) sets, sized so that the Python reference finishes."""
+    import time
+
+    out = {}
+    k = 0
+    for n, d, shaped in [(14, 6, False), (40, 6, False), (36, 6, True), (30, 7, False), (24, 7, True), (22, 8, False), (18, 8, True),
+                         (200, 6, False), (120, 6, True), (100, 7, True), (150, 7, False), (80, 8, True)]:
+        if shaped:
+            P = dtlz2(rng.random((n, d + 4)), d) + 0.05
+            ref = np.full(d, 1.3)
+        else:
+            P = 0.05 + rng.random((n, d))
+            ref = np.full(d, 1.0 + 0.1 * rng.random())
+        t0 = time.time()
+        out[f"c{k}_P"], out[f"c{k}_ref"] = P, ref
+        out[f"c{k}_hv_box"] = np.array(hvbd.HyperVolumeBoxDecomposition(ref).compute_hypervolume(P))
+        out[f"c{k}_hv_adaptive"] = np.array(hv_mod.AdaptiveHyperVolume(ref).compute_hypervolume(P, algorithm="box"))
+        print(f"  hv_many case {k}: n={n} d={d} shaped={shaped}: {time.time() - t0:.1f} s, hv={float(out[f'c{k}_hv_box']):.6g}", flush=True)
+        k += 1
+    out["ncases"] = np.array(k)
+    save("hv_many", **out)
+
+
 def gen_ehvi(rng):
     out = {}
     k = 0
@@ -774,7 +799,7 @@ def gen_trs(rng):
 
 
 def main():
-    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes", "plugins", "trs", "adaptive"]
+    which = sys.argv[1:] or ["dda", "distance", "sortmo", "variation", "tournament", "duplicates", "gp", "hv", "ehvi", "nsga2", "agemoea", "smpso", "cmaes", "plugins", "trs", "adaptive", "hv_many"]
     gens = {
         "dda": gen_dda,
         "distance": gen_distance,
@@ -792,6 +817,7 @@ def main():
         "plugins": gen_plugins,
         "trs": gen_trs,
         "adaptive": gen_adaptive,
+        "hv_many": gen_hv_many,
     }
     for i, name in enumerate(which):
         gens[name](np.random.default_rng(20260921 + i * 0 + sum(map(ord, name))))

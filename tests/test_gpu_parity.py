@@ -648,16 +648,45 @@ def test_hv_known_answers_and_golden(L):
         assert abs(L.hypervolume(g[f"ka{i}_P"], g[f"ka{i}_ref"]) - float(g[f"ka{i}_expected"])) < 1e-12
     for k in cases(g):
         P, ref = g[f"c{k}_P"], g[f"c{k}_ref"]
-        if P.shape[1] > 5:
-            with pytest.raises(L.DmoError):  # >= 6 objectives: not built (the reference switches to Monte-Carlo at 10)
-                L.hypervolume(P, ref)
-            continue
-        v = L.hypervolume(P, ref)
+        v = L.hypervolume(P, ref)  # the 6-objective case takes the limit-set recursion (hv_many.cu)
         assert abs(v - float(g[f"c{k}_hv_adaptive"])) <= 1e-11 * max(1.0, abs(v)), k  # bar: 1e-5 relative
     assert abs(L.hypervolume(g["quirk_P"], g["quirk_ref"]) - 4.0) < 1e-12  # true HV (reference gives 0)
 
 
-@pytest.mark.parametrize("n,M", [(400, 2), (5000, 2), (150, 3), (350, 3), (40, 4), (160, 4), (30, 5), (70, 5)])
+def test_hv_six_to_eight_objectives_vs_reference(L):
+    """The reference computes every M < 10 exactly (hv.py:160-170); tests/golden/hv_many.npz holds its box-decomposition
+    values for 6, 7 and 8 objectives (random clouds and mostly non-dominated DTLZ2-shaped sets, up to 200 points)."""
+    g = load_golden("hv_many")
+    for k in cases(g):
+        P, ref = g[f"c{k}_P"], g[f"c{k}_ref"]
+        v = L.hypervolume(P, ref)
+        want = float(g[f"c{k}_hv_adaptive"])
+        assert abs(v - want) <= 1e-10 * max(1.0, abs(want)), (k, P.shape, v, want)
+        assert abs(L.hypervolume(P[np.random.default_rng(k).permutation(len(P))], ref) - v) <= 1e-12 * max(1.0, v)
+    with pytest.raises(L.DmoError):  # nine objectives: the rank / filter kernels stop at eight
+        L.hypervolume(np.full((3, 9), 0.5), np.ones(9))
+
+
+@pytest.mark.parametrize("n,M", [(60, 4), (300, 4), (40, 5), (150, 5)])
+def test_hv_limit_set_recursion_equals_the_chain_sums(L, n, M):
+    """DMO_HV_WFG=1 sends M = 4, 5 through hv_many.cu as well: two independent exact algorithms on the same sets."""
+    import os
+
+    rng = np.random.default_rng(n * M)
+    x = rng.random((n, M))
+    P = np.vstack((x / np.linalg.norm(x, axis=1, keepdims=True) * (1 + 0.2 * rng.random((n, 1))), 0.4 + 0.7 * rng.random((n // 3, M))))
+    P[: n // 10] = P[n // 2 : n // 2 + n // 10]
+    ref = np.full(M, 1.15)
+    v = L.hypervolume(P, ref)
+    os.environ["DMO_HV_WFG"] = "1"
+    try:
+        w = L.hypervolume(P, ref)
+    finally:
+        del os.environ["DMO_HV_WFG"]
+    assert abs(v - w) <= 1e-12 * v, (v, w)
+
+
+@pytest.mark.parametrize("n,M", [(400, 2), (5000, 2), (150, 3), (350, 3), (40, 4), (160, 4), (30, 5), (70, 5), (30, 6), (22, 7)])
 def test_hv_random_vs_oracle(L, n, M):
     rng = np.random.default_rng(n + M)
     x = rng.random((n, M))
