@@ -747,7 +747,8 @@ __global__ void pad_calpha_f32_kernel(const double* __restrict__ alpha, const do
   CAf[t] = n < N ? (float)(constant[m] * alpha[(int64_t)m * N + n]) : 0.f;
 }
 
-template <bool ISO, int MT>
+// NJ: groups of four input dimensions that are evaluated (the tile always carries KM_D = 32 zero-padded coordinates)
+template <bool ISO, int MT, int NJ>
 __global__ void __launch_bounds__(KM_T, 4)
     gp_mean_direct_kernel(const double* __restrict__ Xn, int64_t P, int64_t p_base, const float* __restrict__ Xtf, int64_t N,
                           int64_t Npad, int64_t n_per_block, int d, int kind, const double* __restrict__ inv_ls,
@@ -758,11 +759,11 @@ __global__ void __launch_bounds__(KM_T, 4)
   __shared__ __align__(16) float s_il[MT * KM_D];
   const int t = threadIdx.x;
   const int64_t qa = (int64_t)blockIdx.y * KM_Q + t, qb = qa + KM_T;  // candidate rows inside this chunk
-  float2 ca[KM_D / 2], cb[KM_D / 2];
+  float2 ca[2 * NJ], cb[2 * NJ];
   {
     const int64_t pa = p_base + qa, pb = p_base + qb;
 #pragma unroll
-    for (int j = 0; j < KM_D / 2; ++j) {
+    for (int j = 0; j < 2 * NJ; ++j) {
       const int j0 = 2 * j, j1 = 2 * j + 1;
       ca[j] = make_float2((pa < P && j0 < d) ? (float)Xn[pa * d + j0] : 0.f, (pa < P && j1 < d) ? (float)Xn[pa * d + j1] : 0.f);
       cb[j] = make_float2((pb < P && j0 < d) ? (float)Xn[pb * d + j0] : 0.f, (pb < P && j1 < d) ? (float)Xn[pb * d + j1] : 0.f);
@@ -800,7 +801,7 @@ __global__ void __launch_bounds__(KM_T, 4)
         const float4* xr = reinterpret_cast<const float4*>(s_x + i * KM_D);
         float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;  // independent chains
 #pragma unroll
-        for (int j = 0; j < KM_D / 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const float4 c = xr[j];
           const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
           const float2 da0 = __fadd2_rn(c01, make_float2(-ca[2 * j].x, -ca[2 * j].y));
@@ -836,7 +837,7 @@ __global__ void __launch_bounds__(KM_T, 4)
           const float4* xr = reinterpret_cast<const float4*>(s_x + i * KM_D);
           float2 aa = make_float2(0.f, 0.f), bb = aa;
 #pragma unroll
-          for (int j = 0; j < KM_D / 4; ++j) {
+          for (int j = 0; j < NJ; ++j) {
             const float4 c = xr[j], il = il4[j];
             const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
             const float2 i01 = make_float2(il.x, il.y), i23 = make_float2(il.z, il.w);
@@ -1203,9 +1204,15 @@ int gp_mean_direct(dmo_ctx* ctx, dmo_gp* gp, const double* dXn, int64_t P, doubl
   dim3 grid((unsigned)nsplit, (unsigned)n_qb);
   {
     ProfileScope ps_(ctx, "gp_mean_direct");
-#define KM_LAUNCH(ISO_, MT_)                                                                                            \
-  DMO_LAUNCH((gp_mean_direct_kernel<ISO_, MT_>), grid, KM_T, 0, dXn, P, (int64_t)0, gp->Xtf.p, N, Npad, n_per_block, d, \
-             gp->kernel, gp->inv_ls.p, gp->constant.p, gp->alpha.p, mpart.p, ld)
+#define KM_LAUNCH(ISO_, MT_)                                                                                                  \
+  do {                                                                                                                      \
+    if (d <= 16)                                                                                                            \
+      DMO_LAUNCH((gp_mean_direct_kernel<ISO_, MT_, 4>), grid, KM_T, 0, dXn, P, (int64_t)0, gp->Xtf.p, N, Npad, n_per_block, \
+                 d, gp->kernel, gp->inv_ls.p, gp->constant.p, gp->alpha.p, mpart.p, ld);                                    \
+    else                                                                                                                    \
+      DMO_LAUNCH((gp_mean_direct_kernel<ISO_, MT_, 8>), grid, KM_T, 0, dXn, P, (int64_t)0, gp->Xtf.p, N, Npad, n_per_block, \
+                 d, gp->kernel, gp->inv_ls.p, gp->constant.p, gp->alpha.p, mpart.p, ld);                                    \
+  } while (0)
 #define KM_SWITCH(ISO_)        \
   switch (M) {                 \
     case 1: KM_LAUNCH(ISO_, 1); break; \
