@@ -251,6 +251,7 @@ int prim_iota_u32(dmo_ctx* ctx, uint32_t* out, int64_t n);
 // internal device-pointer entry points shared between translation units
 // (all pointers are device pointers; outputs in caller-provided device buffers)
 int rank_nd_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_rank);
+int rank_nd_device_keep(dmo_ctx* ctx, const double* dY, int64_t n, int M, int64_t keep, int32_t* d_rank);
 // 0 for non-dominated rows, non-zero otherwise (no ranks: no dependency chain)
 int nondominated_flags_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_flag01);
 int crowding_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, double* dD);

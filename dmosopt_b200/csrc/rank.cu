@@ -999,9 +999,278 @@ int bits_for(int64_t n) {
   return b;
 }
 
+// ------------------------------------------------------------------------------------------------ front peeling (M == 3)
+// A truncation (remove_worst: keep the best `keep` of n rows) needs the ranks of the kept rows only.  When those rows span
+// few fronts -- a converging population: the bench's merged sets put the best 65 536 of 131 072 points into 7 fronts, a
+// sphere-shaped set into 2 -- peeling them one by one is cheaper than the chain, whose 1024 links are serial whatever the
+// data looks like.  Front k = the points of the remaining set that no remaining point dominates, found with the cell grid
+// of the rank-0 filter above, built once on the dense ids (cells over objectives 2 and 3; inside a cell the records are
+// ordered by their objective-1 id, so the smallest living id of a cell is its first living record):
+//   * per peel: per-cell minimum of the living objective-1 ids, its 2-D prefix minimum, one pass over the living points
+//     (table lookup for the cells strictly below, exact tests along the own cell row and column), then the new front is
+//     marked: rank written, its records in both cell-ordered copies overwritten with an id that dominates nothing;
+//   * the loop stops once `keep` rows are ranked (the others get the next rank: they are truncated away), or gives up
+//     when the fronts turn out to be small (many peels ahead): the chain then runs as if nothing had happened.
+constexpr uint32_t PEEL_DEAD = 0xFFFFFFFFu;
+
+__global__ void peel_key_kernel(const uint32_t* __restrict__ R, int64_t n, int cshift, int gbits, uint32_t* __restrict__ key0,
+                                uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t G1 = (1u << gbits) - 1u;
+  const uint32_t a = min(R[n + i] >> cshift, G1), b = min(R[2 * n + i] >> cshift, G1);
+  key0[i] = R[i];
+  keyA[i] = (a << gbits) | b;
+  keyB[i] = (b << gbits) | a;
+}
+
+// cell-ordered copy (ids of the three objectives, point index) and the slot of every point in it
+__global__ void peel_gather_kernel(const uint32_t* __restrict__ R, const uint32_t* __restrict__ order, int64_t n,
+                                   uint4* __restrict__ crec, uint32_t* __restrict__ slot) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t i = order[t];
+  crec[t] = make_uint4(R[i], R[n + i], R[2 * n + i], i);
+  slot[i] = (uint32_t)t;
+}
+
+// smallest living objective-1 id of every cell (the pointer to a cell's first living record only ever moves forward)
+__global__ void peel_cellmin_kernel(const uint32_t* __restrict__ cstart, const uint4* __restrict__ crec, int ncell,
+                                    uint32_t* __restrict__ first, uint32_t* __restrict__ pm) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  uint32_t f = first[c];
+  const uint32_t e = cstart[c + 1];
+  while (f < e && crec[f].x == PEEL_DEAD) ++f;
+  first[c] = f;
+  pm[c] = f < e ? crec[f].x : PEEL_DEAD;
+}
+
+// in-place inclusive prefix minimum: pass 0 along each row of the G x G table, pass 1 along each column
+__global__ void peel_prefix_min_kernel(uint32_t* __restrict__ pm, int gbits, int pass) {
+  extern __shared__ uint32_t sh_scan[];
+  const int G = 1 << gbits;
+  const int line = blockIdx.x, t = threadIdx.x;
+  const int cell = pass == 0 ? line * G + t : t * G + line;
+  uint32_t v = pm[cell];
+  sh_scan[t] = v;
+  __syncthreads();
+  for (int off = 1; off < G; off <<= 1) {
+    const uint32_t o = t >= off ? sh_scan[t - off] : PEEL_DEAD;
+    __syncthreads();
+    v = min(v, o);
+    sh_scan[t] = v;
+    __syncthreads();
+  }
+  pm[cell] = v;
+}
+
+// dom[i] = 1 iff a living point dominates the living point i
+__global__ void peel_flag_kernel(const uint32_t* __restrict__ R, int64_t n, int cshift, int gbits, const uint32_t* __restrict__ pm,
+                                 const uint32_t* __restrict__ cstartA, const uint32_t* __restrict__ cstartB,
+                                 const uint4* __restrict__ crecA, const uint4* __restrict__ crecB,
+                                 const uint8_t* __restrict__ alive, uint8_t* __restrict__ dom_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !alive[i]) return;
+  const int G = 1 << gbits;
+  const uint32_t c0 = R[i], c1 = R[n + i], c2 = R[2 * n + i];
+  const int a = (int)min(c1 >> cshift, (uint32_t)(G - 1)), b = (int)min(c2 >> cshift, (uint32_t)(G - 1));
+  // cells strictly below in both words hold different vectors: "<=" on the first objective is enough there
+  bool dom = a > 0 && b > 0 && __ldg(pm + (a - 1) * G + (b - 1)) <= c0;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if (dom) break;
+    const uint4* cr = pass == 0 ? crecA : crecB;
+    uint32_t t = pass == 0 ? __ldg(cstartA + a * G) : __ldg(cstartB + b * G);
+    const uint32_t t1 = pass == 0 ? __ldg(cstartA + a * G + b + 1) : __ldg(cstartB + b * G + a);
+    // a dead record carries PEEL_DEAD as its first id and fails the first compare
+#define DMO_PEEL_TEST(q) ((q).x <= c0 && (q).y <= c1 && (q).z <= c2 && !((q).x == c0 && (q).y == c1 && (q).z == c2))
+    for (; t + 4 <= t1 && !dom; t += 4) {
+      const uint4 q0 = __ldg(cr + t), q1 = __ldg(cr + t + 1), q2 = __ldg(cr + t + 2), q3 = __ldg(cr + t + 3);
+      dom = DMO_PEEL_TEST(q0) || DMO_PEEL_TEST(q1) || DMO_PEEL_TEST(q2) || DMO_PEEL_TEST(q3);
+    }
+    for (; t < t1 && !dom; ++t) {
+      const uint4 q0 = __ldg(cr + t);
+      dom = DMO_PEEL_TEST(q0);
+    }
+#undef DMO_PEEL_TEST
+  }
+  dom_out[i] = dom ? 1 : 0;
+}
+
+// the living points nobody dominates form front k: rank, death, count
+__global__ void peel_mark_kernel(int64_t n, uint8_t* __restrict__ alive, const uint8_t* __restrict__ dom, int k,
+                                 int32_t* __restrict__ rank, const uint32_t* __restrict__ slotA, const uint32_t* __restrict__ slotB,
+                                 uint4* __restrict__ crecA, uint4* __restrict__ crecB, unsigned long long* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool mine = false;
+  if (i < n && alive[i] && !dom[i]) {
+    mine = true;
+    rank[i] = k;
+    alive[i] = 0;
+    crecA[slotA[i]].x = PEEL_DEAD;
+    crecB[slotB[i]].x = PEEL_DEAD;
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
+__global__ void peel_rest_kernel(int64_t n, const uint8_t* __restrict__ alive, int k, int32_t* __restrict__ rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && alive[i]) rank[i] = k;
+}
+
+// Is the first front worth peeling?  PEEL_PROBE evenly spaced points are tested against the whole set (every thread brings
+// one point and runs it past the probes in shared memory); a probe that nobody dominates stands for n / PEEL_PROBE points of
+// front 0.  A uniform cloud (front 0 = 0.05 % of the set) almost never passes, a converging population always does.
+constexpr int PEEL_PROBE = 256;
+__global__ void peel_probe_kernel(const uint32_t* __restrict__ R, int64_t n, unsigned* __restrict__ dominated) {
+  __shared__ uint32_t sp[PEEL_PROBE][3];
+  __shared__ unsigned sdom[PEEL_PROBE / 32];
+  const int64_t stride = n / PEEL_PROBE;
+  for (int t = threadIdx.x; t < PEEL_PROBE; t += blockDim.x) {
+    const int64_t i = (int64_t)t * stride + (stride >> 1);
+    sp[t][0] = R[i];
+    sp[t][1] = R[n + i];
+    sp[t][2] = R[2 * n + i];
+  }
+  if (threadIdx.x < PEEL_PROBE / 32) sdom[threadIdx.x] = 0u;
+  __syncthreads();
+  unsigned mine[PEEL_PROBE / 32];
+#pragma unroll
+  for (int w = 0; w < PEEL_PROBE / 32; ++w) mine[w] = 0u;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t a = R[j], b = R[n + j], c = R[2 * n + j];
+#pragma unroll
+    for (int w = 0; w < PEEL_PROBE / 32; ++w) {
+      unsigned m = 0u;
+#pragma unroll 8
+      for (int t = 0; t < 32; ++t) {
+        const uint32_t pa = sp[w * 32 + t][0], pb = sp[w * 32 + t][1], pc = sp[w * 32 + t][2];
+        const bool d = a <= pa && b <= pb && c <= pc && !(a == pa && b == pb && c == pc);
+        m |= d ? (1u << t) : 0u;
+      }
+      mine[w] |= m;
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < PEEL_PROBE / 32; ++w) {
+    const unsigned m = __reduce_or_sync(0xFFFFFFFFu, mine[w]);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(&sdom[w], m);
+  }
+  __syncthreads();
+  if (threadIdx.x < PEEL_PROBE / 32 && sdom[threadIdx.x]) atomicOr(&dominated[threadIdx.x], sdom[threadIdx.x]);
+}
+
+__global__ void fill_u8_kernel(uint8_t* __restrict__ a, int64_t n, uint8_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+// *done = true: d_rank holds exact ranks for (at least) the best `keep` rows, a common larger rank for the rest
+int rank_by_peeling(dmo_ctx* ctx, const uint32_t* R, int64_t n, int64_t keep, int32_t* d_rank, bool* done) {
+  *done = false;
+  int max_peels = 14;  // the chain costs about as much as 20 peels plus the grid
+  if (const char* e = getenv("DMO_RANK_PEEL")) max_peels = atoi(e);
+  if (max_peels <= 0) return DMO_OK;
+  ProfileScope ps(ctx, "rank_peel");
+  {  // probe before building anything: fewer than two undominated probes = a first front below ~1 % of the set
+    DevBuf<unsigned> pd;
+    DMO_TRY(pd.alloc(ctx, PEEL_PROBE / 32));
+    DMO_CUDA(cudaMemsetAsync(pd.p, 0, (PEEL_PROBE / 32) * sizeof(unsigned), ctx->stream));
+    const int gridp = (int)(ceil_div(n, 256) < 2 * (int64_t)ctx->sm_count ? ceil_div(n, 256) : 2 * (int64_t)ctx->sm_count);
+    DMO_LAUNCH(peel_probe_kernel, gridp, 256, 0, R, n, pd.p);
+    DMO_CHECK_LAUNCH();
+    unsigned h[PEEL_PROBE / 32];
+    DMO_CUDA(cudaMemcpyAsync(h, pd.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+    int free_probes = PEEL_PROBE;
+    for (int w = 0; w < PEEL_PROBE / 32; ++w) free_probes -= __builtin_popcount(h[w]);
+    if (free_probes < 2 && !(getenv("DMO_RANK_PEEL_NOPROBE") && atoi(getenv("DMO_RANK_PEEL_NOPROBE")))) return DMO_OK;
+  }
+  const int bits = bits_for(n);
+  int gbits = bits / 2;
+  if (gbits < 4) gbits = 4;
+  if (gbits > 9) gbits = 9;
+  const int G = 1 << gbits, GG = G * G;
+  const int cshift = bits > gbits ? bits - gbits : 0;
+  const unsigned g = (unsigned)ceil_div(n, 256);
+  DevBuf<uint32_t> key0, keyA, keyB, keyS, keyT, ord0, ordS, iota, cstartA, cstartB, firstA, pm, slotA, slotB;
+  DevBuf<uint4> crecA, crecB;
+  DevBuf<uint8_t> alive, dom;
+  DevBuf<unsigned long long> count;
+  DMO_TRY(key0.alloc(ctx, n));
+  DMO_TRY(keyA.alloc(ctx, n));
+  DMO_TRY(keyB.alloc(ctx, n));
+  DMO_TRY(keyS.alloc(ctx, n));
+  DMO_TRY(keyT.alloc(ctx, n));
+  DMO_TRY(ord0.alloc(ctx, n));
+  DMO_TRY(ordS.alloc(ctx, n));
+  DMO_TRY(iota.alloc(ctx, n));
+  DMO_TRY(cstartA.alloc(ctx, GG + 1));
+  DMO_TRY(cstartB.alloc(ctx, GG + 1));
+  DMO_TRY(firstA.alloc(ctx, GG));
+  DMO_TRY(pm.alloc(ctx, GG));
+  DMO_TRY(slotA.alloc(ctx, n));
+  DMO_TRY(slotB.alloc(ctx, n));
+  DMO_TRY(crecA.alloc(ctx, n));
+  DMO_TRY(crecB.alloc(ctx, n));
+  DMO_TRY(alive.alloc(ctx, n));
+  DMO_TRY(dom.alloc(ctx, n));
+  DMO_TRY(count.alloc(ctx, 1));
+  DMO_LAUNCH(peel_key_kernel, g, 256, 0, R, n, cshift, gbits, key0.p, keyA.p, keyB.p);
+  DMO_TRY(prim_iota_u32(ctx, iota.p, n));
+  DMO_TRY(prim_sort_pairs_u32(ctx, key0.p, keyS.p, iota.p, ord0.p, n, 0, bits));  // by objective-1 id ...
+  for (int pass = 0; pass < 2; ++pass) {                                        // ... then stably by cell
+    DMO_LAUNCH(gather_u32_kernel, g, 256, 0, pass == 0 ? keyA.p : keyB.p, ord0.p, n, keyT.p);
+    DMO_TRY(prim_sort_pairs_u32(ctx, keyT.p, keyS.p, ord0.p, ordS.p, n, 0, 2 * gbits));
+    DMO_LAUNCH(peel_gather_kernel, g, 256, 0, R, ordS.p, n, pass == 0 ? crecA.p : crecB.p, pass == 0 ? slotA.p : slotB.p);
+    DMO_LAUNCH(ndg_start_kernel, (unsigned)ceil_div(GG + 1, 256), 256, 0, keyS.p, n, GG, pass == 0 ? cstartA.p : cstartB.p);
+  }
+  DMO_CUDA(cudaMemcpyAsync(firstA.p, cstartA.p, (size_t)GG * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  DMO_LAUNCH(fill_u8_kernel, g, 256, 0, alive.p, n, (uint8_t)1);
+  DMO_CUDA(cudaMemsetAsync(count.p, 0, sizeof(unsigned long long), ctx->stream));
+  unsigned long long ranked = 0, before = 0;
+  double prev_front = 0.0;
+  int k = 0;
+  for (;; ++k) {
+    DMO_LAUNCH(peel_cellmin_kernel, (unsigned)ceil_div(GG, 256), 256, 0, cstartA.p, crecA.p, GG, firstA.p, pm.p);
+    DMO_LAUNCH(peel_prefix_min_kernel, G, G, G * sizeof(uint32_t), pm.p, gbits, 0);
+    DMO_LAUNCH(peel_prefix_min_kernel, G, G, G * sizeof(uint32_t), pm.p, gbits, 1);
+    DMO_LAUNCH(peel_flag_kernel, (unsigned)ceil_div(n, 128), 128, 0, R, n, cshift, gbits, pm.p, cstartA.p, cstartB.p, crecA.p, crecB.p,
+               alive.p, dom.p);
+    DMO_LAUNCH(peel_mark_kernel, g, 256, 0, n, alive.p, dom.p, k, d_rank, slotA.p, slotB.p, crecA.p, crecB.p, count.p);
+    DMO_CHECK_LAUNCH();
+    before = ranked;
+    DMO_CUDA(cudaMemcpyAsync(&ranked, count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    DMO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((int64_t)ranked >= keep || (int64_t)ranked >= n) break;
+    // Give up when many peels are still ahead.  Fronts usually grow over the first few peels (the bench's sets: 2.4 k,
+    // then 5 - 12 k points per front), so the forecast extrapolates the last two front sizes linearly, and the first
+    // front only decides when it is tiny (a uniform cloud: 72 of 131 072 points).
+    const double last = (double)(ranked - before);
+    bool give_up;
+    if (k == 0) {
+      give_up = last * 64.0 < (double)keep;
+    } else {
+      const double rem = (double)(keep - (int64_t)ranked);
+      const double grow = last > prev_front ? last - prev_front : 0.0;
+      const double b = last + 0.5 * grow;
+      const double ahead = grow > 0.0 ? (-b + sqrt(b * b + 2.0 * grow * rem)) / grow : rem / (last > 0.0 ? last : 1.0);
+      give_up = (double)(k + 1) + ahead > (double)max_peels;
+    }
+    if (give_up) return DMO_OK;  // *done stays false: the chain takes over
+    prev_front = last;
+  }
+  DMO_LAUNCH(peel_rest_kernel, g, 256, 0, n, alive.p, k + 1, d_rank);
+  DMO_CHECK_LAUNCH();
+  *done = true;
+  return DMO_OK;
+}
+
 }  // namespace
 
-int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_rank, bool flags_only) {
+int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_rank, bool flags_only, int64_t keep = 0) {
   if (n <= 0) return DMO_OK;
   DMO_REQUIRE(M >= 1 && M <= 8, "rank_nd: M=%d out of range [1,8]", M);
   DMO_REQUIRE(n < ((int64_t)1 << 31) - 4096, "rank_nd: n too large");
@@ -1031,6 +1300,11 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
     DMO_LAUNCH(copy_u32_to_i32_kernel, g, 256, 0, R.p, n, d_rank);
     DMO_CHECK_LAUNCH();
     return DMO_OK;
+  }
+  if (!flags_only && M == 3 && keep > 0 && n >= 8192 && 4 * keep <= 3 * n) {  // truncation: the best `keep` rows are enough
+    bool done = false;
+    DMO_TRY(rank_by_peeling(ctx, R.p, n, keep, d_rank, &done));
+    if (done) return DMO_OK;
   }
 
   // lexicographic order of the id vectors: LSD passes, least significant objective first
@@ -1162,6 +1436,10 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
 
 int rank_nd_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_rank) {
   return rank_nd_device_ex(ctx, dY, n, M, d_rank, false);
+}
+// ranks that are exact for (at least) the `keep` best rows; the other rows share one larger value (see rank_by_peeling)
+int rank_nd_device_keep(dmo_ctx* ctx, const double* dY, int64_t n, int M, int64_t keep, int32_t* d_rank) {
+  return rank_nd_device_ex(ctx, dY, n, M, d_rank, false, keep);
 }
 int nondominated_flags_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t* d_flag01) {
   return rank_nd_device_ex(ctx, dY, n, M, d_flag01, true);

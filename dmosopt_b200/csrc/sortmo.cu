@@ -382,11 +382,16 @@ int lexsort_device(dmo_ctx* ctx, const int32_t* d_rank, const double* const* d_d
 }
 
 // shared body of dmo_order_mo / dmo_remove_worst on device pointers
+// keep > 0: only the first `keep` rows of the order are wanted (remove_worst), so the ranks of the rows behind them need not
+// be told apart (rank_nd_device_keep)
 static int order_mo_device(dmo_ctx* ctx, const double* dY, int64_t n, int M, int metric, const double* const* d_extra,
-                           int n_extra, DevBuf<int32_t>& rank, DevBuf<double>& dist, DevBuf<uint32_t>& perm) {
+                           int n_extra, DevBuf<int32_t>& rank, DevBuf<double>& dist, DevBuf<uint32_t>& perm, int64_t keep = 0) {
   DMO_TRY(rank.alloc(ctx, n));
   DMO_TRY(perm.alloc(ctx, n));
-  DMO_TRY(rank_nd_device(ctx, dY, n, M, rank.p));
+  if (keep > 0 && keep < n)
+    DMO_TRY(rank_nd_device_keep(ctx, dY, n, M, keep, rank.p));
+  else
+    DMO_TRY(rank_nd_device(ctx, dY, n, M, rank.p));
   const double* keys[16];
   int nk = 0;
   for (int k = 0; k < n_extra && nk < 15; ++k) keys[nk++] = d_extra[k];
@@ -492,7 +497,7 @@ int dmo_remove_worst(dmo_ctx* ctx, const double* X, const double* Y, int64_t n, 
   DevBuf<int32_t> rank;
   DevBuf<double> dist;
   DevBuf<uint32_t> p;
-  DMO_TRY(order_mo_device(ctx, y.d, n, M, metric, dex, n_extra, rank, dist, p));
+  DMO_TRY(order_mo_device(ctx, y.d, n, M, metric, dex, n_extra, rank, dist, p, keep));
   Out<double> ox, oy;
   Out<int32_t> orank;
   Out<int64_t> op;
@@ -541,7 +546,7 @@ int dmo_remove_worst_pair(dmo_ctx* ctx, const double* Xa, const double* Ya, int6
   DevBuf<int32_t> rank;
   DevBuf<double> dist;
   DevBuf<uint32_t> p;
-  DMO_TRY(order_mo_device(ctx, y.p, n, M, metric, nullptr, 0, rank, dist, p));
+  DMO_TRY(order_mo_device(ctx, y.p, n, M, metric, nullptr, 0, rank, dist, p, keep));
   Out<double> ox, oy;
   Out<int32_t> orank;
   Out<int64_t> op;

@@ -839,6 +839,71 @@ def test_duplicates(L):
     assert not dupB.any() and dt < 0.05, dt
 
 
+# ------------------------------------------------------------------------------------------ truncation by front peeling
+@pytest.mark.parametrize("kind", ["layers", "sphere", "uniform", "ties", "duplicates", "bench"])
+@pytest.mark.parametrize("n,frac", [(20000, 0.5), (131072, 0.5), (40000, 0.25)])
+def test_remove_worst_front_peeling_equals_the_chain(L, kind, n, frac):
+    """remove_worst with three objectives and n >= 8192 ranks the kept rows by peeling fronts off a cell grid when few
+    fronts are needed, and falls back to the chain otherwise (rank.cu: rank_by_peeling).  Both routes must agree bit for
+    bit -- kept rows, their order and their ranks -- and the ranks must be the full set's ranks (dmo_rank_nd)."""
+    import os
+
+    if kind == "bench" and n != 131072:
+        pytest.skip("one size is enough for the GP-predicted set")
+    rng = np.random.default_rng(n + len(kind))
+    M, d = 3, 4
+    if kind == "layers":  # a handful of thick fronts: shells of a sphere octant
+        x = np.abs(rng.standard_normal((n, M)))
+        Y = x / np.linalg.norm(x, axis=1, keepdims=True) * (1.0 + 0.05 * rng.integers(0, 9, size=(n, 1)) + 1e-4 * rng.random((n, 1)))
+    elif kind == "sphere":
+        x = np.abs(rng.standard_normal((n, M)))
+        Y = x / np.linalg.norm(x, axis=1, keepdims=True)
+    elif kind == "uniform":
+        Y = rng.random((n, M))
+    elif kind == "ties":
+        x = np.abs(rng.standard_normal((n, M)))
+        Y = np.round(x / np.linalg.norm(x, axis=1, keepdims=True) * (1.0 + 0.1 * rng.integers(0, 4, size=(n, 1))), 2)
+    elif kind == "duplicates":
+        x = np.abs(rng.standard_normal((n // 2, M)))
+        h = x / np.linalg.norm(x, axis=1, keepdims=True) * (1.0 + 0.2 * rng.integers(0, 3, size=(n // 2, 1)))
+        Y = np.vstack((h, h))[rng.permutation(2 * (n // 2))]
+        n = Y.shape[0]
+    else:  # the merged objective set of a bench generation: GP-predicted children over float32 parents
+        import bench
+        import dmosopt_b200 as b2
+
+        w = bench.workload(65536, 30, 3, 1024)
+        sm = b2.GPR_Matern(w["Xtr"], w["Ytr"], 30, 3, w["xlb"], w["xub"], optimizer=None)
+        Y = np.vstack((sm.evaluate(rng.random((65536, 30))), sm.evaluate(w["X0"]).astype(np.float32).astype(np.float64)))
+    X = rng.random((n, d))
+    keep = int(n * frac)
+    full = L.rank_nd(Y)
+    for metric in (L.METRIC_NONE, L.METRIC_CROWDING):
+        got = L.remove_worst(X, Y, keep, metric)
+        os.environ["DMO_RANK_PEEL"] = "0"
+        try:
+            ref = L.remove_worst(X, Y, keep, metric)
+        finally:
+            del os.environ["DMO_RANK_PEEL"]
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b), (kind, n, metric)
+        if n <= 40000:  # peeling forced all the way (no probe, no forecast), also where it would never be chosen
+            os.environ["DMO_RANK_PEEL"], os.environ["DMO_RANK_PEEL_NOPROBE"] = "100000", "1"
+            try:
+                forced = L.remove_worst(X, Y, keep, metric)
+            finally:
+                del os.environ["DMO_RANK_PEEL"], os.environ["DMO_RANK_PEEL_NOPROBE"]
+            for a, b in zip(forced, ref):
+                assert np.array_equal(a, b), (kind, n, metric, "forced")
+        assert np.array_equal(got[2], full[got[3]])  # the kept rows carry their ranks in the full set
+        assert got[2].max() <= np.sort(full)[keep - 1]  # nothing better was left behind
+    xa, ya, xb, yb = X[: n // 2], Y[: n // 2], X[n // 2 :], Y[n // 2 :]
+    pair = L.remove_worst_pair(xa, ya, xb, yb, keep, L.METRIC_NONE)
+    one = L.remove_worst(X, Y, keep, L.METRIC_NONE)
+    for a, b in zip(pair, one):
+        assert np.array_equal(np.asarray(a), b), kind
+
+
 # ------------------------------------------------------------------------------------------ plugins on the real library
 def test_nsga2_plugin_golden_sequence_on_gpu(L):
     import dmosopt_b200 as b2
