@@ -807,14 +807,21 @@ __global__ void __launch_bounds__(T) nd_flag_kernel(const uint32_t* __restrict__
 // smaller than its own.  Only the points in the target's own cell row and cell column need the exact test; two
 // cell-ordered copies of the records (row-major and column-major) make both of them contiguous streams.
 // (M == 2 duplicates its single compare word, i.e. only the diagonal cells are populated.)
-__global__ void ndg_key_kernel(const uint32_t* __restrict__ rec, int64_t npad, int M, int cshift, int gbits,
+// cell of a dense id: the ids of an objective run from 0 to maxid (its number of distinct values - 1), which can be far below
+// n (quantised or heavily tied objectives); the shift follows maxid, so the grid stays populated evenly either way
+__device__ __forceinline__ int cell_shift(uint32_t maxid, int gbits) {
+  const int b = 32 - __clz(maxid | 1u);
+  return b > gbits ? b - gbits : 0;
+}
+
+__global__ void ndg_key_kernel(const uint32_t* __restrict__ rec, int64_t npad, int M, const uint32_t* __restrict__ maxid, int gbits,
                                uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB, uint32_t* __restrict__ pos) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npad) return;
   const uint32_t G1 = (1u << gbits) - 1u;
   const uint32_t* w = rec + p * 4;  // W == 4 for M <= 3
-  const uint32_t a = min(w[0] >> cshift, G1);
-  const uint32_t b = (M == 3) ? min(w[1] >> cshift, G1) : a;
+  const uint32_t a = min(w[0] >> cell_shift(maxid[1], gbits), G1);
+  const uint32_t b = (M == 3) ? min(w[1] >> cell_shift(maxid[2], gbits), G1) : a;
   keyA[p] = (a << gbits) | b;
   keyB[p] = (b << gbits) | a;
   pos[p] = (uint32_t)p;
@@ -868,7 +875,7 @@ __global__ void ndg_prefix_min_kernel(const uint32_t* __restrict__ cstartA, cons
   pm[cell] = v;
 }
 
-__global__ void ndg_flag_kernel(const uint32_t* __restrict__ rec, int64_t n, int M, int cshift, int gbits,
+__global__ void ndg_flag_kernel(const uint32_t* __restrict__ rec, int64_t n, int M, const uint32_t* __restrict__ maxid, int gbits,
                                 const uint32_t* __restrict__ pm, const uint32_t* __restrict__ cstartA,
                                 const uint32_t* __restrict__ cstartB, const uint4* __restrict__ crecA,
                                 const uint4* __restrict__ crecB, int* __restrict__ flagS) {
@@ -878,7 +885,8 @@ __global__ void ndg_flag_kernel(const uint32_t* __restrict__ rec, int64_t n, int
   const int G = 1 << gbits;
   const uint4 r = *reinterpret_cast<const uint4*>(rec + p64 * 4);
   const uint32_t c0 = r.x, c1 = (M == 3) ? r.y : r.x, gid = (M == 3) ? r.z : r.y;
-  const int a = (int)min(c0 >> cshift, (uint32_t)(G - 1)), b = (int)min(c1 >> cshift, (uint32_t)(G - 1));
+  const int sh0 = cell_shift(maxid[1], gbits), sh1 = (M == 3) ? cell_shift(maxid[2], gbits) : sh0;
+  const int a = (int)min(c0 >> sh0, (uint32_t)(G - 1)), b = (int)min(c1 >> sh1, (uint32_t)(G - 1));
   bool dom = a > 0 && b > 0 && __ldg(pm + (a - 1) * G + (b - 1)) < p;
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
@@ -903,13 +911,12 @@ __global__ void ndg_flag_kernel(const uint32_t* __restrict__ rec, int64_t n, int
 int bits_for(int64_t n);
 
 // flagS[p] = 1 iff the record at lexicographic position p is dominated (M <= 3, W == 4)
-int nd_flags_grid(dmo_ctx* ctx, const uint32_t* rec, int64_t n, int64_t npad, int M, int* flagS) {
+int nd_flags_grid(dmo_ctx* ctx, const uint32_t* rec, int64_t n, int64_t npad, int M, const uint32_t* maxid, int* flagS) {
   const int bits = bits_for(n);
   int gbits = bits / 2;
   if (gbits < 4) gbits = 4;
   if (gbits > 9) gbits = 9;
   const int G = 1 << gbits, GG = G * G;
-  const int cshift = bits > gbits ? bits - gbits : 0;  // dense ids are < n <= 2^bits
   DevBuf<uint32_t> keyA, keyB, keyS, pos, ord, cstartA, cstartB, pm;
   DevBuf<uint4> crecA, crecB;
   DMO_TRY(keyA.alloc(ctx, npad));
@@ -924,7 +931,7 @@ int nd_flags_grid(dmo_ctx* ctx, const uint32_t* rec, int64_t n, int64_t npad, in
   DMO_TRY(crecB.alloc(ctx, npad));
   const unsigned gp = (unsigned)ceil_div(npad, 256);
   ProfileScope ps(ctx, "nd_flags");
-  DMO_LAUNCH(ndg_key_kernel, gp, 256, 0, rec, npad, M, cshift, gbits, keyA.p, keyB.p, pos.p);
+  DMO_LAUNCH(ndg_key_kernel, gp, 256, 0, rec, npad, M, maxid, gbits, keyA.p, keyB.p, pos.p);
   for (int pass = 0; pass < 2; ++pass) {  // stable sorts: positions stay ascending inside a cell
     DMO_TRY(prim_sort_pairs_u32(ctx, pass == 0 ? keyA.p : keyB.p, keyS.p, pos.p, ord.p, npad, 0, 2 * gbits));
     DMO_LAUNCH(ndg_gather_kernel, gp, 256, 0, rec, ord.p, npad, M, pass == 0 ? crecA.p : crecB.p);
@@ -933,7 +940,7 @@ int nd_flags_grid(dmo_ctx* ctx, const uint32_t* rec, int64_t n, int64_t npad, in
   }
   DMO_LAUNCH(ndg_prefix_min_kernel, G, G, G * sizeof(uint32_t), cstartA.p, crecA.p, gbits, 0, pm.p);
   DMO_LAUNCH(ndg_prefix_min_kernel, G, G, G * sizeof(uint32_t), cstartA.p, crecA.p, gbits, 1, pm.p);
-  DMO_LAUNCH(ndg_flag_kernel, (unsigned)ceil_div(n, 128), 128, 0, rec, n, M, cshift, gbits, pm.p, cstartA.p, cstartB.p,
+  DMO_LAUNCH(ndg_flag_kernel, (unsigned)ceil_div(n, 128), 128, 0, rec, n, M, maxid, gbits, pm.p, cstartA.p, cstartB.p,
              crecA.p, crecB.p, flagS);
   DMO_CHECK_LAUNCH();
   return DMO_OK;
@@ -1013,12 +1020,12 @@ int bits_for(int64_t n) {
 //     when the fronts turn out to be small (many peels ahead): the chain then runs as if nothing had happened.
 constexpr uint32_t PEEL_DEAD = 0xFFFFFFFFu;
 
-__global__ void peel_key_kernel(const uint32_t* __restrict__ R, int64_t n, int cshift, int gbits, uint32_t* __restrict__ key0,
-                                uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB) {
+__global__ void peel_key_kernel(const uint32_t* __restrict__ R, int64_t n, const uint32_t* __restrict__ maxid, int gbits,
+                                uint32_t* __restrict__ key0, uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t G1 = (1u << gbits) - 1u;
-  const uint32_t a = min(R[n + i] >> cshift, G1), b = min(R[2 * n + i] >> cshift, G1);
+  const uint32_t a = min(R[n + i] >> cell_shift(maxid[1], gbits), G1), b = min(R[2 * n + i] >> cell_shift(maxid[2], gbits), G1);
   key0[i] = R[i];
   keyA[i] = (a << gbits) | b;
   keyB[i] = (b << gbits) | a;
@@ -1066,7 +1073,8 @@ __global__ void peel_prefix_min_kernel(uint32_t* __restrict__ pm, int gbits, int
 }
 
 // dom[i] = 1 iff a living point dominates the living point i
-__global__ void peel_flag_kernel(const uint32_t* __restrict__ R, int64_t n, int cshift, int gbits, const uint32_t* __restrict__ pm,
+__global__ void peel_flag_kernel(const uint32_t* __restrict__ R, int64_t n, const uint32_t* __restrict__ maxid, int gbits,
+                                 const uint32_t* __restrict__ pm,
                                  const uint32_t* __restrict__ cstartA, const uint32_t* __restrict__ cstartB,
                                  const uint4* __restrict__ crecA, const uint4* __restrict__ crecB,
                                  const uint8_t* __restrict__ alive, uint8_t* __restrict__ dom_out) {
@@ -1074,7 +1082,8 @@ __global__ void peel_flag_kernel(const uint32_t* __restrict__ R, int64_t n, int 
   if (i >= n || !alive[i]) return;
   const int G = 1 << gbits;
   const uint32_t c0 = R[i], c1 = R[n + i], c2 = R[2 * n + i];
-  const int a = (int)min(c1 >> cshift, (uint32_t)(G - 1)), b = (int)min(c2 >> cshift, (uint32_t)(G - 1));
+  const int a = (int)min(c1 >> cell_shift(maxid[1], gbits), (uint32_t)(G - 1));
+  const int b = (int)min(c2 >> cell_shift(maxid[2], gbits), (uint32_t)(G - 1));
   // cells strictly below in both words hold different vectors: "<=" on the first objective is enough there
   bool dom = a > 0 && b > 0 && __ldg(pm + (a - 1) * G + (b - 1)) <= c0;
 #pragma unroll
@@ -1168,7 +1177,7 @@ __global__ void fill_u8_kernel(uint8_t* __restrict__ a, int64_t n, uint8_t v) {
 }
 
 // *done = true: d_rank holds exact ranks for (at least) the best `keep` rows, a common larger rank for the rest
-int rank_by_peeling(dmo_ctx* ctx, const uint32_t* R, int64_t n, int64_t keep, int32_t* d_rank, bool* done) {
+int rank_by_peeling(dmo_ctx* ctx, const uint32_t* R, const uint32_t* maxid, int64_t n, int64_t keep, int32_t* d_rank, bool* done) {
   *done = false;
   int max_peels = 14;  // the chain costs about as much as 20 peels plus the grid
   if (const char* e = getenv("DMO_RANK_PEEL")) max_peels = atoi(e);
@@ -1193,7 +1202,6 @@ int rank_by_peeling(dmo_ctx* ctx, const uint32_t* R, int64_t n, int64_t keep, in
   if (gbits < 4) gbits = 4;
   if (gbits > 9) gbits = 9;
   const int G = 1 << gbits, GG = G * G;
-  const int cshift = bits > gbits ? bits - gbits : 0;
   const unsigned g = (unsigned)ceil_div(n, 256);
   DevBuf<uint32_t> key0, keyA, keyB, keyS, keyT, ord0, ordS, iota, cstartA, cstartB, firstA, pm, slotA, slotB;
   DevBuf<uint4> crecA, crecB;
@@ -1218,7 +1226,7 @@ int rank_by_peeling(dmo_ctx* ctx, const uint32_t* R, int64_t n, int64_t keep, in
   DMO_TRY(alive.alloc(ctx, n));
   DMO_TRY(dom.alloc(ctx, n));
   DMO_TRY(count.alloc(ctx, 1));
-  DMO_LAUNCH(peel_key_kernel, g, 256, 0, R, n, cshift, gbits, key0.p, keyA.p, keyB.p);
+  DMO_LAUNCH(peel_key_kernel, g, 256, 0, R, n, maxid, gbits, key0.p, keyA.p, keyB.p);
   DMO_TRY(prim_iota_u32(ctx, iota.p, n));
   DMO_TRY(prim_sort_pairs_u32(ctx, key0.p, keyS.p, iota.p, ord0.p, n, 0, bits));  // by objective-1 id ...
   for (int pass = 0; pass < 2; ++pass) {                                        // ... then stably by cell
@@ -1237,7 +1245,7 @@ int rank_by_peeling(dmo_ctx* ctx, const uint32_t* R, int64_t n, int64_t keep, in
     DMO_LAUNCH(peel_cellmin_kernel, (unsigned)ceil_div(GG, 256), 256, 0, cstartA.p, crecA.p, GG, firstA.p, pm.p);
     DMO_LAUNCH(peel_prefix_min_kernel, G, G, G * sizeof(uint32_t), pm.p, gbits, 0);
     DMO_LAUNCH(peel_prefix_min_kernel, G, G, G * sizeof(uint32_t), pm.p, gbits, 1);
-    DMO_LAUNCH(peel_flag_kernel, (unsigned)ceil_div(n, 128), 128, 0, R, n, cshift, gbits, pm.p, cstartA.p, cstartB.p, crecA.p, crecB.p,
+    DMO_LAUNCH(peel_flag_kernel, (unsigned)ceil_div(n, 128), 128, 0, R, n, maxid, gbits, pm.p, cstartA.p, cstartB.p, crecA.p, crecB.p,
                alive.p, dom.p);
     DMO_LAUNCH(peel_mark_kernel, g, 256, 0, n, alive.p, dom.p, k, d_rank, slotA.p, slotB.p, crecA.p, crecB.p, count.p);
     DMO_CHECK_LAUNCH();
@@ -1277,7 +1285,9 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
   const unsigned g = (unsigned)ceil_div(n, 256);
 
   DevBuf<uint32_t> R;  // M x n dense integer ids (SoA)
+  DevBuf<uint32_t> maxid;  // largest id per objective (= number of distinct values - 1)
   DMO_TRY(R.alloc(ctx, (size_t)M * n));
+  DMO_TRY(maxid.alloc(ctx, M));
   {
     DevBuf<uint64_t> k0, k1;
     DevBuf<uint32_t> i0, i1, flag, dense;
@@ -1293,6 +1303,7 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
       DMO_LAUNCH(flag_new_u64_kernel, g, 256, 0, k1.p, n, flag.p);
       DMO_TRY(prim_inclusive_sum_u32(ctx, flag.p, dense.p, n));
       DMO_LAUNCH(scatter_dense_kernel, g, 256, 0, dense.p, i1.p, n, R.p + (size_t)j * n);
+      DMO_CUDA(cudaMemcpyAsync(maxid.p + j, dense.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     DMO_CHECK_LAUNCH();
   }
@@ -1303,7 +1314,7 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
   }
   if (!flags_only && M == 3 && keep > 0 && n >= 8192 && 4 * keep <= 3 * n) {  // truncation: the best `keep` rows are enough
     bool done = false;
-    DMO_TRY(rank_by_peeling(ctx, R.p, n, keep, d_rank, &done));
+    DMO_TRY(rank_by_peeling(ctx, R.p, maxid.p, n, keep, d_rank, &done));
     if (done) return DMO_OK;
   }
 
@@ -1367,7 +1378,7 @@ int rank_nd_device_ex(dmo_ctx* ctx, const double* dY, int64_t n, int M, int32_t*
   int* ticket = sync.p + nblocks;
   int* errflag = sync.p + nblocks + 1;
   if (flags_only && M <= 3 && n >= 8192 && getenv("DMO_ND_BRUTE") == nullptr) {
-    DMO_TRY(nd_flags_grid(ctx, rec.p, n, npad, M, rankS.p));
+    DMO_TRY(nd_flags_grid(ctx, rec.p, n, npad, M, maxid.p, rankS.p));
     DMO_LAUNCH(scatter_rank_kernel, g, 256, 0, rankS.p, perm, n, d_rank);
     DMO_CHECK_LAUNCH();
     return DMO_OK;
