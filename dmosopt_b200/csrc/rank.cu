@@ -1198,8 +1198,9 @@ int rank_by_peeling(dmo_ctx* ctx, const uint32_t* R, const uint32_t* maxid, int6
     if (free_probes < 2 && !(getenv("DMO_RANK_PEEL_NOPROBE") && atoi(getenv("DMO_RANK_PEEL_NOPROBE")))) return DMO_OK;
   }
   const int bits = bits_for(n);
-  int gbits = bits / 2;
+  int gbits = (bits + 1) / 2;  // two cells per point at n = 131 072: measured 0.80 ms per bench step against 0.96 ms with 2^8 cells per axis
   if (gbits < 4) gbits = 4;
+  if (const char* e = getenv("DMO_PEEL_GBITS")) gbits = atoi(e);
   if (gbits > 9) gbits = 9;
   const int G = 1 << gbits, GG = G * G;
   const unsigned g = (unsigned)ceil_div(n, 256);
