@@ -15,8 +15,10 @@
 //     accumulator; four epilogue warps drain TMEM with tcgen05.ld;
 //   * persistent CTAs (one per SM) walk a list of equal-cost work items in an L2-friendly order (version 3, below).
 //
-// K_* itself is produced by kstar_tensor_kernel in fp32 (relative error ~1e-6 on K_*), the mean reduction is
-// accumulated in float64 in a fixed order (deterministic).
+// K_* itself is produced in fp32 (relative error ~1e-6 on K_*) by kstar_mean_kernel, which accumulates the mean from the same
+// kernel values (packed fp32 over 16 training points, then float64, slices added in a fixed order: deterministic);
+// kstar_tensor_kernel + mean_split_kernel are the fallback for shapes that kernel does not take.  Predicts without
+// variance never write K_*: gp_mean_direct_kernel.
 //
 // Accuracy contract of this path: |var - var_ref| <= 1e-5 * prior variance and |mean - mean_ref| <= 1e-5 on
 // well-conditioned posteriors (tests/test_gpu_parity.py); DMO_GP_AUTO (gp.cu) measures both against the float64 path

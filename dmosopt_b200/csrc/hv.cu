@@ -12,7 +12,8 @@
 //          with smaller z.  Every A_k is an independent sweep over the x-sorted points (running min of y among the
 //          points with smaller z), so the whole computation is n independent O(n) scans: thread-per-point, sources
 //          streamed through shared memory in coalesced tiles, no dynamic data structures.
-//   M >= 4: the same slicing identity applied recursively (see hv_slice_kernel), O(n^(M-1)).
+//   M = 4, 5: the same slicing identity applied recursively as chain sums (see hv_slice_kernel), O(n^(M-1)).
+//   M = 6 .. 8: the identity with non-dominated limit sets at every level (hv_many.cu).
 // All arithmetic is float64; block partial sums are combined in a fixed order (deterministic result).
 #include <stdlib.h>
 

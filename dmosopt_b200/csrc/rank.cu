@@ -20,6 +20,8 @@
 //      (no co-residency assumption, no deadlock); every wait is bounded by a watchdog that raises an error flag.
 //
 // Rank-0-only queries (the hypervolume's filter) take the cell-grid kernels `ndg_*` (M <= 3) or a plain block scan.
+// Truncations (remove_worst: only the ranks of the kept rows matter) of three-objective sets peel the fronts they need off
+// the same kind of grid instead of running the chain, when those fronts are few (`rank_by_peeling`, below).
 //
 // Algorithmic bytes: 8 n M read + 4 n written; pair tests <= n^2 / 2 (compare / latency bound).
 #include <stdlib.h>
