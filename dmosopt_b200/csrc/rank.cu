@@ -663,6 +663,11 @@ __global__ void __launch_bounds__(T, SEG ? 4 : 5) rank_chain_kernel(uint32_t* re
           best = may_share_group ? rank_pair_tests<M, W, NV, T, false, true, false>(tb, c1tb, v, gidv, c1v, best)
                                  : rank_pair_tests<M, W, NV, T, false, false, false>(tb, c1tb, v, gidv, c1v, best);
         }
+        // Second barrier of the tile.  The double buffering alone orders the accesses (a buffer is rewritten two tiles
+        // later, after the next tile's barrier, which every reader of this tile has to reach first), but compute-sanitizer's
+        // racecheck reports the read above against the next write of the same buffer as a potential WAR hazard; with this
+        // barrier the tool is clean (profiles/r2_sanitizer.txt) at no measurable cost (the chain is latency bound).
+        __syncthreads();
         k = kn;
         kind = kind_n;
         pb ^= 1;
