@@ -1101,6 +1101,15 @@ __global__ void peel_flag_kernel(const uint32_t* __restrict__ R, int64_t n, cons
     const uint32_t t1 = pass == 0 ? __ldg(cstartA + a * G + b + 1) : __ldg(cstartB + b * G + a);
     // a dead record carries PEEL_DEAD as its first id and fails the first compare
 #define DMO_PEEL_TEST(q) ((q).x <= c0 && (q).y <= c1 && (q).z <= c2 && !((q).x == c0 && (q).y == c1 && (q).z == c2))
+    // the few threads that get here walk hundreds of records: sixteen loads in flight per step (ncu: 9 % of the issue slots
+    // busy with four, the kernel's time is the dependent-load latency of its longest walks)
+    for (; t + 16 <= t1 && !dom; t += 16) {
+      uint4 q[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) q[u] = __ldg(cr + t + u);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) dom = dom || DMO_PEEL_TEST(q[u]);
+    }
     for (; t + 4 <= t1 && !dom; t += 4) {
       const uint4 q0 = __ldg(cr + t), q1 = __ldg(cr + t + 1), q2 = __ldg(cr + t + 2), q3 = __ldg(cr + t + 3);
       dom = DMO_PEEL_TEST(q0) || DMO_PEEL_TEST(q1) || DMO_PEEL_TEST(q2) || DMO_PEEL_TEST(q3);
