@@ -45,9 +45,17 @@ _worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="dmosopt_b200_cma
 
 
 def _stable_order(rank):
-    """np.argsort(rank, kind="stable"); 16-bit keys take NumPy's radix sort (ranks are small non-negative integers)."""
-    if rank.size and 0 <= int(rank.min()) and int(rank.max()) < 65536:
+    """np.argsort(rank, kind="stable") for non-negative integers: NumPy sorts 16-bit keys with a radix sort, so one or two
+    16-bit passes (least significant half first) beat its merge sort on 64-bit keys by 3x at the sizes of this plugin."""
+    rank = np.asarray(rank)
+    if rank.size == 0 or int(rank.min()) < 0:
+        return np.argsort(rank, kind="stable")
+    top = int(rank.max())
+    if top < 65536:
         return np.argsort(rank.astype(np.uint16), kind="stable")
+    if top < (1 << 32):
+        low = np.argsort((rank & 0xFFFF).astype(np.uint16), kind="stable")
+        return low[np.argsort((rank[low] >> 16).astype(np.uint16), kind="stable")]
     return np.argsort(rank, kind="stable")
 
 
@@ -215,7 +223,7 @@ class CMAES(MOEA):
         ev_parent = np.concatenate((par, pidx[nc_off]))
         ev_success = np.concatenate((np.ones(len(par), dtype=bool), np.zeros(len(nc_off), dtype=bool)))
         if len(ev_parent) > 0:
-            order = np.argsort(ev_parent, kind="stable")
+            order = _stable_order(ev_parent)
             ep, es = ev_parent[order], ev_success[order]
             first = np.r_[True, ep[1:] != ep[:-1]]
             seg_start = np.flatnonzero(first)
